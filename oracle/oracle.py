@@ -1,0 +1,164 @@
+"""ctypes front-end of the CPU oracle (oracle/spi_oracle.hpp).
+
+TEST INFRASTRUCTURE — only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` legs import this module.  The product package (spi_active_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "_build" / "libspi_oracle.so"
+_lib = None
+
+
+def build(force: bool = False) -> Path:
+    src_m = max((_HERE / f).stat().st_mtime for f in ("spi_oracle_capi.cpp", "spi_oracle.hpp"))
+    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src_m:
+        env = dict(os.environ)
+        env.pop("CXX", None)
+        subprocess.run(["make", "-C", str(_HERE), "CXX=g++"], check=True, env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            build()
+        _lib = C.CDLL(str(_LIB_PATH))
+    return _lib
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a, ty=C.c_float):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ty))
+
+
+def eval_candidates(blob, params, param_ids, seg_init, seg_actions, seg_target, seg_gains=None, seg_mask=None,
+                    decimation=4, motor_model=0, flags=0, cost_denominator=0.0, precision=64, n_threads=0,
+                    return_per_seg=False):
+    """-> cost[C,3] float64, status[C] int32 (, per_seg[C,S,3])"""
+    blob = _f32(blob); params = _f32(params); seg_init = _f32(seg_init)
+    seg_actions = _f32(seg_actions); seg_target = _f32(seg_target); seg_gains = _f32(seg_gains)
+    ids = np.ascontiguousarray(param_ids, dtype=np.int32)
+    Cn, P = params.shape
+    S, H = seg_actions.shape[0], seg_actions.shape[1]
+    mask = None if seg_mask is None else np.ascontiguousarray(seg_mask, dtype=np.uint8)
+    cost = np.zeros((Cn, 3), dtype=np.float64)
+    per = np.zeros((Cn, S, 3), dtype=np.float64) if return_per_seg else None
+    status = np.zeros(Cn, dtype=np.int32)
+    rc = lib().spi_oracle_eval_candidates(
+        C.c_int(precision), _ptr(blob), C.c_int(blob.size), _ptr(params), C.c_int(Cn), C.c_int(P),
+        _ptr(ids, C.c_int), _ptr(seg_init), _ptr(seg_actions), _ptr(seg_target), _ptr(seg_gains),
+        _ptr(mask, C.c_ubyte), C.c_int(S), C.c_int(H), C.c_int(decimation), C.c_int(motor_model),
+        C.c_uint(flags), C.c_float(cost_denominator), _ptr(cost, C.c_double), _ptr(per, C.c_double),
+        _ptr(status, C.c_int), C.c_int(n_threads))
+    if rc != 0:
+        raise RuntimeError(f"spi_oracle_eval_candidates failed: {rc}")
+    return (cost, status, per) if return_per_seg else (cost, status)
+
+
+def rollout_states(blob, params, param_ids, seg_init, seg_actions, seg_gains=None, decimation=4, motor_model=0,
+                   flags=0, precision=64):
+    """-> states[C,S,H,37] float64"""
+    blob = _f32(blob); params = _f32(params); seg_init = _f32(seg_init)
+    seg_actions = _f32(seg_actions); seg_gains = _f32(seg_gains)
+    ids = np.ascontiguousarray(param_ids, dtype=np.int32)
+    Cn, P = params.shape
+    S, H = seg_actions.shape[0], seg_actions.shape[1]
+    out = np.zeros((Cn, S, H, 37), dtype=np.float64)
+    rc = lib().spi_oracle_rollout_states(
+        C.c_int(precision), _ptr(blob), C.c_int(blob.size), _ptr(params), C.c_int(Cn), C.c_int(P),
+        _ptr(ids, C.c_int), _ptr(seg_init), _ptr(seg_actions), _ptr(seg_gains), C.c_int(S), C.c_int(H),
+        C.c_int(decimation), C.c_int(motor_model), C.c_uint(flags), _ptr(out, C.c_double))
+    if rc != 0:
+        raise RuntimeError(f"spi_oracle_rollout_states failed: {rc}")
+    return out
+
+
+def sim_step(blob, state, torques, n_steps=1, params=None, param_ids=None, flags=0, return_foot_force=False):
+    """state[N,37] float64 (copied), torques[N,12] -> new state (, foot_force[N,4,3])"""
+    blob = _f32(blob)
+    state = np.array(state, dtype=np.float64, order="C").reshape(-1, 37)
+    torques = np.ascontiguousarray(torques, dtype=np.float64).reshape(-1, 12)
+    N = state.shape[0]
+    P = 0
+    ids = np.zeros(1, dtype=np.int32)
+    if params is not None:
+        params = _f32(params).reshape(N, -1)
+        P = params.shape[1]
+        ids = np.ascontiguousarray(param_ids, dtype=np.int32)
+    ff = np.zeros((N, 4, 3), dtype=np.float64)
+    rc = lib().spi_oracle_sim_step(_ptr(blob), C.c_int(blob.size), _ptr(params), C.c_int(P), _ptr(ids, C.c_int),
+                                   C.c_uint(flags), _ptr(state, C.c_double), _ptr(torques, C.c_double),
+                                   C.c_int(N), C.c_int(n_steps), _ptr(ff, C.c_double))
+    if rc != 0:
+        raise RuntimeError(f"spi_oracle_sim_step failed: {rc}")
+    return (state, ff) if return_foot_force else state
+
+
+def forward_dynamics(blob, state, tau, params=None, param_ids=None, flags=0, with_contact=True, with_gravity=True):
+    """-> base spatial accel in base coords [ang3, lin3], qdd[12], foot_force[4,3]"""
+    blob = _f32(blob)
+    state = np.ascontiguousarray(state, dtype=np.float64).reshape(37)
+    tau = np.ascontiguousarray(tau, dtype=np.float64).reshape(12)
+    P = 0
+    ids = np.zeros(1, dtype=np.int32)
+    if params is not None:
+        params = _f32(params).reshape(-1)
+        P = params.size
+        ids = np.ascontiguousarray(param_ids, dtype=np.int32)
+    acc = np.zeros(6); qdd = np.zeros(12); foot = np.zeros((4, 3))
+    rc = lib().spi_oracle_forward_dynamics(_ptr(blob), C.c_int(blob.size), _ptr(params), C.c_int(P),
+                                           _ptr(ids, C.c_int), C.c_uint(flags), _ptr(state, C.c_double),
+                                           _ptr(tau, C.c_double), C.c_int(int(with_contact)),
+                                           C.c_int(int(with_gravity)), _ptr(acc, C.c_double),
+                                           _ptr(qdd, C.c_double), _ptr(foot, C.c_double))
+    if rc != 0:
+        raise RuntimeError(f"spi_oracle_forward_dynamics failed: {rc}")
+    return acc, qdd, foot
+
+
+def compute_torques(blob, actions, q, qd, gains=None, motor_params=None, motor_model=0, flags=0, precision=64):
+    blob = _f32(blob); actions = _f32(actions).reshape(-1, 12); q = _f32(q).reshape(-1, 12)
+    qd = _f32(qd).reshape(-1, 12); gains = _f32(gains); motor_params = _f32(motor_params)
+    N = actions.shape[0]
+    out = np.zeros((N, 12), dtype=np.float64)
+    rc = lib().spi_oracle_compute_torques(C.c_int(precision), _ptr(blob), C.c_int(blob.size), _ptr(actions), _ptr(q),
+                                          _ptr(qd), _ptr(gains), _ptr(motor_params), C.c_int(N),
+                                          C.c_int(motor_model), C.c_uint(flags), _ptr(out, C.c_double))
+    if rc != 0:
+        raise RuntimeError(f"spi_oracle_compute_torques failed: {rc}")
+    return out
+
+
+def count_flops(blob, params, param_ids, init, actions, target, decimation=4, motor_model=0, flags=0):
+    """op counts of one (candidate, segment) rollout -> dict"""
+    blob = _f32(blob); params = _f32(params).reshape(-1); init = _f32(init).reshape(37)
+    actions = _f32(actions).reshape(-1, 12); target = _f32(target).reshape(19)
+    ids = np.ascontiguousarray(param_ids, dtype=np.int32)
+    out = np.zeros(6, dtype=np.uint64)
+    rc = lib().spi_oracle_count_flops(_ptr(blob), C.c_int(blob.size), _ptr(params), C.c_int(params.size),
+                                      _ptr(ids, C.c_int), _ptr(init), _ptr(actions), _ptr(target),
+                                      C.c_int(actions.shape[0]), C.c_int(decimation), C.c_int(motor_model),
+                                      C.c_uint(flags), _ptr(out, C.c_ulonglong))
+    if rc != 0:
+        raise RuntimeError(f"spi_oracle_count_flops failed: {rc}")
+    names = ("add", "mul", "div", "sqrt", "transcendental", "compare")
+    d = {k: int(v) for k, v in zip(names, out)}
+    d["total"] = int(out.sum())
+    return d
+
+
+def num_threads() -> int:
+    return int(lib().spi_oracle_num_threads())

@@ -1,0 +1,106 @@
+"""Loader of the in-tree CUDA library libspi_b200.so (C-ABI of include/spi_b200.h).
+
+There is no CPU fallback: if the library is missing or cannot be loaded, every product entry point
+raises.  `build()` compiles it with nvcc for sm_100a (used by __graft_entry__.build()).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libspi_b200.so"
+SOURCES = [_PKG / "csrc" / "spi_b200.cu"]
+HEADERS = [_PKG / "csrc" / "aba_leg.cuh", _PKG.parent / "include" / "spi_b200.h"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
+
+_lib = None
+
+
+class SpiB200Error(RuntimeError):
+    pass
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise SpiB200Error("nvcc not found; cannot build libspi_b200.so")
+
+
+def needs_build() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    newest = max(p.stat().st_mtime for p in SOURCES + HEADERS)
+    return LIB_PATH.stat().st_mtime < newest
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB_PATH
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB_PATH), *map(str, SOURCES)]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose:
+        print(" ".join(cmd)); print(res.stdout)
+    if res.returncode != 0:
+        raise SpiB200Error(f"nvcc failed:\n{res.stdout}")
+    return LIB_PATH
+
+
+_F = C.POINTER(C.c_float)
+_I = C.POINTER(C.c_int)
+_U8 = C.POINTER(C.c_ubyte)
+_V = C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/spi_b200.h declares
+SIGNATURES = {
+    "spi_b200_version": (C.c_int, []),
+    "spi_b200_last_error": (C.c_char_p, []),
+    "spi_b200_launch_count": (C.c_longlong, []),
+    "spi_b200_model_create": (C.c_int, [_F, C.c_int, C.POINTER(_V)]),
+    "spi_b200_model_destroy": (C.c_int, [_V]),
+    "spi_b200_eval_candidates": (C.c_int, [_V, _V, C.c_int, C.c_int, _I, _V, _V, _V, _V, _V, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, C.c_uint, C.c_float, _V, _V, _V, _V]),
+    "spi_b200_eval_candidates_host": (C.c_int, [_V, _F, C.c_int, C.c_int, _I, _F, _F, _F, _F, _U8, C.c_int,
+                                                C.c_int, C.c_int, C.c_int, C.c_uint, C.c_float, _F, _I, _V]),
+    "spi_b200_rollout_states": (C.c_int, [_V, _V, C.c_int, C.c_int, _I, _V, _V, _V, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_uint, _V, _V]),
+    "spi_b200_sim_step": (C.c_int, [_V, _V, C.c_int, _I, C.c_uint, _V, _V, C.c_int, C.c_int, _V, _V]),
+    "spi_b200_compute_torques": (C.c_int, [_V, _V, _V, _V, _V, _V, C.c_int, C.c_int, C.c_uint, _V, _V]),
+    "spi_b200_fim_reward": (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_float, C.c_int, _V, _V, _V]),
+    "spi_b200_cem_refit": (C.c_int, [_V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_float, _V, _V, _V, _V, _V]),
+    "spi_b200_cem_sample": (C.c_int, [_V, _V, _V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_int,
+                                      _V, _V]),
+    "spi_b200_weighted_cost": (C.c_int, [_V, _V, C.c_int, C.c_float, C.c_float, C.c_float, _V, _V]),
+    "spi_b200_fp32_peak": (C.c_int, [C.c_int, _F, _F, _V]),
+}
+
+
+def lib():
+    """The loaded library; raises SpiB200Error (never falls back) if it is not there."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise SpiB200Error(
+                f"{LIB_PATH} is missing — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback for the rollout engine)")
+        try:
+            handle = C.CDLL(str(LIB_PATH))
+        except OSError as e:  # pragma: no cover
+            raise SpiB200Error(f"cannot load {LIB_PATH}: {e}") from e
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().spi_b200_last_error()
+        raise SpiB200Error(f"{what} failed ({rc}): {msg.decode() if msg else ''}")

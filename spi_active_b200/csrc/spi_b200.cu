@@ -1,0 +1,757 @@
+// spi_b200.cu — kernels + C-ABI of libspi_b200.so (see include/spi_b200.h for the contract and the
+// reference call sites each entry point replaces).  sm_100a only; no torch types; no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "aba_leg.cuh"
+
+using namespace spi;
+
+// ================================================================================================
+// kernels
+// ================================================================================================
+namespace {
+
+constexpr int kThreads = 128;           // 4 warps = 32 rollouts per CTA
+constexpr int kRolloutsPerCta = kThreads / 4;
+constexpr int kRolloutsPerWarp = 8;
+
+struct EvalArgs {
+  const DeviceModel* model;
+  const float* params; int C, P; ParamIds ids;
+  const float* seg_init; const float* seg_actions; const float* seg_target; const float* seg_gains;
+  const unsigned char* seg_mask;
+  int S, H, decimation, motor_model; unsigned flags;
+  int n_cta_per_cand, n_warp_per_cand;
+  float* partial;      // [C][n_warp_per_cand][3]
+  float* per_seg;      // [C][S][3] or null
+  int* bad;            // [C]
+  float* out_states;   // [C][S][H][37] (RECORD)
+};
+
+SPI_DEV void load_leg_const(const DeviceModel& M, int leg, LegConst& L) {
+  const LegConst& G = M.leg[leg];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    L.m[j] = G.m[j];
+    L.qdef[j] = G.qdef[j];
+    L.tlim[j] = G.tlim[j];
+    L.foot[j] = G.foot[j];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { L.h[j][k] = G.h[j][k]; L.r[j][k] = G.r[j][k]; }
+#pragma unroll
+    for (int k = 0; k < 6; k++) L.Io[j][k] = G.Io[j][k];
+  }
+}
+
+SPI_DEV void load_lane_state(const float* row, int leg, LaneState& s) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) { s.p[i] = __ldg(row + i); s.v[i] = __ldg(row + 7 + i); s.w[i] = __ldg(row + 10 + i); }
+#pragma unroll
+  for (int i = 0; i < 4; i++) s.quat[i] = __ldg(row + 3 + i);
+#pragma unroll
+  for (int j = 0; j < 3; j++) { s.q[j] = __ldg(row + 13 + 3 * leg + j); s.qd[j] = __ldg(row + 25 + 3 * leg + j); }
+}
+
+SPI_DEV void store_lane_state(float* row, int leg, const LaneState& s) {
+  if (leg == 0) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) { row[i] = s.p[i]; row[7 + i] = s.v[i]; row[10 + i] = s.w[i]; }
+#pragma unroll
+    for (int i = 0; i < 4; i++) row[3 + i] = s.quat[i];
+  }
+#pragma unroll
+  for (int j = 0; j < 3; j++) { row[13 + 3 * leg + j] = s.q[j]; row[25 + 3 * leg + j] = s.qd[j]; }
+}
+
+SPI_DEV bool lane_finite(const LaneState& s) {
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) acc += s.p[i] * 0.f + s.v[i] * 0.f + s.w[i] * 0.f + s.q[i] * 0.f + s.qd[i] * 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; i++) acc += s.quat[i] * 0.f;
+  return acc == 0.f;  // NaN/Inf * 0 = NaN
+}
+
+// The fused hot path: reset -> H x (clip, decimation x (PD + motor model, nsub x ABA sub-step)) -> errors
+// -> per-warp masked partial sums.  4 lanes per (candidate, segment) rollout.
+template <bool RECORD>
+__global__ void __launch_bounds__(kThreads) rollout_kernel(const EvalArgs A) {
+  const DeviceModel& M = *A.model;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int leg = lane & 3;
+  const int c = blockIdx.x / A.n_cta_per_cand;
+  const int cta_in_cand = blockIdx.x - c * A.n_cta_per_cand;
+  const int seg_raw = cta_in_cand * kRolloutsPerCta + (threadIdx.x >> 2);
+  const bool active = seg_raw < A.S;
+  const int seg = active ? seg_raw : A.S - 1;
+
+  SimConst S = M.sim;
+  LegConst L;
+  load_leg_const(M, leg, L);
+  BaseInertia B;
+  float motor[3];
+  {
+    float motor_all[3];
+    apply_candidate(M, A.params ? A.params + (size_t)c * A.P : nullptr, A.ids, A.flags, B, motor_all);
+    // act2tau_scalar uses one gain for every joint; vec3 variants are per joint group = per joint of the leg
+    motor[0] = motor_all[0]; motor[1] = motor_all[1]; motor[2] = motor_all[2];
+    if (A.motor_model == SPI_MOTOR_SCALAR) { motor[1] = motor_all[0]; motor[2] = motor_all[0]; }
+  }
+  LaneState s;
+  load_lane_state(A.seg_init + (size_t)seg * SPI_STATE_DIM, leg, s);
+  float kp[3], kd[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    kp[j] = A.seg_gains ? __ldg(A.seg_gains + (size_t)seg * 24 + 3 * leg + j) : M.kp[3 * leg + j];
+    kd[j] = A.seg_gains ? __ldg(A.seg_gains + (size_t)seg * 24 + 12 + 3 * leg + j) : M.kd[3 * leg + j];
+  }
+  const float h = S.dt / (float)S.nsub;
+  const float* act_row = A.seg_actions + (size_t)seg * A.H * 12 + 3 * leg;
+  for (int k = 0; k < A.H; k++) {
+    float act[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) act[j] = fminf(fmaxf(__ldg(act_row + 12 * k + j), -S.action_clip), S.action_clip);
+    for (int d = 0; d < A.decimation; d++) {
+      float tau[3];
+      lane_torques(S, L, act, s.q, s.qd, kp, kd, motor, A.motor_model, A.flags, tau);
+      for (int n = 0; n < S.nsub; n++) substep(S, L, B, s, tau, h, nullptr);
+    }
+    if (RECORD) {
+      if (active) store_lane_state(A.out_states + (((size_t)c * A.S + seg) * A.H + k) * SPI_STATE_DIM, leg, s);
+    }
+  }
+  if (RECORD) return;
+
+  // scripts/eval.py:287-292 — L2 errors of the final state
+  const float* tgt = A.seg_target + (size_t)seg * SPI_TARGET_DIM;
+  float ep = 0.f, eq = 0.f, ej = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { const float e = s.p[i] - __ldg(tgt + i); ep += e * e; }
+#pragma unroll
+  for (int i = 0; i < 4; i++) { const float e = s.quat[i] - __ldg(tgt + 3 + i); eq += e * e; }
+#pragma unroll
+  for (int j = 0; j < 3; j++) { const float e = s.q[j] - __ldg(tgt + 7 + 3 * leg + j); ej += e * e; }
+  ej = group_sum(ej);
+  float err[3] = {sqrtf(ep), sqrtf(eq), sqrtf(ej)};
+  bool ok = lane_finite(s);
+  if (!ok && active) atomicOr(A.bad + c, 1);
+  if (A.per_seg && active && leg == 0) {
+    float* o = A.per_seg + ((size_t)c * A.S + seg) * 3;
+    o[0] = err[0]; o[1] = err[1]; o[2] = err[2];
+  }
+  const bool counts = active && (A.seg_mask ? (A.seg_mask[seg] != 0) : true);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    float v = counts ? err[i] : 0.f;
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    err[i] = v;
+  }
+  if (lane == 0) {
+    float* o = A.partial + ((size_t)c * A.n_warp_per_cand + cta_in_cand * (kThreads / 32) + warp) * 3;
+    o[0] = err[0]; o[1] = err[1]; o[2] = err[2];
+  }
+}
+
+// fixed-order sum of the per-warp partials -> mean costs (scripts/eval.py:304-309)
+__global__ void reduce_cost_kernel(const float* partial, const int* bad, const unsigned char* seg_mask, int C, int S,
+                                   int n_warp_per_cand, float cost_denominator, float* out_cost, int* out_status) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * 3) return;
+  const int c = idx / 3, k = idx - 3 * c;
+  float denom = cost_denominator;
+  if (!(denom > 0.f)) {
+    int n = 0;
+    if (seg_mask) { for (int s = 0; s < S; s++) n += seg_mask[s] ? 1 : 0; } else n = S;
+    denom = (float)n;
+  }
+  float sum = 0.f;
+  const float* p = partial + (size_t)c * n_warp_per_cand * 3 + k;
+  for (int w = 0; w < n_warp_per_cand; w++) sum += p[3 * w];
+  const int b = bad[c];
+  out_cost[idx] = b ? INFINITY : sum / denom;
+  if (out_status && k == 0) out_status[c] = b;
+}
+
+// BaseSimulator.simulate_at_each_physics_step for N envs (4 lanes per env), n_steps physics steps
+struct StepArgs {
+  const DeviceModel* model;
+  const float* params; int P; ParamIds ids; unsigned flags;
+  float* state; const float* torques; int N, n_steps;
+  float* foot_force;
+};
+__global__ void __launch_bounds__(kThreads) sim_step_kernel(const StepArgs A) {
+  const DeviceModel& M = *A.model;
+  const int leg = threadIdx.x & 3;
+  const int env_raw = blockIdx.x * kRolloutsPerCta + (threadIdx.x >> 2);
+  const bool active = env_raw < A.N;
+  const int env = active ? env_raw : A.N - 1;
+  SimConst S = M.sim;
+  LegConst L;
+  load_leg_const(M, leg, L);
+  BaseInertia B;
+  float motor[3];
+  apply_candidate(M, A.params ? A.params + (size_t)env * A.P : nullptr, A.ids, A.flags, B, motor);
+  LaneState s;
+  load_lane_state(A.state + (size_t)env * SPI_STATE_DIM, leg, s);
+  float tau[3], ff[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 3; j++) tau[j] = A.torques[(size_t)env * 12 + 3 * leg + j];
+  const float h = S.dt / (float)S.nsub;
+  for (int k = 0; k < A.n_steps; k++)
+    for (int n = 0; n < S.nsub; n++) substep(S, L, B, s, tau, h, ff);
+  if (active) {
+    store_lane_state(A.state + (size_t)env * SPI_STATE_DIM, leg, s);
+    if (A.foot_force) {
+      float* o = A.foot_force + ((size_t)env * 4 + leg) * 3;
+      o[0] = ff[0]; o[1] = ff[1]; o[2] = ff[2];
+    }
+  }
+}
+
+// torque law on its own, one thread per (row, joint)
+__global__ void torque_kernel(const DeviceModel* Mp, const float* actions, const float* q, const float* qd,
+                              const float* gains, const float* motor_params, int N, int motor_model, unsigned flags,
+                              float* out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * 12) return;
+  const DeviceModel& M = *Mp;
+  const int e = idx / 12, j = idx - 12 * e, leg = j / 3, jj = j - 3 * leg;
+  const float clipv = M.sim.action_clip;
+  float as = fminf(fmaxf(actions[idx], -clipv), clipv) * M.sim.action_scale;
+  if (jj == 0 && (flags & SPI_FLAG_HIP_HALF)) as *= 0.5f;
+  const float kp = gains ? gains[e * 24 + j] : M.kp[j];
+  const float kd = gains ? gains[e * 24 + 12 + j] : M.kd[j];
+  const float lim = M.leg[leg].tlim[jj];
+  float t = kp * (as + M.leg[leg].qdef[jj] - q[idx]) - kd * qd[idx];
+  const float g = motor_params ? motor_params[e * 3 + jj] : 20.0f;
+  const float g0 = motor_params ? motor_params[e * 3] : 20.0f;
+  if (motor_model == SPI_MOTOR_VEC3_TANH && (flags & SPI_FLAG_TANH_BEFORE_CLIP)) {
+    t = g * tanhf((1.0f / g) * t);
+    t = fminf(fmaxf(t, -lim), lim);
+  } else {
+    t = fminf(fmaxf(t, -lim), lim);
+    if (motor_model == SPI_MOTOR_SCALAR) t *= g0;
+    else if (motor_model == SPI_MOTOR_VEC3) t *= g;
+    else if (motor_model == SPI_MOTOR_VEC3_TANH) t = g * tanhf((1.0f / g) * t);
+  }
+  out[idx] = t;
+}
+
+// Fisher-information reward (active_sysid_openloop.py:402-426), one warp per main env:
+//   J[p][d] = (main[d] - aux_p[d]) / delta,  trace = sum J^2,  JJt[p][q] = sum_d J[p][d] J[q][d]
+__global__ void fim_reward_kernel(const float* states, int Mn, int P, float delta, int accumulate, float* out_JtJ,
+                                  float* out_trace) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= Mn) return;
+  const float* base = states + (size_t)warp * (P + 1) * 25;
+  const float inv = 1.0f / delta;
+  const float main_d = (lane < 25) ? base[lane] : 0.f;
+  float tr = 0.f;
+  for (int p = 0; p < P; p++) {
+    const float jp = (lane < 25) ? (main_d - base[(size_t)(p + 1) * 25 + lane]) * inv : 0.f;
+    tr += jp * jp;
+    if (out_JtJ) {
+      for (int q = 0; q <= p; q++) {
+        const float jq = (lane < 25) ? (main_d - base[(size_t)(q + 1) * 25 + lane]) * inv : 0.f;
+        float v = jp * jq;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) {
+          float* d1 = out_JtJ + ((size_t)warp * P + p) * P + q;
+          float* d2 = out_JtJ + ((size_t)warp * P + q) * P + p;
+          if (accumulate) { *d1 += v; if (p != q) *d2 += v; }
+          else { *d1 = v; *d2 = v; }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
+  if (lane == 0 && out_trace) { if (accumulate) out_trace[warp] += tr; else out_trace[warp] = tr; }
+}
+
+// total[c] = w . cost[c,:]
+__global__ void weighted_cost_kernel(const float* cost3, int C, float w0, float w1, float w2, float* out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) out[c] = w0 * cost3[3 * c] + w1 * cost3[3 * c + 1] + w2 * cost3[3 * c + 2];
+}
+
+// ---- CEM on device -----------------------------------------------------------------------------
+// counter-based RNG (Philox-4x32-10), keyed by (seed), counter = (global candidate, param, iteration)
+SPI_DEV void philox4x32(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned* out) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+    const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+    const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1;
+    const unsigned n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__global__ void cem_sample_kernel(const float* mean, const float* stdv, const float* lo, const float* hi, int C, int P,
+                                  int c0, unsigned long long seed, int iteration, float* out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * P) return;
+  const int c = idx / P, p = idx - c * P;
+  unsigned r[4];
+  philox4x32((unsigned)(c0 + c), (unsigned)p, (unsigned)iteration, 0x5B1u, (unsigned)seed, (unsigned)(seed >> 32), r);
+  const float u1 = ((float)(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = ((float)(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float z = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+  float v = mean[p] + stdv[p] * z;
+  if (lo) v = fmaxf(v, lo[p]);
+  if (hi) v = fminf(v, hi[p]);
+  out[idx] = v;
+}
+// rank[i] = #{ j : cost_j < cost_i  or (cost_j == cost_i and j < i) }; NaN/inf sort last
+__global__ void cem_rank_kernel(const float* cost, int C, int* rank) {
+  __shared__ float tile[256];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float ci = (i < C) ? cost[i] : INFINITY;
+  if (!(ci == ci)) ci = INFINITY;
+  int r = 0;
+  for (int base = 0; base < C; base += 256) {
+    const int j = base + threadIdx.x;
+    float cj = (j < C) ? cost[j] : INFINITY;
+    if (!(cj == cj)) cj = INFINITY;
+    __syncthreads();
+    tile[threadIdx.x] = cj;
+    __syncthreads();
+    const int n = min(256, C - base);
+    for (int t = 0; t < n; t++) {
+      const float v = tile[t];
+      r += (v < ci || (v == ci && (base + t) < i)) ? 1 : 0;
+    }
+  }
+  if (i < C) rank[i] = r;
+}
+// one CTA per parameter: elite mean / std in a fixed summation order, smoothed update; CTA 0 also
+// writes the best candidate (rank 0)
+__global__ void cem_refit_kernel(const float* params, const float* cost, const int* rank, int C, int P, int n_elite,
+                                 float alpha, const float* std_floor, float* mean, float* stdv, float* out_best) {
+  __shared__ float sh[256];
+  __shared__ float sh_mean;
+  const int p = blockIdx.x, t = threadIdx.x;
+  float acc = 0.f;
+  for (int i = t; i < C; i += 256) acc += (rank[i] < n_elite) ? params[(size_t)i * P + p] : 0.f;
+  sh[t] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (t < o) sh[t] += sh[t + o]; __syncthreads(); }
+  if (t == 0) sh_mean = sh[0] / (float)n_elite;
+  __syncthreads();
+  const float mu = sh_mean;
+  acc = 0.f;
+  for (int i = t; i < C; i += 256) {
+    const float d = params[(size_t)i * P + p] - mu;
+    acc += (rank[i] < n_elite) ? d * d : 0.f;
+  }
+  __syncthreads();
+  sh[t] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (t < o) sh[t] += sh[t + o]; __syncthreads(); }
+  if (t == 0) {
+    float sd = sqrtf(sh[0] / (float)n_elite);
+    float m2 = (1.f - alpha) * mean[p] + alpha * mu;
+    float s2 = (1.f - alpha) * stdv[p] + alpha * sd;
+    if (std_floor) s2 = fmaxf(s2, std_floor[p]);
+    mean[p] = m2; stdv[p] = s2;
+  }
+  if (out_best) {
+    for (int i = t; i < C; i += 256)
+      if (rank[i] == 0) { out_best[p] = params[(size_t)i * P + p]; if (p == 0) out_best[P] = cost[i]; }
+  }
+}
+
+// FP32 FMA peak: 8 independent FFMA chains per thread, register resident
+__global__ void __launch_bounds__(256) fp32_peak_kernel(int iters, float seed, float* sink) {
+  float a0 = seed, a1 = seed + 1.f, a2 = seed + 2.f, a3 = seed + 3.f, a4 = seed + 4.f, a5 = seed + 5.f, a6 = seed + 6.f,
+        a7 = seed + 7.f;
+  const float m = 0.999f, b = 0.001f;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      a0 = fmaf(a0, m, b); a1 = fmaf(a1, m, b); a2 = fmaf(a2, m, b); a3 = fmaf(a3, m, b);
+      a4 = fmaf(a4, m, b); a5 = fmaf(a5, m, b); a6 = fmaf(a6, m, b); a7 = fmaf(a7, m, b);
+    }
+  }
+  const float r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (r == 123456.789f) sink[0] = r;
+}
+
+}  // namespace
+
+// ================================================================================================
+// host side: model handle, error handling, C-ABI
+// ================================================================================================
+struct spi_b200_model {
+  DeviceModel host_model;
+  DeviceModel* d_model = nullptr;
+  int device = 0;
+  // workspaces (grown on demand)
+  float* d_partial = nullptr; size_t partial_cap = 0;
+  int* d_bad = nullptr; size_t bad_cap = 0;
+  int* d_rank = nullptr; size_t rank_cap = 0;
+  // staging for the *_host entry point
+  char* d_stage = nullptr; size_t d_stage_cap = 0;
+  char* h_stage = nullptr; size_t h_stage_cap = 0;
+};
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+#define CUDA_OK(expr)                                                                             \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return fail(-100, std::string(#expr) + ": " + cudaGetErrorString(_e));                      \
+  } while (0)
+
+int check_launch(const char* what) {
+  g_launches.fetch_add(1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(-101, std::string(what) + " launch failed: " + cudaGetErrorString(e));
+  return 0;
+}
+
+template <class T> int ensure(T** ptr, size_t* cap, size_t need) {
+  if (*cap >= need) return 0;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr; *cap = 0;
+  CUDA_OK(cudaMalloc((void**)ptr, need * sizeof(T)));
+  *cap = need;
+  return 0;
+}
+
+int make_ids(int P, const int* param_ids, ParamIds* out) {
+  if (P < 0 || P > 16) return fail(-3, "P must be in [0,16]");
+  out->n = P;
+  for (int i = 0; i < 16; i++) out->id[i] = -1;
+  for (int i = 0; i < P; i++) {
+    if (!param_ids) return fail(-3, "param_ids is NULL");
+    if (param_ids[i] < 0 || param_ids[i] >= SPI_PARAM_COUNT) return fail(-3, "param id out of range");
+    out->id[i] = param_ids[i];
+  }
+  return 0;
+}
+
+int blob_to_model(const float* b, int n, DeviceModel* M) {
+  if (!b || n < SPI_BLOB_SIZE) return fail(-2, "model blob too short");
+  if (b[SPI_BLOB_MAGIC] != SPI_BLOB_MAGIC_VALUE) return fail(-2, "model blob magic mismatch");
+  std::memset(M, 0, sizeof(*M));
+  M->sim.dt = b[SPI_BLOB_DT]; M->sim.gz = b[SPI_BLOB_GRAVITY_Z];
+  M->sim.action_scale = b[SPI_BLOB_ACTION_SCALE]; M->sim.action_clip = b[SPI_BLOB_ACTION_CLIP];
+  M->sim.kn = b[SPI_BLOB_CONTACT_KN]; M->sim.cn = b[SPI_BLOB_CONTACT_CN]; M->sim.mu = b[SPI_BLOB_CONTACT_MU];
+  M->sim.dtan = b[SPI_BLOB_CONTACT_DT]; M->sim.radius = b[SPI_BLOB_FOOT_RADIUS];
+  M->sim.veps2 = b[SPI_BLOB_CONTACT_VEPS] * b[SPI_BLOB_CONTACT_VEPS];
+  M->sim.nsub = (int)b[SPI_BLOB_NSUB];
+  if (M->sim.nsub < 1) M->sim.nsub = 1;
+  if (!(M->sim.dt > 0.f)) return fail(-2, "model blob: dt must be positive");
+  for (int k = 0; k < 10; k++) M->base_inertial[k] = b[SPI_BLOB_BASE_INERTIAL + k];
+  if (!(M->base_inertial[0] > 0.f)) return fail(-2, "model blob: base mass must be positive");
+  for (int l = 0; l < 2; l++)
+    for (int k = 0; k < 10; k++) M->lumps[l][k] = b[SPI_BLOB_BASE_LUMPS + 10 * l + k];
+  for (int leg = 0; leg < 4; leg++) {
+    LegConst& L = M->leg[leg];
+    for (int j = 0; j < 3; j++) {
+      const float* p = b + SPI_BLOB_LEG_BODIES + SPI_LEG_BODY_STRIDE * (3 * leg + j);
+      const int axis = (int)p[13];
+      // the leg-per-lane kernel is specialised for the Go2 chain hip(x) - thigh(y) - calf(y)
+      if (axis != (j == 0 ? 0 : 1)) return fail(-2, "model blob: joint axes must be hip=x, thigh=y, calf=y");
+      const float m = p[0];
+      const float c[3] = {p[1], p[2], p[3]};
+      const float cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+      L.m[j] = m;
+      for (int k = 0; k < 3; k++) { L.h[j][k] = m * c[k]; L.r[j][k] = p[10 + k]; }
+      const float Ic[6] = {p[4], p[5], p[6], p[7], p[8], p[9]};
+      for (int r = 0; r < 3; r++)
+        for (int k = r; k < 3; k++) {
+          const int s = (r == k) ? r : ((r + k == 1) ? 3 : ((r + k == 2) ? 4 : 5));
+          L.Io[j][s] = Ic[s] + m * ((r == k ? cc : 0.f) - c[r] * c[k]);
+        }
+      L.qdef[j] = b[SPI_BLOB_Q_DEFAULT + 3 * leg + j];
+      L.tlim[j] = b[SPI_BLOB_TORQUE_LIMIT + 3 * leg + j];
+    }
+    for (int k = 0; k < 3; k++) L.foot[k] = b[SPI_BLOB_FOOT_OFFSET + 3 * leg + k];
+  }
+  for (int j = 0; j < 12; j++) { M->kp[j] = b[SPI_BLOB_KP + j]; M->kd[j] = b[SPI_BLOB_KD + j]; }
+  return 0;
+}
+
+int launch_rollout(spi_b200_model* m, bool record, const float* params, int C, int P, const int* param_ids,
+                   const float* seg_init, const float* seg_actions, const float* seg_target, const float* seg_gains,
+                   const unsigned char* seg_mask, int S, int H, int decimation, int motor_model, unsigned flags,
+                   float cost_denominator, float* out_cost, float* out_per_seg, int* out_status, float* out_states,
+                   cudaStream_t st) {
+  if (!m) return fail(-1, "model handle is NULL");
+  if (C <= 0 || S <= 0 || H <= 0 || decimation <= 0) return fail(-3, "C, S, H, decimation must be positive");
+  if (!seg_init || !seg_actions) return fail(-3, "seg_init / seg_actions is NULL");
+  if (!record && (!seg_target || !out_cost)) return fail(-3, "seg_target / out_cost is NULL");
+  if (record && !out_states) return fail(-3, "out_states is NULL");
+  if (P > 0 && !params) return fail(-3, "params is NULL");
+  if (motor_model < SPI_MOTOR_NONE || motor_model > SPI_MOTOR_VEC3_TANH) return fail(-3, "unknown motor_model");
+  EvalArgs A;
+  std::memset(&A, 0, sizeof(A));
+  if (int rc = make_ids(P, param_ids, &A.ids)) return rc;
+  A.model = m->d_model;
+  A.params = (P > 0) ? params : nullptr; A.C = C; A.P = P;
+  A.seg_init = seg_init; A.seg_actions = seg_actions; A.seg_target = seg_target; A.seg_gains = seg_gains;
+  A.seg_mask = seg_mask; A.S = S; A.H = H; A.decimation = decimation; A.motor_model = motor_model; A.flags = flags;
+  A.n_cta_per_cand = (S + kRolloutsPerCta - 1) / kRolloutsPerCta;
+  A.n_warp_per_cand = A.n_cta_per_cand * (kThreads / 32);
+  const long long n_cta = (long long)C * A.n_cta_per_cand;
+  if (n_cta > 2147483647LL) return fail(-3, "C * ceil(S/32) exceeds the grid limit");
+  if (!record) {
+    if (int rc = ensure(&m->d_partial, &m->partial_cap, (size_t)C * A.n_warp_per_cand * 3)) return rc;
+    if (int rc = ensure(&m->d_bad, &m->bad_cap, (size_t)C)) return rc;
+    CUDA_OK(cudaMemsetAsync(m->d_bad, 0, (size_t)C * sizeof(int), st));
+    A.partial = m->d_partial; A.bad = m->d_bad; A.per_seg = out_per_seg;
+    rollout_kernel<false><<<(unsigned)n_cta, kThreads, 0, st>>>(A);
+    if (int rc = check_launch("rollout_kernel")) return rc;
+    const int n = C * 3;
+    reduce_cost_kernel<<<(n + 127) / 128, 128, 0, st>>>(m->d_partial, m->d_bad, seg_mask, C, S, A.n_warp_per_cand,
+                                                        cost_denominator, out_cost, out_status);
+    return check_launch("reduce_cost_kernel");
+  }
+  A.out_states = out_states;
+  rollout_kernel<true><<<(unsigned)n_cta, kThreads, 0, st>>>(A);
+  return check_launch("rollout_kernel<record>");
+}
+
+}  // namespace
+
+extern "C" {
+
+int spi_b200_version(void) { return SPI_B200_VERSION; }
+const char* spi_b200_last_error(void) { return g_last_error.c_str(); }
+long long spi_b200_launch_count(void) { return g_launches.load(); }
+
+int spi_b200_model_create(const float* model_blob, int n_floats, spi_b200_model** out_model) {
+  if (!out_model) return fail(-1, "out_model is NULL");
+  *out_model = nullptr;
+  spi_b200_model* m = new (std::nothrow) spi_b200_model();
+  if (!m) return fail(-4, "out of host memory");
+  if (int rc = blob_to_model(model_blob, n_floats, &m->host_model)) { delete m; return rc; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    delete m;
+    return fail(-5, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0"));
+  }
+  e = cudaGetDevice(&m->device);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_model, sizeof(DeviceModel));
+  if (e == cudaSuccess) e = cudaMemcpy(m->d_model, &m->host_model, sizeof(DeviceModel), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (m->d_model) cudaFree(m->d_model);
+    delete m;
+    return fail(-100, std::string("model upload failed: ") + cudaGetErrorString(e));
+  }
+  *out_model = m;
+  return 0;
+}
+
+int spi_b200_model_destroy(spi_b200_model* m) {
+  if (!m) return 0;
+  if (m->d_model) cudaFree(m->d_model);
+  if (m->d_partial) cudaFree(m->d_partial);
+  if (m->d_bad) cudaFree(m->d_bad);
+  if (m->d_rank) cudaFree(m->d_rank);
+  if (m->d_stage) cudaFree(m->d_stage);
+  if (m->h_stage) cudaFreeHost(m->h_stage);
+  delete m;
+  return 0;
+}
+
+int spi_b200_eval_candidates(spi_b200_model* model, const float* params, int C, int P, const int* param_ids,
+                             const float* seg_init, const float* seg_actions, const float* seg_target,
+                             const float* seg_gains, const unsigned char* seg_mask, int S, int H, int decimation,
+                             int motor_model, unsigned flags, float cost_denominator, float* out_cost,
+                             float* out_per_seg, int* out_status, void* cuda_stream) {
+  return launch_rollout(model, false, params, C, P, param_ids, seg_init, seg_actions, seg_target, seg_gains, seg_mask,
+                        S, H, decimation, motor_model, flags, cost_denominator, out_cost, out_per_seg, out_status,
+                        nullptr, (cudaStream_t)cuda_stream);
+}
+
+int spi_b200_rollout_states(spi_b200_model* model, const float* params, int C, int P, const int* param_ids,
+                            const float* seg_init, const float* seg_actions, const float* seg_gains, int S, int H,
+                            int decimation, int motor_model, unsigned flags, float* out_states, void* cuda_stream) {
+  return launch_rollout(model, true, params, C, P, param_ids, seg_init, seg_actions, nullptr, seg_gains, nullptr, S, H,
+                        decimation, motor_model, flags, 0.f, nullptr, nullptr, nullptr, out_states,
+                        (cudaStream_t)cuda_stream);
+}
+
+int spi_b200_eval_candidates_host(spi_b200_model* m, const float* params, int C, int P, const int* param_ids,
+                                  const float* seg_init, const float* seg_actions, const float* seg_target,
+                                  const float* seg_gains, const unsigned char* seg_mask, int S, int H, int decimation,
+                                  int motor_model, unsigned flags, float cost_denominator, float* out_cost,
+                                  int* out_status, void* cuda_stream) {
+  if (!m) return fail(-1, "model handle is NULL");
+  if (C <= 0 || S <= 0 || H <= 0) return fail(-3, "C, S, H must be positive");
+  if (!seg_init || !seg_actions || !seg_target || !out_cost) return fail(-3, "NULL host buffer");
+  if (P > 0 && !params) return fail(-3, "params is NULL");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t b_params = al((size_t)C * P * 4), b_init = al((size_t)S * SPI_STATE_DIM * 4),
+               b_act = al((size_t)S * H * 12 * 4), b_tgt = al((size_t)S * SPI_TARGET_DIM * 4),
+               b_gain = seg_gains ? al((size_t)S * 24 * 4) : 0, b_mask = seg_mask ? al((size_t)S) : 0,
+               b_cost = al((size_t)C * 3 * 4), b_stat = al((size_t)C * 4);
+  const size_t in_bytes = b_params + b_init + b_act + b_tgt + b_gain + b_mask;
+  const size_t total = in_bytes + b_cost + b_stat;
+  if (m->d_stage_cap < total) {
+    if (m->d_stage) cudaFree(m->d_stage);
+    if (m->h_stage) cudaFreeHost(m->h_stage);
+    m->d_stage = nullptr; m->h_stage = nullptr; m->d_stage_cap = m->h_stage_cap = 0;
+    CUDA_OK(cudaMalloc((void**)&m->d_stage, total));
+    CUDA_OK(cudaMallocHost((void**)&m->h_stage, total));
+    m->d_stage_cap = m->h_stage_cap = total;
+  }
+  size_t o = 0;
+  auto put = [&](const void* src, size_t bytes, size_t padded) -> size_t {
+    size_t at = o;
+    if (src && bytes) std::memcpy(m->h_stage + at, src, bytes);
+    o += padded;
+    return at;
+  };
+  const size_t o_params = put(params, (size_t)C * P * 4, b_params);
+  const size_t o_init = put(seg_init, (size_t)S * SPI_STATE_DIM * 4, b_init);
+  const size_t o_act = put(seg_actions, (size_t)S * H * 12 * 4, b_act);
+  const size_t o_tgt = put(seg_target, (size_t)S * SPI_TARGET_DIM * 4, b_tgt);
+  const size_t o_gain = put(seg_gains, (size_t)S * 24 * 4, b_gain);
+  const size_t o_mask = put(seg_mask, (size_t)S, b_mask);
+  const size_t o_cost = o, o_stat = o + b_cost;
+  CUDA_OK(cudaMemcpyAsync(m->d_stage, m->h_stage, in_bytes, cudaMemcpyHostToDevice, st));
+  char* d = m->d_stage;
+  int rc = launch_rollout(m, false, (const float*)(d + o_params), C, P, param_ids, (const float*)(d + o_init),
+                          (const float*)(d + o_act), (const float*)(d + o_tgt),
+                          seg_gains ? (const float*)(d + o_gain) : nullptr,
+                          seg_mask ? (const unsigned char*)(d + o_mask) : nullptr, S, H, decimation, motor_model, flags,
+                          cost_denominator, (float*)(d + o_cost), nullptr, (int*)(d + o_stat), nullptr, st);
+  if (rc) return rc;
+  CUDA_OK(cudaMemcpyAsync(m->h_stage + o_cost, d + o_cost, b_cost + b_stat, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  std::memcpy(out_cost, m->h_stage + o_cost, (size_t)C * 3 * 4);
+  if (out_status) std::memcpy(out_status, m->h_stage + o_stat, (size_t)C * 4);
+  return 0;
+}
+
+int spi_b200_sim_step(spi_b200_model* m, const float* params, int P, const int* param_ids, unsigned flags, float* state,
+                      const float* torques, int N, int n_steps, float* out_foot_force, void* cuda_stream) {
+  if (!m) return fail(-1, "model handle is NULL");
+  if (N <= 0 || n_steps < 0) return fail(-3, "N must be positive, n_steps non-negative");
+  if (!state || !torques) return fail(-3, "state / torques is NULL");
+  StepArgs A;
+  std::memset(&A, 0, sizeof(A));
+  if (int rc = make_ids(params ? P : 0, param_ids, &A.ids)) return rc;
+  A.model = m->d_model; A.params = params; A.P = P; A.flags = flags;
+  A.state = state; A.torques = torques; A.N = N; A.n_steps = n_steps; A.foot_force = out_foot_force;
+  const int n_cta = (N + kRolloutsPerCta - 1) / kRolloutsPerCta;
+  sim_step_kernel<<<n_cta, kThreads, 0, (cudaStream_t)cuda_stream>>>(A);
+  return check_launch("sim_step_kernel");
+}
+
+int spi_b200_compute_torques(spi_b200_model* m, const float* actions, const float* q, const float* qd,
+                             const float* gains, const float* motor_params, int N, int motor_model, unsigned flags,
+                             float* out_tau, void* cuda_stream) {
+  if (!m) return fail(-1, "model handle is NULL");
+  if (N <= 0) return fail(-3, "N must be positive");
+  if (!actions || !q || !qd || !out_tau) return fail(-3, "NULL buffer");
+  if (motor_model < SPI_MOTOR_NONE || motor_model > SPI_MOTOR_VEC3_TANH) return fail(-3, "unknown motor_model");
+  const int n = N * 12;
+  torque_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(m->d_model, actions, q, qd, gains,
+                                                                        motor_params, N, motor_model, flags, out_tau);
+  return check_launch("torque_kernel");
+}
+
+int spi_b200_fim_reward(spi_b200_model* m, const float* states, int Mn, int P, float delta, int accumulate,
+                        float* out_JtJ, float* out_trace, void* cuda_stream) {
+  if (!m) return fail(-1, "model handle is NULL");
+  if (Mn <= 0 || P <= 0) return fail(-3, "M and P must be positive");
+  if (!states || (!out_JtJ && !out_trace)) return fail(-3, "NULL buffer");
+  if (!(delta != 0.f)) return fail(-3, "delta must be non-zero");
+  const int threads = 128, warps_per_cta = threads / 32;
+  fim_reward_kernel<<<(Mn + warps_per_cta - 1) / warps_per_cta, threads, 0, (cudaStream_t)cuda_stream>>>(
+      states, Mn, P, delta, accumulate, out_JtJ, out_trace);
+  return check_launch("fim_reward_kernel");
+}
+
+int spi_b200_weighted_cost(spi_b200_model* m, const float* cost3, int C, float w_pos, float w_quat, float w_joint,
+                           float* out_total, void* cuda_stream) {
+  if (!m) return fail(-1, "model handle is NULL");
+  if (C <= 0 || !cost3 || !out_total) return fail(-3, "bad arguments");
+  weighted_cost_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(cost3, C, w_pos, w_quat, w_joint,
+                                                                               out_total);
+  return check_launch("weighted_cost_kernel");
+}
+
+int spi_b200_cem_sample(spi_b200_model* m, const float* mean, const float* std, const float* lo, const float* hi, int C,
+                        int P, int c0, unsigned long long seed, int iteration, float* out_params, void* cuda_stream) {
+  if (!m) return fail(-1, "model handle is NULL");
+  if (C <= 0 || P <= 0 || !mean || !std || !out_params) return fail(-3, "bad arguments");
+  const int n = C * P;
+  cem_sample_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(mean, std, lo, hi, C, P, c0, seed,
+                                                                            iteration, out_params);
+  return check_launch("cem_sample_kernel");
+}
+
+int spi_b200_cem_refit(spi_b200_model* m, const float* params, const float* cost, int C, int P, int n_elite,
+                       float alpha, const float* std_floor, float* mean, float* std, float* out_best,
+                       void* cuda_stream) {
+  if (!m) return fail(-1, "model handle is NULL");
+  if (C <= 0 || P <= 0 || n_elite <= 0 || n_elite > C) return fail(-3, "bad C / P / n_elite");
+  if (!params || !cost || !mean || !std) return fail(-3, "NULL buffer");
+  if (int rc = ensure(&m->d_rank, &m->rank_cap, (size_t)C)) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  cem_rank_kernel<<<(C + 255) / 256, 256, 0, st>>>(cost, C, m->d_rank);
+  if (int rc = check_launch("cem_rank_kernel")) return rc;
+  cem_refit_kernel<<<P, 256, 0, st>>>(params, cost, m->d_rank, C, P, n_elite, alpha, std_floor, mean, std, out_best);
+  return check_launch("cem_refit_kernel");
+}
+
+int spi_b200_fp32_peak(int iters, float* out_tflops, float* out_ms, void* cuda_stream) {
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int dev = 0, sms = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  float* sink = nullptr;
+  CUDA_OK(cudaMalloc((void**)&sink, 4));
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  const int grid = sms * 8, threads = 256;
+  fp32_peak_kernel<<<grid, threads, 0, st>>>(iters / 4 + 1, 1.0f, sink);  // warm-up
+  g_launches.fetch_add(1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    CUDA_OK(cudaEventRecord(e0, st));
+    fp32_peak_kernel<<<grid, threads, 0, st>>>(iters, 1.0f, sink);
+    g_launches.fetch_add(1);
+    CUDA_OK(cudaEventRecord(e1, st));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+  const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)grid * (double)threads;
+  if (out_tflops) *out_tflops = (float)(flops / (best * 1e-3) / 1e12);
+  if (out_ms) *out_ms = best;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,257 @@
+"""Python face of the C-ABI (include/spi_b200.h): torch tensors in, torch tensors out, raw pointers
+across the boundary.  PyTorch is only the owner of device memory and streams here.
+
+`RolloutEngine.evaluate_candidates` is the fused replacement of the reference's candidate loop
+(scripts/mass_landscape.py:123-126: apply_base_mass + evaluate_batch per candidate).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import go2_model as gm
+from .dataset import SegmentBatch
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _ids(names_or_ids: Sequence) -> np.ndarray:
+    out = []
+    for x in names_or_ids:
+        if isinstance(x, str):
+            if x not in gm.PARAM_IDS:
+                raise KeyError(f"unknown parameter name {x!r}; known: {sorted(gm.PARAM_IDS)}")
+            out.append(gm.PARAM_IDS[x])
+        else:
+            out.append(int(x))
+    return np.asarray(out, dtype=np.int32)
+
+
+def motor_model_id(name_or_id) -> int:
+    if isinstance(name_or_id, str):
+        return gm.MOTOR_MODELS[name_or_id]
+    return int(name_or_id)
+
+
+class RolloutEngine:
+    """Device-resident Go2 model + workspaces; one instance per (process, GPU, stream)."""
+
+    def __init__(self, model: Optional[gm.Go2Model] = None, device: Optional[torch.device] = None):
+        self.lib = _lib.lib()  # raises if libspi_b200.so is missing: no CPU fallback
+        if not torch.cuda.is_available():
+            raise _lib.SpiB200Error("RolloutEngine needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.model = model or gm.go2_nominal()
+        self.blob = gm.build_model_blob(self.model)
+        self._handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_model_create(self.blob.ctypes.data_as(C.POINTER(C.c_float)), int(self.blob.size),
+                                                C.byref(self._handle))
+        _lib.check(rc, "spi_b200_model_create")
+
+    def close(self):
+        if getattr(self, "_handle", None) and self._handle.value:
+            self.lib.spi_b200_model_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers --------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _f32(self, t, shape=None) -> Optional[torch.Tensor]:
+        if t is None:
+            return None
+        t = torch.as_tensor(t, device=self.device, dtype=torch.float32).contiguous()
+        if shape is not None:
+            t = t.reshape(shape)
+        return t
+
+    # ---- fused hot path -------------------------------------------------------------------
+    def evaluate_candidates(self, params, param_names, segs: SegmentBatch, decimation: Optional[int] = None,
+                            motor_model="none", flags: int = 0, cost_denominator: Optional[float] = None,
+                            return_per_seg: bool = False, return_status: bool = False, out: torch.Tensor = None):
+        """params[C,P] -> cost[C,3] (mean base_pos, base_quat, joint_pos L2 errors)."""
+        params = self._f32(params)
+        if params.dim() == 1:
+            params = params[:, None]
+        Cn, P = params.shape
+        ids = _ids(param_names)
+        assert ids.size == P, "one name/id per parameter column"
+        S, H = segs.num_segments, segs.horizon
+        cost = out if out is not None else torch.empty((Cn, 3), device=self.device, dtype=torch.float32)
+        per = torch.empty((Cn, S, 3), device=self.device, dtype=torch.float32) if return_per_seg else None
+        status = torch.empty((Cn,), device=self.device, dtype=torch.int32)
+        denom = segs.cost_denominator if cost_denominator is None else cost_denominator
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_eval_candidates(
+                self._handle, _ptr(params), Cn, P, ids.ctypes.data_as(C.POINTER(C.c_int)), _ptr(segs.seg_init),
+                _ptr(segs.seg_actions), _ptr(segs.seg_target), _ptr(segs.seg_gains), _ptr(segs.seg_mask), S, H,
+                int(decimation or self.model.control_decimation), motor_model_id(motor_model), int(flags),
+                float(denom), _ptr(cost), _ptr(per), _ptr(status), self._stream())
+        _lib.check(rc, "spi_b200_eval_candidates")
+        res = (cost,)
+        if return_per_seg:
+            res += (per,)
+        if return_status:
+            res += (status,)
+        return res if len(res) > 1 else cost
+
+    def evaluate_candidates_host(self, params: np.ndarray, param_names, seg_init: np.ndarray, seg_actions: np.ndarray,
+                                 seg_target: np.ndarray, seg_gains: Optional[np.ndarray] = None,
+                                 seg_mask: Optional[np.ndarray] = None, decimation: Optional[int] = None,
+                                 motor_model="none", flags: int = 0, cost_denominator: float = 0.0):
+        """numpy in / numpy out through spi_b200_eval_candidates_host (H2D + D2H inside the call)."""
+        params = np.ascontiguousarray(params, dtype=np.float32).reshape(len(params), -1)
+        seg_init = np.ascontiguousarray(seg_init, dtype=np.float32)
+        seg_actions = np.ascontiguousarray(seg_actions, dtype=np.float32)
+        seg_target = np.ascontiguousarray(seg_target, dtype=np.float32)
+        seg_gains = None if seg_gains is None else np.ascontiguousarray(seg_gains, dtype=np.float32)
+        seg_mask = None if seg_mask is None else np.ascontiguousarray(seg_mask, dtype=np.uint8)
+        Cn, P = params.shape
+        ids = _ids(param_names)
+        S, H = seg_actions.shape[0], seg_actions.shape[1]
+        cost = np.empty((Cn, 3), dtype=np.float32)
+        status = np.empty((Cn,), dtype=np.int32)
+        fp = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_eval_candidates_host(
+                self._handle, fp(params), Cn, P, ids.ctypes.data_as(C.POINTER(C.c_int)), fp(seg_init), fp(seg_actions),
+                fp(seg_target), fp(seg_gains),
+                None if seg_mask is None else seg_mask.ctypes.data_as(C.POINTER(C.c_ubyte)), S, H,
+                int(decimation or self.model.control_decimation), motor_model_id(motor_model), int(flags),
+                float(cost_denominator), fp(cost), status.ctypes.data_as(C.POINTER(C.c_int)), self._stream())
+        _lib.check(rc, "spi_b200_eval_candidates_host")
+        return cost, status
+
+    def rollout_states(self, params, param_names, seg_init, seg_actions, seg_gains=None, decimation=None,
+                       motor_model="none", flags: int = 0) -> torch.Tensor:
+        """-> states[C,S,H,37] after each control step (parity hook, dataset recorder)."""
+        params = self._f32(params)
+        if params.dim() == 1:
+            params = params[:, None]
+        Cn, P = params.shape
+        ids = _ids(param_names)
+        seg_init = self._f32(seg_init).reshape(-1, gm.STATE_DIM)
+        S = seg_init.shape[0]
+        seg_actions = self._f32(seg_actions).reshape(S, -1, 12)
+        H = seg_actions.shape[1]
+        seg_gains = self._f32(seg_gains)
+        out = torch.empty((Cn, S, H, gm.STATE_DIM), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_rollout_states(
+                self._handle, _ptr(params), Cn, P, ids.ctypes.data_as(C.POINTER(C.c_int)), _ptr(seg_init),
+                _ptr(seg_actions), _ptr(seg_gains), S, H, int(decimation or self.model.control_decimation),
+                motor_model_id(motor_model), int(flags), _ptr(out), self._stream())
+        _lib.check(rc, "spi_b200_rollout_states")
+        return out
+
+    # ---- stepwise boundary ------------------------------------------------------------------
+    def sim_step(self, state: torch.Tensor, torques: torch.Tensor, n_steps: int = 1, params=None, param_names=(),
+                 flags: int = 0, foot_force: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Advance state[N,37] IN PLACE by n_steps physics steps under constant torques[N,12]."""
+        assert state.is_cuda and state.dtype == torch.float32 and state.is_contiguous()
+        torques = self._f32(torques)
+        N = state.shape[0]
+        P = 0
+        ids = np.zeros(1, dtype=np.int32)
+        if params is not None:
+            params = self._f32(params).reshape(N, -1)
+            P = params.shape[1]
+            ids = _ids(param_names)
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_sim_step(self._handle, _ptr(params), P, ids.ctypes.data_as(C.POINTER(C.c_int)),
+                                            int(flags), _ptr(state), _ptr(torques), N, int(n_steps), _ptr(foot_force),
+                                            self._stream())
+        _lib.check(rc, "spi_b200_sim_step")
+        return state
+
+    def compute_torques(self, actions, q, qd, gains=None, motor_params=None, motor_model="none", flags: int = 0):
+        actions = self._f32(actions).reshape(-1, 12)
+        q = self._f32(q).reshape(-1, 12)
+        qd = self._f32(qd).reshape(-1, 12)
+        gains = self._f32(gains)
+        motor_params = self._f32(motor_params)
+        N = actions.shape[0]
+        out = torch.empty((N, 12), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_compute_torques(self._handle, _ptr(actions), _ptr(q), _ptr(qd), _ptr(gains),
+                                                   _ptr(motor_params), N, motor_model_id(motor_model), int(flags),
+                                                   _ptr(out), self._stream())
+        _lib.check(rc, "spi_b200_compute_torques")
+        return out
+
+    # ---- Fisher information ---------------------------------------------------------------------
+    def fim_reward(self, states: torch.Tensor, delta: float, out_JtJ: Optional[torch.Tensor] = None,
+                   out_trace: Optional[torch.Tensor] = None, accumulate: bool = False):
+        """states[M,P+1,25] (main + P aux; root13 + q12) -> (JJt[M,P,P], trace[M])."""
+        states = self._f32(states)
+        Mn, P1, D = states.shape
+        assert D == 25 and P1 >= 2
+        P = P1 - 1
+        if out_JtJ is None:
+            out_JtJ = torch.zeros((Mn, P, P), device=self.device, dtype=torch.float32)
+        if out_trace is None:
+            out_trace = torch.zeros((Mn,), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_fim_reward(self._handle, _ptr(states), Mn, P, float(delta), int(accumulate),
+                                              _ptr(out_JtJ), _ptr(out_trace), self._stream())
+        _lib.check(rc, "spi_b200_fim_reward")
+        return out_JtJ, out_trace
+
+    # ---- optimiser pieces -------------------------------------------------------------------------
+    def weighted_cost(self, cost3: torch.Tensor, w=(10.0, 5.0, 1.0), out: Optional[torch.Tensor] = None):
+        cost3 = self._f32(cost3)
+        Cn = cost3.shape[0]
+        out = out if out is not None else torch.empty((Cn,), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_weighted_cost(self._handle, _ptr(cost3), Cn, float(w[0]), float(w[1]), float(w[2]),
+                                                 _ptr(out), self._stream())
+        _lib.check(rc, "spi_b200_weighted_cost")
+        return out
+
+    def cem_sample(self, mean, std, lo, hi, C_local: int, c0: int, seed: int, iteration: int,
+                   out: Optional[torch.Tensor] = None):
+        mean = self._f32(mean); std = self._f32(std); lo = self._f32(lo); hi = self._f32(hi)
+        P = mean.numel()
+        out = out if out is not None else torch.empty((C_local, P), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_cem_sample(self._handle, _ptr(mean), _ptr(std), _ptr(lo), _ptr(hi), int(C_local), P,
+                                              int(c0), C.c_ulonglong(seed), int(iteration), _ptr(out), self._stream())
+        _lib.check(rc, "spi_b200_cem_sample")
+        return out
+
+    def cem_refit(self, params, cost, n_elite: int, alpha: float, mean, std, std_floor=None, out_best=None):
+        """mean/std updated IN PLACE; returns out_best[P+1] (best params, best cost)."""
+        params = self._f32(params); cost = self._f32(cost)
+        Cn, P = params.shape
+        assert mean.is_cuda and std.is_cuda and mean.dtype == torch.float32 and std.dtype == torch.float32
+        std_floor = self._f32(std_floor)
+        out_best = out_best if out_best is not None else torch.empty((P + 1,), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_cem_refit(self._handle, _ptr(params), _ptr(cost), Cn, P, int(n_elite), float(alpha),
+                                             _ptr(std_floor), _ptr(mean), _ptr(std), _ptr(out_best), self._stream())
+        _lib.check(rc, "spi_b200_cem_refit")
+        return out_best
+
+    # ---- measurement ----------------------------------------------------------------------------------
+    def fp32_peak(self, iters: int = 4096):
+        tf, ms = C.c_float(), C.c_float()
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_fp32_peak(int(iters), C.byref(tf), C.byref(ms), self._stream())
+        _lib.check(rc, "spi_b200_fp32_peak")
+        return float(tf.value), float(ms.value)
+
+    def launch_count(self) -> int:
+        return int(self.lib.spi_b200_launch_count())
