@@ -229,6 +229,13 @@ int spi_b200_fp32_peak(int iters, float* out_tflops, float* out_ms, void* cuda_s
 /* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
 long long spi_b200_launch_count(void);
 
+/* Roofline instrumentation: when enabled, every launch of the rollout kernel is
+ * bracketed by a pair of CUDA events recorded on the launching stream.  spi_b200_timing_read
+ * synchronises on the recorded events and returns the summed kernel time and the launch count
+ * since the last reset; `reset` != 0 clears the accumulator.  Off by default (zero overhead).   */
+int spi_b200_timing_enable(spi_b200_model* model, int enable);
+int spi_b200_timing_read(spi_b200_model* model, double* out_total_ms, long long* out_launches, int reset);
+
 #ifdef __cplusplus
 }
 #endif

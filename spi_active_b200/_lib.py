@@ -77,6 +77,8 @@ SIGNATURES = {
                                       _V, _V]),
     "spi_b200_weighted_cost": (C.c_int, [_V, _V, C.c_int, C.c_float, C.c_float, C.c_float, _V, _V]),
     "spi_b200_fp32_peak": (C.c_int, [C.c_int, _F, _F, _V]),
+    "spi_b200_timing_enable": (C.c_int, [_V, C.c_int]),
+    "spi_b200_timing_read": (C.c_int, [_V, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),
 }
 
 

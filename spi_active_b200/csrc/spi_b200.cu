@@ -8,6 +8,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "aba_leg.cuh"
 
@@ -405,6 +406,11 @@ struct spi_b200_model {
   // staging for the *_host entry point
   char* d_stage = nullptr; size_t d_stage_cap = 0;
   char* h_stage = nullptr; size_t h_stage_cap = 0;
+  // roofline instrumentation: event pairs around every rollout-kernel launch (spi_b200_timing_*)
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_pool;   // recycled events
+  std::vector<cudaEvent_t> ev_pending;  // start0, stop0, start1, stop1, ...
+  double timing_ms = 0.0; long long timing_launches = 0;
 };
 
 namespace {
@@ -494,6 +500,28 @@ int blob_to_model(const float* b, int n, DeviceModel* M) {
   return 0;
 }
 
+int timing_events(spi_b200_model* m, cudaEvent_t* e0, cudaEvent_t* e1) {
+  cudaEvent_t* out[2] = {e0, e1};
+  for (auto* e : out) {
+    if (!m->ev_pool.empty()) { *e = m->ev_pool.back(); m->ev_pool.pop_back(); }
+    else CUDA_OK(cudaEventCreate(e));
+  }
+  return 0;
+}
+
+// drain the pending event pairs into the accumulator (synchronises on each stop event)
+int timing_drain(spi_b200_model* m) {
+  for (size_t i = 0; i + 1 < m->ev_pending.size(); i += 2) {
+    float ms = 0.f;
+    CUDA_OK(cudaEventSynchronize(m->ev_pending[i + 1]));
+    CUDA_OK(cudaEventElapsedTime(&ms, m->ev_pending[i], m->ev_pending[i + 1]));
+    m->timing_ms += ms; m->timing_launches += 1;
+    m->ev_pool.push_back(m->ev_pending[i]); m->ev_pool.push_back(m->ev_pending[i + 1]);
+  }
+  m->ev_pending.clear();
+  return 0;
+}
+
 int launch_rollout(spi_b200_model* m, bool record, const float* params, int C, int P, const int* param_ids,
                    const float* seg_init, const float* seg_actions, const float* seg_target, const float* seg_gains,
                    const unsigned char* seg_mask, int S, int H, int decimation, int motor_model, unsigned flags,
@@ -522,8 +550,17 @@ int launch_rollout(spi_b200_model* m, bool record, const float* params, int C, i
     if (int rc = ensure(&m->d_bad, &m->bad_cap, (size_t)C)) return rc;
     CUDA_OK(cudaMemsetAsync(m->d_bad, 0, (size_t)C * sizeof(int), st));
     A.partial = m->d_partial; A.bad = m->d_bad; A.per_seg = out_per_seg;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (m->timing) {
+      if (int rc = timing_events(m, &e0, &e1)) return rc;
+      CUDA_OK(cudaEventRecord(e0, st));
+    }
     rollout_kernel<false><<<(unsigned)n_cta, kThreads, 0, st>>>(A);
     if (int rc = check_launch("rollout_kernel")) return rc;
+    if (m->timing) {
+      CUDA_OK(cudaEventRecord(e1, st));
+      m->ev_pending.push_back(e0); m->ev_pending.push_back(e1);
+    }
     const int n = C * 3;
     reduce_cost_kernel<<<(n + 127) / 128, 128, 0, st>>>(m->d_partial, m->d_bad, seg_mask, C, S, A.n_warp_per_cand,
                                                         cost_denominator, out_cost, out_status);
@@ -574,7 +611,24 @@ int spi_b200_model_destroy(spi_b200_model* m) {
   if (m->d_rank) cudaFree(m->d_rank);
   if (m->d_stage) cudaFree(m->d_stage);
   if (m->h_stage) cudaFreeHost(m->h_stage);
+  for (auto e : m->ev_pool) cudaEventDestroy(e);
+  for (auto e : m->ev_pending) cudaEventDestroy(e);
   delete m;
+  return 0;
+}
+
+int spi_b200_timing_enable(spi_b200_model* m, int enable) {
+  if (!m) return fail(-1, "model handle is NULL");
+  m->timing = enable != 0;
+  return 0;
+}
+
+int spi_b200_timing_read(spi_b200_model* m, double* out_total_ms, long long* out_launches, int reset) {
+  if (!m) return fail(-1, "model handle is NULL");
+  if (int rc = timing_drain(m)) return rc;
+  if (out_total_ms) *out_total_ms = m->timing_ms;
+  if (out_launches) *out_launches = m->timing_launches;
+  if (reset) { m->timing_ms = 0.0; m->timing_launches = 0; }
   return 0;
 }
 

@@ -253,5 +253,16 @@ class RolloutEngine:
         _lib.check(rc, "spi_b200_fp32_peak")
         return float(tf.value), float(ms.value)
 
+    def timing_enable(self, on: bool = True) -> None:
+        """Bracket every rollout-kernel launch with CUDA events on its stream (roofline instrumentation)."""
+        _lib.check(self.lib.spi_b200_timing_enable(self._handle, int(bool(on))), "spi_b200_timing_enable")
+
+    def timing_read(self, reset: bool = True):
+        """-> (summed rollout-kernel ms, launches) since the last reset; synchronises on the events."""
+        ms, n = C.c_double(), C.c_longlong()
+        _lib.check(self.lib.spi_b200_timing_read(self._handle, C.byref(ms), C.byref(n), int(reset)),
+                   "spi_b200_timing_read")
+        return float(ms.value), int(n.value)
+
     def launch_count(self) -> int:
         return int(self.lib.spi_b200_launch_count())

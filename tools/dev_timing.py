@@ -2,7 +2,7 @@
 import sys, time
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-sys.path.insert(0, str(Path(__file__).resolve().parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tests"))
 import numpy as np, torch
 from spi_active_b200.engine import RolloutEngine
 from spi_active_b200 import recorders
