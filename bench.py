@@ -198,7 +198,7 @@ def run_reference(args):
     packed = pack_numpy(ds)
     cfg = cem.default_full_config()
     # each step = a bounded sample of the N x 4096-candidate population; sized so K + W steps end in minutes
-    budget_s = 120.0
+    budget_s = float(os.environ.get("SPI_BENCH_REFERENCE_BUDGET_S", "120"))
     n_cand = calibrate_oracle(blob, packed, cfg, budget_s / max(1, args.steps + args.warmup))
     n_cand = min(n_cand, CANDIDATES_PER_GPU * args.gpus)
     for w in range(args.warmup):

@@ -162,3 +162,44 @@ def count_flops(blob, params, param_ids, init, actions, target, decimation=4, mo
 
 def num_threads() -> int:
     return int(lib().spi_oracle_num_threads())
+
+
+# ---- numpy restatements of the reference's small torch reductions (pinned by tests/golden) -----------
+def fim_reward(root_states, dof_pos, env_origins, num_main, param_dim, delta):
+    """ActiveSysId_OpenLoop._reward_fisher_information_matrix
+    (spigym/envs/sysid/active_sysid_openloop.py:402-426): envs interleaved [main, aux_1..aux_P] per group,
+    J = [(root13_main - root13_aux) / delta | (q_main - q_aux) / delta] with origin-compensated positions,
+    reward = trace(J^T J) repeated to all P+1 envs of the group.  Returns (reward[N], JJt[M,P,P])."""
+    root = np.asarray(root_states, dtype=np.float64).reshape(num_main, param_dim + 1, 13).copy()
+    dof = np.asarray(dof_pos, dtype=np.float64).reshape(num_main, param_dim + 1, 12)
+    org = np.asarray(env_origins, dtype=np.float64).reshape(num_main, param_dim + 1, 3)
+    root[..., :3] -= org
+    x = np.concatenate([root, dof], axis=2)              # [M, P+1, 25]
+    J = (x[:, 0:1, :] - x[:, 1:, :]) / float(delta)      # [M, P, 25]
+    trace = (J * J).sum(axis=(1, 2))
+    JJt = np.einsum("mpd,mqd->mpq", J, J)
+    return np.repeat(trace, param_dim + 1), JJt
+
+
+def fim_states(root_states, dof_pos, env_origins, num_main, param_dim):
+    """Pack (root13 origin-compensated, q12) -> states[M, P+1, 25], the input layout of spi_b200_fim_reward."""
+    root = np.asarray(root_states, dtype=np.float32).reshape(num_main, param_dim + 1, 13).copy()
+    root[..., :3] -= np.asarray(env_origins, dtype=np.float32).reshape(num_main, param_dim + 1, 3)
+    dof = np.asarray(dof_pos, dtype=np.float32).reshape(num_main, param_dim + 1, 12)
+    return np.concatenate([root, dof], axis=2)
+
+
+def weighted_cost(cost3, weights=(10.0, 5.0, 1.0)):
+    """scripts/mass_landscape.py:162-164 / scripts/mass_opt.py:62-76."""
+    c = np.asarray(cost3, dtype=np.float64)
+    return c[..., 0] * weights[0] + c[..., 1] * weights[1] + c[..., 2] * weights[2]
+
+
+def quat_rotate_inverse(q_xyzw, v):
+    """spigym/utils/torch_utils.py:83-92 — rotate v by the inverse of the unit quaternion q (x,y,z,w)."""
+    q = np.asarray(q_xyzw, dtype=np.float64); v = np.asarray(v, dtype=np.float64)
+    w = q[:, 3:4]; u = q[:, :3]
+    a = v * (2.0 * w ** 2 - 1.0)
+    b = np.cross(u, v) * w * 2.0
+    c = u * (u * v).sum(axis=1, keepdims=True) * 2.0
+    return a - b + c

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -82,8 +83,8 @@ SPI_DEV bool lane_finite(const LaneState& s) {
 
 // The fused hot path: reset -> H x (clip, decimation x (PD + motor model, nsub x ABA sub-step)) -> errors
 // -> per-warp masked partial sums.  4 lanes per (candidate, segment) rollout.
-template <bool RECORD>
-__global__ void __launch_bounds__(kThreads) rollout_kernel(const EvalArgs A) {
+template <bool RECORD, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) rollout_kernel(const EvalArgs A) {
   const DeviceModel& M = *A.model;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int leg = lane & 3;
@@ -555,7 +556,10 @@ int launch_rollout(spi_b200_model* m, bool record, const float* params, int C, i
       if (int rc = timing_events(m, &e0, &e1)) return rc;
       CUDA_OK(cudaEventRecord(e0, st));
     }
-    rollout_kernel<false><<<(unsigned)n_cta, kThreads, 0, st>>>(A);
+    static const int variant = getenv("SPI_B200_MINB") ? atoi(getenv("SPI_B200_MINB")) : 2;
+    if (variant == 3) rollout_kernel<false, 3><<<(unsigned)n_cta, kThreads, 0, st>>>(A);
+    else if (variant == 4) rollout_kernel<false, 4><<<(unsigned)n_cta, kThreads, 0, st>>>(A);
+    else rollout_kernel<false, 2><<<(unsigned)n_cta, kThreads, 0, st>>>(A);
     if (int rc = check_launch("rollout_kernel")) return rc;
     if (m->timing) {
       CUDA_OK(cudaEventRecord(e1, st));
@@ -567,7 +571,7 @@ int launch_rollout(spi_b200_model* m, bool record, const float* params, int C, i
     return check_launch("reduce_cost_kernel");
   }
   A.out_states = out_states;
-  rollout_kernel<true><<<(unsigned)n_cta, kThreads, 0, st>>>(A);
+  rollout_kernel<true, 2><<<(unsigned)n_cta, kThreads, 0, st>>>(A);
   return check_launch("rollout_kernel<record>");
 }
 

@@ -1,0 +1,299 @@
+"""Generate the committed golden vectors under tests/golden/ by EXECUTING THE REFERENCE'S OWN PYTHON.
+
+Run in the build container (it needs /root/reference; the GPU box and the test-suite never do):
+
+    python tests/golden/make_golden.py
+
+The reference (LeCAR-Lab/SPI-Active) is pure Python around the closed-source Isaac Gym binary, and its
+hot-path modules import hydra / omegaconf / optuna / matplotlib / isaacgym, none of which exist here.
+Those imports are replaced by inert stubs (MagicMock modules); every function exercised below is then the
+reference's real, unmodified code object, called with plain torch tensors:
+
+  torques.npz        LeggedRobotBase._pre_physics_step + _compute_torques
+                         (spigym/envs/legged_base_task/legged_robot_base.py:185-198, 529-560)
+                     go2_omni_interface._compute_torques, hip x0.5
+                         (spigym/envs/locomotion/go2_omni.py:423-465)
+                     ActiveSysId_OpenLoop.act2tau_scalar / act2tau_vec3 / act2tau_vec3_tanh
+                         (spigym/envs/sysid/active_sysid_openloop.py:356-400)
+  windowing.npz      scripts/eval.py:101-171 load_dataset on two small synthetic recordings
+  fim.npz            ActiveSysId_OpenLoop._reward_fisher_information_matrix (:402-426)
+  cost.npz           scripts/mass_opt.py:62-76 compute_cost; mass_landscape.py COST_COEFF / argmin (:162-171)
+  quat.npz           spigym/utils/torch_utils.py quat_rotate_inverse / quat_rotate (:49-92)
+  mass_sweep.npz     scripts/mass_landscape.py:111-128 mass_sweep -> scripts/eval.py:204-214 apply_base_mass
+                     -> :217-310 evaluate_batch -> LeggedRobotBase._pre_physics_step/_physics_step/
+                     _apply_force_in_physics_step/_compute_torques, all real, driving tests/oracle_sim.OracleSim
+                     (our CPU oracle as the physics engine in place of PhysX).  Pins the replay / masking /
+                     averaging / PD-gain / control-decimation semantics end to end, including quirks D2
+                     (chunk-dependent eval_mask) and D3 (gains of row 0 of each chunk).
+
+What this cannot pin is the rigid-body physics itself: PhysX is not available.
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+import tempfile
+from pathlib import Path
+from types import SimpleNamespace
+from unittest import mock
+
+import numpy as np
+import torch
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+REF = Path("/root/reference")
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+STUBBED = ["hydra", "hydra.core", "hydra.core.config_store", "hydra.utils", "hydra.core.hydra_config", "omegaconf",
+           "matplotlib", "matplotlib.pyplot", "matplotlib.cm", "matplotlib.colors", "mpl_toolkits",
+           "mpl_toolkits.mplot3d", "termcolor", "easydict", "isaacgym", "optuna", "optuna.samplers", "loguru", "rich",
+           "rich.progress", "ipdb", "pynput"]
+
+
+def import_reference():
+    if not REF.exists():
+        raise SystemExit("/root/reference is not present: golden vectors can only be regenerated in the build container")
+    sys.path.insert(0, str(REF))
+    sys.path.insert(0, str(REF / "isaac_utils"))
+    for name in STUBBED:
+        try:
+            importlib.import_module(name)
+        except Exception:
+            sys.modules[name] = mock.MagicMock(name=name)
+    import warnings
+    warnings.filterwarnings("ignore", category=SyntaxWarning)
+    import scripts.eval as ev
+    import scripts.mass_landscape as ml
+    import scripts.mass_opt as mo
+    from spigym.envs.legged_base_task.legged_robot_base import LeggedRobotBase
+    from spigym.envs.locomotion.go2_omni import go2_omni_interface
+    from spigym.envs.sysid.active_sysid_openloop import ActiveSysId_OpenLoop
+    import spigym.utils.torch_utils as tu
+    return SimpleNamespace(ev=ev, ml=ml, mo=mo, LeggedRobotBase=LeggedRobotBase, go2_omni=go2_omni_interface,
+                           ActiveSysId=ActiveSysId_OpenLoop, tu=tu)
+
+
+def control_config(decimation=4):
+    """The values of spigym/config/robot/go2/go2.yaml:107-109 and config/simulator/isaacgym.yaml:16 as the
+    attribute tree the reference methods read."""
+    return SimpleNamespace(
+        robot=SimpleNamespace(control=SimpleNamespace(action_scale=0.25, action_clip_value=20.0, control_type="P",
+                                                      clip_torques=True)),
+        domain_rand=SimpleNamespace(randomize_ctrl_delay=False, randomize_torque_rfi=False),
+        simulator=SimpleNamespace(config=SimpleNamespace(sim=SimpleNamespace(control_decimation=decimation))),
+    )
+
+
+# ------------------------------------------------------------------------------------------------
+def gen_torques(R, rng):
+    from spi_active_b200 import go2_model as gm
+    m = gm.go2_nominal()
+    N = 64
+    actions = rng.uniform(-30, 30, (N, 12)).astype(np.float32)
+    q = rng.uniform(-2.5, 2.5, (N, 12)).astype(np.float32)
+    qd = rng.uniform(-25, 25, (N, 12)).astype(np.float32)
+    kp = rng.uniform(15, 40, 12).astype(np.float32)
+    kd = rng.uniform(0.3, 1.2, 12).astype(np.float32)
+    self = SimpleNamespace(
+        config=control_config(), device="cpu", num_envs=N, log_dict={},
+        p_gains=torch.from_numpy(kp), d_gains=torch.from_numpy(kd),
+        _kp_scale=torch.ones(N, 12), _kd_scale=torch.ones(N, 12),
+        default_dof_pos=torch.tensor(m.q_default, dtype=torch.float32).unsqueeze(0),
+        torque_limits=torch.tensor(m.torque_limit, dtype=torch.float32),
+        simulator=SimpleNamespace(dof_pos=torch.from_numpy(q), dof_vel=torch.from_numpy(qd)),
+    )
+    R.LeggedRobotBase._pre_physics_step(self, torch.from_numpy(actions.copy()))
+    clipped = self.actions_after_delay.clone()
+    tau_base = R.LeggedRobotBase._compute_torques(self, clipped.clone())
+    tau_omni = R.go2_omni._compute_torques(self, clipped.clone())
+    out = dict(actions=actions, q=q, qd=qd, kp=kp, kd=kd, clipped_actions=clipped.numpy(),
+               tau_base=tau_base.numpy(), tau_omni=tau_omni.numpy())
+    # motor models on top of the clipped nominal torques (active_sysid_openloop.py:184-186)
+    g_scalar = rng.uniform(0.6, 1.3, N).astype(np.float32)
+    g3 = rng.uniform(0.6, 1.3, (N, 3)).astype(np.float32)
+    a3 = rng.uniform(8.0, 40.0, (N, 3)).astype(np.float32)
+    out["scalar_gain"] = g_scalar
+    out["vec3_gain"] = g3
+    out["tanh_a"] = a3
+    for label, nominal in (("base", tau_base), ("omni", tau_omni)):
+        out[f"tau_scalar_{label}"] = R.ActiveSysId.act2tau_scalar(self, nominal.clone(), scalar_gain=g_scalar.tolist()).numpy()
+        out[f"tau_vec3_{label}"] = R.ActiveSysId.act2tau_vec3(self, nominal.clone(), hip_gain=g3[:, 0].tolist(),
+                                                              thigh_gain=g3[:, 1].tolist(), calf_gain=g3[:, 2].tolist()).numpy()
+        self.params_dict = {"motor_model_hip_a": {"value": a3[:, 0].tolist()},
+                            "motor_model_thigh_a": {"value": a3[:, 1].tolist()},
+                            "motor_model_calf_a": {"value": a3[:, 2].tolist()}}
+        out[f"tau_tanh_{label}"] = R.ActiveSysId.act2tau_vec3_tanh(self, nominal.clone()).numpy()
+    np.savez(HERE / "torques.npz", **out)
+    print("torques.npz", {k: v.shape for k, v in out.items() if k.startswith("tau")})
+
+
+def synthetic_recording(rng, T):
+    quat = rng.standard_normal((T, 4)); quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    return dict(joint_positions=rng.standard_normal((T, 12)).astype(np.float32),
+                joint_velocities=rng.standard_normal((T, 12)).astype(np.float32),
+                joint_torques=rng.standard_normal((T, 12)).astype(np.float32),
+                actions=rng.standard_normal((T, 12)),  # float64 on purpose: load_dataset casts (eval.py:121)
+                base_positions=rng.standard_normal((T, 3)).astype(np.float32),
+                base_orientations=quat.astype(np.float32),
+                base_linear_velocities=rng.standard_normal((T, 3)).astype(np.float32),
+                base_angular_velocities=rng.standard_normal((T, 3)).astype(np.float32),
+                timestamps=np.arange(T) * 0.02, sim_duration=T * 0.02, data_frequency=50, robot_type="go2",
+                pd_gain_kp=np.full(12, 20.0 + T, np.float32), pd_gain_kd=np.full(12, 0.5 + 0.01 * T, np.float32))
+
+
+def gen_windowing(R, rng):
+    recs = [synthetic_recording(rng, 12), synthetic_recording(rng, 9)]
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        paths = []
+        for i, r in enumerate(recs):
+            p = Path(d) / f"rec{i}.npz"
+            np.savez(p, **r)
+            paths.append(p)
+            for k, v in r.items():
+                out[f"in{i}_{k}"] = np.asarray(v)
+        for H in (3, 5):
+            total, ds = R.ev.load_dataset(paths, H)
+            out[f"H{H}_total"] = np.int64(total)
+            for k, v in ds.items():
+                out[f"H{H}_{k}"] = np.asarray(v)
+    np.savez(HERE / "windowing.npz", **out)
+    print("windowing.npz", int(out["H3_total"]), int(out["H5_total"]))
+
+
+def gen_fim(R, rng):
+    M, P = 6, 4
+    N = M * (P + 1)
+    root = rng.standard_normal((N, 13)).astype(np.float32)
+    dof = rng.standard_normal((N, 12)).astype(np.float32)
+    origins = rng.standard_normal((N, 3)).astype(np.float32)
+    idx = torch.arange(0, N).view(M, P + 1)
+    self = SimpleNamespace(simulator=SimpleNamespace(robot_root_states=torch.from_numpy(root), dof_pos=torch.from_numpy(dof)),
+                           env_origins=torch.from_numpy(origins), main_idx=idx[:, 0:1], aux_idx=idx[:, 1:],
+                           delta_param=0.1, param_dim=P)
+    rew = R.ActiveSysId._reward_fisher_information_matrix(self).numpy()
+    np.savez(HERE / "fim.npz", root=root, dof=dof, origins=origins, M=M, P=P, delta=np.float32(0.1), reward=rew)
+    print("fim.npz", rew.shape)
+
+
+def gen_cost(R, rng):
+    costs = rng.uniform(0, 0.1, (20, 3)).astype(np.float32)
+    totals = np.array([R.mo.compute_cost(row.astype(np.float64)) for row in costs], dtype=np.float64)
+    w = R.ml.COST_COEFF
+    np.savez(HERE / "cost.npz", costs=costs, totals=totals,
+             weights=np.array([w["base_pos"], w["base_quat"], w["joint_pos"]]),
+             mass_scale_range=np.array([R.ml.MASS_SCALE_MIN, R.ml.MASS_SCALE_MAX]), mass_samples=R.ml.MASS_SAMPLES,
+             max_safe_env_batch=R.ml.MAX_SAFE_ENV_BATCH)
+    print("cost.npz", totals[:3])
+
+
+def gen_quat(R, rng):
+    N = 32
+    q = rng.standard_normal((N, 4)).astype(np.float32); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    v = rng.standard_normal((N, 3)).astype(np.float32)
+    out = dict(q=q, v=v, rotate_inverse=R.tu.quat_rotate_inverse(torch.from_numpy(q), torch.from_numpy(v)).numpy())
+    if hasattr(R.tu, "quat_rotate"):
+        out["rotate"] = R.tu.quat_rotate(torch.from_numpy(q), torch.from_numpy(v)).numpy()
+    np.savez(HERE / "quat.npz", **out)
+    print("quat.npz")
+
+
+# ------------------------------------------------------------------------------------------------
+def make_harness_env(R, num_envs):
+    """An env object whose control path is the reference's real code and whose simulator is OracleSim."""
+    from oracle_sim import OracleSim
+    from spi_active_b200 import go2_model as gm
+    m = gm.go2_nominal()
+
+    class HarnessEnv:
+        _pre_physics_step = R.LeggedRobotBase._pre_physics_step
+        _physics_step = R.LeggedRobotBase._physics_step
+        _apply_force_in_physics_step = R.LeggedRobotBase._apply_force_in_physics_step
+        _compute_torques = R.LeggedRobotBase._compute_torques
+
+        def render(self):
+            pass
+
+        def step(self, actor_state):
+            # LeggedRobotBase.step (:169-183) without _post_physics_step: that only refreshes the tensors
+            # and computes rewards / observations / resets that evaluate_batch discards (terminations are
+            # off in the replay config: SURVEY.md §8a row 7)
+            self._pre_physics_step(actor_state["actions"])
+            self._physics_step()
+            self.simulator.refresh_sim_tensors()
+
+        def reset_all(self):
+            # base_task.py:90-100 randomises the state and burns one env step; evaluate_batch overwrites
+            # the state right after, so it has no observable effect (quirk D5)
+            pass
+
+    env = HarnessEnv()
+    N = num_envs
+    env.config = control_config()
+    env.device, env.num_envs, env.dim_actions, env.log_dict = "cpu", N, 12, {}
+    env.simulator = OracleSim(N, m)
+    env.p_gains = torch.tensor(m.kp, dtype=torch.float32)
+    env.d_gains = torch.tensor(m.kd, dtype=torch.float32)
+    env._kp_scale, env._kd_scale = torch.ones(N, 12), torch.ones(N, 12)
+    env.default_dof_pos = torch.tensor(m.q_default, dtype=torch.float32).unsqueeze(0)
+    env.torque_limits = torch.tensor(m.torque_limit, dtype=torch.float32)
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt)
+    env.torques, env.actions, env.last_actions, env.actions_after_delay = z(N, 12), z(N, 12), z(N, 12), z(N, 12)
+    env.last_dof_vel, env.feet_air_time = z(N, 12), z(N, 4)
+    env.episode_length_buf, env.reset_buf = z(N, dt=torch.long), z(N, dt=torch.long)
+    return env
+
+
+def gen_mass_sweep(R, rng):
+    import synth
+    from spi_active_b200 import recorders
+    out = {}
+    # three short recordings with different PD gains per file (exercises D3), recorded with the oracle
+    recs = []
+    for name, steps, kp, kd in (("jump", 40, 25.0, 0.6), ("sine", 33, 22.0, 0.5), ("stand", 21, 28.0, 0.7)):
+        r = dict(synth.recording(name, steps))
+        r["pd_gain_kp"] = np.full(12, kp, np.float32)
+        r["pd_gain_kd"] = np.full(12, kd, np.float32)
+        r.update(timestamps=np.arange(steps) * 0.02, sim_duration=steps * 0.02, data_frequency=50, robot_type="go2")
+        recs.append(r)
+    scales = np.array([0.6, 1.0, 1.7])
+    with tempfile.TemporaryDirectory() as d:
+        paths = []
+        for i, r in enumerate(recs):
+            p = Path(d) / f"rec{i}.npz"
+            np.savez(p, **r)
+            paths.append(p)
+            for k in ("joint_positions", "joint_velocities", "actions", "base_positions", "base_orientations",
+                      "base_linear_velocities", "base_angular_velocities", "pd_gain_kp", "pd_gain_kd"):
+                out[f"rec{i}_{k}"] = np.asarray(r[k])
+        for H in (5, 3):
+            total, ds_np = R.ev.load_dataset(paths, H)
+            for B in (16, 32, 4096):
+                batch = min(B, total, R.ml.MAX_SAFE_ENV_BATCH)   # mass_landscape.py:146
+                env = make_harness_env(R, batch)
+                dataset = R.ev.to_device(ds_np, env.device)
+                ref_masses = R.ev.capture_reference_masses(env.simulator)
+                res = R.ml.mass_sweep(env, dataset, H, ref_masses, scales)
+                out[f"H{H}_B{B}_costs"] = res
+                out[f"H{H}_B{B}_batch"] = np.int64(batch)
+                print(f"mass_sweep H={H} B={B} (batch {batch}) S={total}:", res.tolist())
+        out["ref_masses"] = ref_masses
+    out["scales"] = scales
+    np.savez(HERE / "mass_sweep.npz", **out)
+
+
+def main():
+    R = import_reference()
+    rng = np.random.default_rng(20251017)
+    gen_torques(R, rng)
+    gen_windowing(R, rng)
+    gen_fim(R, rng)
+    gen_cost(R, rng)
+    gen_quat(R, rng)
+    gen_mass_sweep(R, rng)
+
+
+if __name__ == "__main__":
+    main()
