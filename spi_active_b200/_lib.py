@@ -12,9 +12,10 @@ import subprocess
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libspi_b200.so"
+LIB_PATH = Path(os.environ.get("SPI_B200_LIB", _PKG / "libspi_b200.so"))  # override: kernel experiments only
 SOURCES = [_PKG / "csrc" / "spi_b200.cu"]
-HEADERS = [_PKG / "csrc" / "aba_leg.cuh", _PKG.parent / "include" / "spi_b200.h"]
+HEADERS = [_PKG / "csrc" / "aba_leg.cuh", _PKG / "csrc" / "go2_ws.cuh", _PKG / "csrc" / "rollout_ws.cuh",
+           _PKG.parent / "include" / "spi_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
 

@@ -1,0 +1,754 @@
+// go2_ws.cuh — warp-specialised floating-base articulated-body dynamics for Go2-family quadrupeds.
+//
+// Mapping: one CTA = 32 rollouts (lanes) x 5 roles (warps):
+//     roles 0..3  : leg FL / FR / RL / RR — a 3-joint chain hip(x) - thigh(y) - calf(y), lane-private
+//     role  4     : base — sums the four hips' articulated inertias / bias forces, solves the 6x6 base
+//                   system once per rollout, integrates the floating base
+// The roles exchange 27 + 22 floats per rollout per sub-step through shared memory (two CTA barriers per
+// sub-step).  Compared with the leg-per-lane kernel (aba_leg.cuh) nothing is computed redundantly, the
+// per-leg constants are warp-uniform (they are read straight from the kernel-parameter constant bank as
+// FFMA operands and cost no registers), the calf's constant joint projection is precomputed, and the
+// joint-origin sparsity of the Go2 chain (hip r = (x,y,0), thigh r = (0,y,0), calf r = (0,0,z)) is
+// compiled in.
+//
+// Everything here is __host__ __device__ so that tests/host_emulation can run the very same arithmetic
+// on the CPU, role by role, against the oracle (tests/test_ws_emulation.py) — the only way to debug
+// device code in a container without a GPU.
+//
+// Same published algorithm as the oracle (Featherstone, RBDA 2008, Table 9.4), written independently.
+#pragma once
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define WS_HD __host__ __device__ __forceinline__
+#else
+#include <cmath>
+#define WS_HD inline
+#endif
+
+#include "../../include/spi_b200.h"
+
+namespace ws {
+
+// symmetric 3x3 stored as (xx, yy, zz, xy, xz, yz)
+WS_HD constexpr int sidx(int i, int j) { return (i == j) ? i : ((i + j == 1) ? 3 : ((i + j == 2) ? 4 : 5)); }
+
+// ---- fast scalar helpers -------------------------------------------------------------------------------
+WS_HD float rcp_fast(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * fmaf(-x, r, 2.0f);   // one Newton step: full fp32 accuracy without the IEEE slow path
+#else
+  return 1.0f / x;
+#endif
+}
+WS_HD float rsqrt_fast(float x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / std::sqrt(x);
+#endif
+}
+WS_HD void sincos_joint(float q, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+#if defined(SPI_WS_FAST_SINCOS)
+  // MUFU path: reduce to [-pi, pi] (joint angles are bounded, |q| < ~5), abs error <= 2^-21
+  const float k = rintf(q * 0.15915494309189535f);
+  float r = fmaf(k, -6.2831854820251465f, q);
+  r = fmaf(k, 1.7484555314695172e-07f, r);
+  __sincosf(r, s, c);
+#else
+  sincosf(q, s, c);
+#endif
+#else
+  *s = std::sin(q); *c = std::cos(q);
+#endif
+}
+
+// ---- constants -------------------------------------------------------------------------------------------
+struct SimK {
+  float dt, gz, action_scale, action_clip, kn, cn, mu, dtan, radius, veps2;
+  int nsub;
+};
+
+struct LegK {
+  float m[3];        // body masses (hip, thigh, calf + foot)
+  float h[3][3];     // m * com
+  float Io[3][6];    // inertia about the link origin, symmetric storage
+  float rh[2];       // hip joint origin in the base frame (x, y);   z == 0
+  float rt;          // thigh joint origin in the hip frame, y;      x == z == 0
+  float rc;          // calf joint origin in the thigh frame, z;     x == y == 0
+  float foot[3];     // foot sphere centre in the calf frame
+  float qdef[3], tlim[3];
+  // the calf is a leaf: its articulated inertia is its rigid inertia, so the joint projection
+  // Ia = IA - U U^T / D (axis y) is a per-leg constant
+  float cUa[3], cUl[3], cDinv;
+  float cIbb, cIbc, cIcc;   // (b, c) = (z, x) block of the projected rotational inertia
+  float cHb[3], cHc[3];     // rows b, c of the projected coupling block
+  float cMa[6];             // projected linear block, symmetric storage
+};
+
+struct ModelK {
+  SimK sim;
+  float base_inertial[10];
+  float lumps[2][10];
+  LegK leg[4];
+  float kp[12], kd[12];
+};
+
+// joint-origin sparsity masks (bit i set <=> component i may be non-zero)
+constexpr int kMaskHip = 0b011, kMaskThigh = 0b010, kMaskCalf = 0b100;
+
+// the joint-origin vector of joint J of the chain as a 3-array (masked components are never read)
+WS_HD void joint_r(const LegK& L, int j, float* r) {
+  if (j == 0) { r[0] = L.rh[0]; r[1] = L.rh[1]; r[2] = 0.f; }
+  else if (j == 1) { r[0] = 0.f; r[1] = L.rt; r[2] = 0.f; }
+  else { r[0] = 0.f; r[1] = 0.f; r[2] = L.rc; }
+}
+
+// ---- small vector helpers ------------------------------------------------------------------------------
+WS_HD void cross3(const float* a, const float* b, float* o) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+WS_HD void sym_mulv(const float* S, const float* v, float* o) {
+  o[0] = S[0] * v[0] + S[3] * v[1] + S[4] * v[2];
+  o[1] = S[3] * v[0] + S[1] * v[1] + S[5] * v[2];
+  o[2] = S[4] * v[0] + S[5] * v[1] + S[2] * v[2];
+}
+// o += a x r   with r sparse
+template <int MASK> WS_HD void add_cross_ar(const float* a, const float* r, float* o) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const int j = (i + 1) % 3, k = (i + 2) % 3;
+    if ((MASK >> k) & 1) o[i] = fmaf(a[j], r[k], o[i]);
+    if ((MASK >> j) & 1) o[i] = fmaf(-a[k], r[j], o[i]);
+  }
+}
+// o += r x f   with r sparse
+template <int MASK> WS_HD void add_cross_rf(const float* r, const float* f, float* o) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const int j = (i + 1) % 3, k = (i + 2) % 3;
+    if ((MASK >> j) & 1) o[i] = fmaf(r[j], f[k], o[i]);
+    if ((MASK >> k) & 1) o[i] = fmaf(-r[k], f[j], o[i]);
+  }
+}
+
+// planar rotation helpers for a joint about coordinate axis AX with (a, b, c) cyclic:
+//   R e_a = e_a, R e_b = cs e_b + sn e_c, R e_c = -sn e_b + cs e_c      (child -> parent)
+template <int AX> struct Ax { static constexpr int a = AX, b = (AX + 1) % 3, c = (AX + 2) % 3; };
+template <int AX> WS_HD void rot_up(float cs, float sn, const float* v, float* o) {  // R v
+  o[Ax<AX>::a] = v[Ax<AX>::a];
+  o[Ax<AX>::b] = cs * v[Ax<AX>::b] - sn * v[Ax<AX>::c];
+  o[Ax<AX>::c] = sn * v[Ax<AX>::b] + cs * v[Ax<AX>::c];
+}
+template <int AX> WS_HD void rot_down(float cs, float sn, const float* v, float* o) {  // R^T v
+  o[Ax<AX>::a] = v[Ax<AX>::a];
+  o[Ax<AX>::b] = cs * v[Ax<AX>::b] + sn * v[Ax<AX>::c];
+  o[Ax<AX>::c] = cs * v[Ax<AX>::c] - sn * v[Ax<AX>::b];
+}
+
+struct Twist { float a[3]; float l[3]; };   // motion [w; v] or force [n; f]
+
+// what a joint keeps between the inward and the acceleration pass
+struct Keep {
+  float cs, sn;
+  float cab, cac, clb, clc;  // velocity-product acceleration c = v x (e_a qd): components b, c
+  float Ua[3], Ul[3], dinv, u;
+};
+
+// ---- outward pass for one joint: velocity, velocity-product terms, bias force of the rigid body ---------
+template <int AX, int MASK>
+WS_HD void joint_outward(const Twist& vp, const float* r, float q, float qd, float mass, const float* h,
+                         const float* Io, Twist& v, Keep& k, Twist& pA) {
+  constexpr int a = Ax<AX>::a, b = Ax<AX>::b, c = Ax<AX>::c;
+  sincos_joint(q, &k.sn, &k.cs);
+  float t[3] = {vp.l[0], vp.l[1], vp.l[2]};
+  add_cross_ar<MASK>(vp.a, r, t);
+  rot_down<AX>(k.cs, k.sn, vp.a, v.a);
+  v.a[a] += qd;
+  rot_down<AX>(k.cs, k.sn, t, v.l);
+  k.cab = v.a[c] * qd;  k.cac = -(v.a[b] * qd);
+  k.clb = v.l[c] * qd;  k.clc = -(v.l[b] * qd);
+  // momentum: n = Io w + h x v,  f = m v - h x w ;  pA = [w x n + v x f ; w x f]
+  float n[3], f[3], hv[3], hw[3], t1[3], t2[3];
+  sym_mulv(Io, v.a, n);
+  cross3(h, v.l, hv);
+  cross3(h, v.a, hw);
+#pragma unroll
+  for (int i = 0; i < 3; i++) { n[i] += hv[i]; f[i] = mass * v.l[i] - hw[i]; }
+  cross3(v.a, n, t1);
+  cross3(v.l, f, t2);
+  cross3(v.a, f, pA.l);
+#pragma unroll
+  for (int i = 0; i < 3; i++) pA.a[i] = t1[i] + t2[i];
+}
+
+// articulated inertia [[I, H], [H^T, M]], I and M symmetric
+struct ABI { float I[6]; float H[9]; float M[6]; };
+
+WS_HD void abi_from_rigid(float mass, const float* h, const float* Io, ABI& A) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) A.I[i] = Io[i];
+  A.H[0] = 0.f;   A.H[1] = -h[2]; A.H[2] = h[1];
+  A.H[3] = h[2];  A.H[4] = 0.f;   A.H[5] = -h[0];
+  A.H[6] = -h[1]; A.H[7] = h[0];  A.H[8] = 0.f;
+  A.M[0] = A.M[1] = A.M[2] = mass;
+  A.M[3] = A.M[4] = A.M[5] = 0.f;
+}
+
+// The projected quantities of a joint (row/column a of I and row a of H vanish identically).
+struct Proj { float Ibb, Ibc, Icc, Hb[3], Hc[3], Ma[6]; };
+
+// ---- transform a projected inertia + force to the parent and accumulate -------------------------------
+// pa = pA + Ia c + U u / D must be given; IAp / pAp already hold the parent's own inertia / bias force.
+template <int AX, int MASK>
+WS_HD void project_to_parent(const Proj& P, const float* pa_a, const float* pa_l, float cs, float sn, const float* r,
+                             ABI& IAp, Twist& pAp) {
+  constexpr int a = Ax<AX>::a, b = Ax<AX>::b, c = Ax<AX>::c;
+  // rotate the blocks to parent orientation:  X' = R X R^T
+  //   I: only the (b,c) 2x2 block is non-zero
+  const float t1 = cs * P.Ibb - sn * P.Ibc, t2 = cs * P.Ibc - sn * P.Icc;
+  const float t3 = sn * P.Ibb + cs * P.Ibc, t4 = sn * P.Ibc + cs * P.Icc;
+  const float I2bb = t1 * cs - t2 * sn, I2bc = t1 * sn + t2 * cs, I2cc = t3 * sn + t4 * cs;
+  //   H: rows b, c non-zero
+  float Xb[3], Xc[3], H2b[3], H2c[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) { Xb[j] = cs * P.Hb[j] - sn * P.Hc[j]; Xc[j] = sn * P.Hb[j] + cs * P.Hc[j]; }
+  H2b[a] = Xb[a]; H2b[b] = cs * Xb[b] - sn * Xb[c]; H2b[c] = sn * Xb[b] + cs * Xb[c];
+  H2c[a] = Xc[a]; H2c[b] = cs * Xc[b] - sn * Xc[c]; H2c[c] = sn * Xc[b] + cs * Xc[c];
+  //   M: full symmetric
+  float M2[6];
+  {
+    const float Bbb = cs * P.Ma[sidx(b, b)] - sn * P.Ma[sidx(c, b)], Bbc = cs * P.Ma[sidx(b, c)] - sn * P.Ma[sidx(c, c)];
+    const float Bcb = sn * P.Ma[sidx(b, b)] + cs * P.Ma[sidx(c, b)], Bcc = sn * P.Ma[sidx(b, c)] + cs * P.Ma[sidx(c, c)];
+    M2[sidx(a, a)] = P.Ma[sidx(a, a)];
+    M2[sidx(a, b)] = cs * P.Ma[sidx(a, b)] - sn * P.Ma[sidx(a, c)];
+    M2[sidx(a, c)] = sn * P.Ma[sidx(a, b)] + cs * P.Ma[sidx(a, c)];
+    M2[sidx(b, b)] = cs * Bbb - sn * Bbc;
+    M2[sidx(b, c)] = sn * Bbb + cs * Bbc;
+    M2[sidx(c, c)] = sn * Bcb + cs * Bcc;
+  }
+  // shift the reference point by r:  Hp = H2 + r x M2 ;  Ip = I2 + r x H2^T - Hp r x
+  // (H2 row a is identically zero; masked components of r are skipped at compile time)
+  float Hp[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      float v = (i == b) ? H2b[j] : ((i == c) ? H2c[j] : 0.f);
+      bool have = (i != a);
+      if ((MASK >> i1) & 1) { v = have ? fmaf(r[i1], M2[sidx(i2, j)], v) : r[i1] * M2[sidx(i2, j)]; have = true; }
+      if ((MASK >> i2) & 1) { v = have ? fmaf(-r[i2], M2[sidx(i1, j)], v) : -(r[i2] * M2[sidx(i1, j)]); have = true; }
+      Hp[3 * i + j] = have ? v : 0.f;
+    }
+  }
+  // rows of Hp that are structurally zero: row i is zero iff i == a and neither r[i1] nor r[i2] is present
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = i; j < 3; j++) {
+      // Ip[i][j] = I2[i][j] + (r x H2row_j)_i - (Hprow_i x r)_j
+      float v = 0.f;
+      bool have = false;
+      if (i != a && j != a) {
+        v = (i == b && j == b) ? I2bb : ((i == c && j == c) ? I2cc : I2bc);
+        have = true;
+      }
+      // (r x x)_i = r[i1] x[i2] - r[i2] x[i1],  x = row j of H2 (zero when j == a)
+      if (j != a) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+        const float* x = (j == b) ? H2b : H2c;
+        if ((MASK >> i1) & 1) { v = have ? fmaf(r[i1], x[i2], v) : r[i1] * x[i2]; have = true; }
+        if ((MASK >> i2) & 1) { v = have ? fmaf(-r[i2], x[i1], v) : -(r[i2] * x[i1]); have = true; }
+      }
+      // (y x r)_j = y[j1] r[j2] - y[j2] r[j1],  y = row i of Hp
+      {
+        const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        const bool row_zero = (i == a) && !((MASK >> ((i + 1) % 3)) & 1) && !((MASK >> ((i + 2) % 3)) & 1);
+        if (!row_zero) {
+          if ((MASK >> j2) & 1) { v = have ? fmaf(-Hp[3 * i + j1], r[j2], v) : -(Hp[3 * i + j1] * r[j2]); have = true; }
+          if ((MASK >> j1) & 1) { v = have ? fmaf(Hp[3 * i + j2], r[j1], v) : Hp[3 * i + j2] * r[j1]; have = true; }
+        }
+      }
+      if (have) IAp.I[sidx(i, j)] += v;
+    }
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const bool row_zero = (i == a) && !((MASK >> ((i + 1) % 3)) & 1) && !((MASK >> ((i + 2) % 3)) & 1);
+    if (!row_zero) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) IAp.H[3 * i + j] += Hp[3 * i + j];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) IAp.M[i] += M2[i];
+  // force to the parent
+  float fl[3], fa[3];
+  rot_up<AX>(cs, sn, pa_l, fl);
+  rot_up<AX>(cs, sn, pa_a, fa);
+  add_cross_rf<MASK>(r, fl, fa);
+#pragma unroll
+  for (int i = 0; i < 3; i++) { pAp.a[i] += fa[i]; pAp.l[i] += fl[i]; }
+}
+
+// ---- inward pass for a joint with a state-dependent articulated inertia (hip, thigh) ------------------------
+template <int AX, int MASK>
+WS_HD void joint_inward(const ABI& IA, const Twist& pA, float tau, const float* r, Keep& k, ABI& IAp, Twist& pAp) {
+  constexpr int a = Ax<AX>::a, b = Ax<AX>::b, c = Ax<AX>::c;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { k.Ua[i] = IA.I[sidx(i, a)]; k.Ul[i] = IA.H[3 * a + i]; }
+  k.dinv = rcp_fast(k.Ua[a]);
+  k.u = tau - pA.a[a];
+  float Uad[3], Uld[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) { Uad[i] = k.Ua[i] * k.dinv; Uld[i] = k.Ul[i] * k.dinv; }
+  Proj P;
+  P.Ibb = IA.I[sidx(b, b)] - Uad[b] * k.Ua[b];
+  P.Ibc = IA.I[sidx(b, c)] - Uad[b] * k.Ua[c];
+  P.Icc = IA.I[sidx(c, c)] - Uad[c] * k.Ua[c];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    P.Hb[j] = IA.H[3 * b + j] - Uad[b] * k.Ul[j];
+    P.Hc[j] = IA.H[3 * c + j] - Uad[c] * k.Ul[j];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = i; j < 3; j++) P.Ma[sidx(i, j)] = IA.M[sidx(i, j)] - Uld[i] * k.Ul[j];
+  // pa = pA + Ia c + U u / D     (c has no component along a)
+  const float ud = k.u * k.dinv;
+  float pa_a[3], pa_l[3];
+  pa_a[a] = pA.a[a] + ud * k.Ua[a];
+  pa_a[b] = pA.a[b] + P.Ibb * k.cab + P.Ibc * k.cac + P.Hb[b] * k.clb + P.Hb[c] * k.clc + ud * k.Ua[b];
+  pa_a[c] = pA.a[c] + P.Ibc * k.cab + P.Icc * k.cac + P.Hc[b] * k.clb + P.Hc[c] * k.clc + ud * k.Ua[c];
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+    pa_l[j] = pA.l[j] + P.Hb[j] * k.cab + P.Hc[j] * k.cac + P.Ma[sidx(j, b)] * k.clb + P.Ma[sidx(j, c)] * k.clc + ud * k.Ul[j];
+  project_to_parent<AX, MASK>(P, pa_a, pa_l, k.cs, k.sn, r, IAp, pAp);
+}
+
+// ---- inward pass for the calf (leaf, axis y): the projection is the per-leg constant in LegK -----------------
+WS_HD void calf_inward(const LegK& L, const Twist& pA, float tau, Keep& k, ABI& IAp, Twist& pAp) {
+  constexpr int a = 1, b = 2, c = 0;
+  k.u = tau - pA.a[a];
+  const float ud = k.u * L.cDinv;
+  float pa_a[3], pa_l[3];
+  pa_a[a] = pA.a[a] + ud * L.cUa[a];
+  pa_a[b] = pA.a[b] + L.cIbb * k.cab + L.cIbc * k.cac + L.cHb[b] * k.clb + L.cHb[c] * k.clc + ud * L.cUa[b];
+  pa_a[c] = pA.a[c] + L.cIbc * k.cab + L.cIcc * k.cac + L.cHc[b] * k.clb + L.cHc[c] * k.clc + ud * L.cUa[c];
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+    pa_l[j] = pA.l[j] + L.cHb[j] * k.cab + L.cHc[j] * k.cac + L.cMa[sidx(j, b)] * k.clb + L.cMa[sidx(j, c)] * k.clc +
+              ud * L.cUl[j];
+  Proj P;
+  P.Ibb = L.cIbb; P.Ibc = L.cIbc; P.Icc = L.cIcc;
+#pragma unroll
+  for (int j = 0; j < 3; j++) { P.Hb[j] = L.cHb[j]; P.Hc[j] = L.cHc[j]; }
+#pragma unroll
+  for (int i = 0; i < 6; i++) P.Ma[i] = L.cMa[i];
+  const float r[3] = {0.f, 0.f, L.rc};
+  project_to_parent<1, kMaskCalf>(P, pa_a, pa_l, k.cs, k.sn, r, IAp, pAp);
+}
+
+// ---- outward acceleration pass for one joint --------------------------------------------------------------
+template <int AX, int MASK>
+WS_HD float joint_accel(const Twist& ap, const float* r, const float* Ua, const float* Ul, float dinv, const Keep& k,
+                        Twist& acc) {
+  constexpr int a = Ax<AX>::a, b = Ax<AX>::b, c = Ax<AX>::c;
+  float t[3] = {ap.l[0], ap.l[1], ap.l[2]};
+  add_cross_ar<MASK>(ap.a, r, t);
+  rot_down<AX>(k.cs, k.sn, ap.a, acc.a);
+  rot_down<AX>(k.cs, k.sn, t, acc.l);
+  acc.a[b] += k.cab; acc.a[c] += k.cac;
+  acc.l[b] += k.clb; acc.l[c] += k.clc;
+  const float dotU = Ua[0] * acc.a[0] + Ua[1] * acc.a[1] + Ua[2] * acc.a[2] +
+                     Ul[0] * acc.l[0] + Ul[1] * acc.l[1] + Ul[2] * acc.l[2];
+  const float qdd = (k.u - dotU) * dinv;
+  acc.a[a] += qdd;
+  return qdd;
+}
+
+// number of floats a leg hands to the base role: I(6) H(9) M(6) pA(6)
+constexpr int kLegOut = 27;
+// number of floats the base role hands to the legs: a0(6) R(9) v0(6) pz(1)
+constexpr int kBaseOut = 22;
+constexpr int kBcA0 = 0, kBcR = 6, kBcV0 = 15, kBcPz = 21;
+
+struct LegState { float q[3], qd[3]; };
+struct LegKeep { Keep k1, k2, k3; };
+
+// ---- leg role, phase 1: outward pass, foot contact, inward pass -> 27 floats for the base ------------------
+// Rv0[22] = the base broadcast (a0 unused here).  out[27] = hip-projected inertia/force in base coordinates.
+// foot_force (optional): world-frame contact force on this leg's foot.
+WS_HD void leg_phase1(const SimK& S, const LegK& L, const float* bc, const LegState& s, const float* tau, LegKeep& K,
+                      float* out, float* foot_force) {
+  const float* R = bc + kBcR;
+  Twist v0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { v0.a[i] = bc[kBcV0 + i]; v0.l[i] = bc[kBcV0 + 3 + i]; }
+  float r0[3], r1[3], r2[3];
+  joint_r(L, 0, r0); joint_r(L, 1, r1); joint_r(L, 2, r2);
+  Twist v1, v2, v3, p1, p2, p3;
+  joint_outward<0, kMaskHip>(v0, r0, s.q[0], s.qd[0], L.m[0], L.h[0], L.Io[0], v1, K.k1, p1);
+  joint_outward<1, kMaskThigh>(v1, r1, s.q[1], s.qd[1], L.m[1], L.h[1], L.Io[1], v2, K.k2, p2);
+  joint_outward<1, kMaskCalf>(v2, r2, s.q[2], s.qd[2], L.m[2], L.h[2], L.Io[2], v3, K.k3, p3);
+  // foot contact (compliant sphere on the plane z = 0)
+  {
+    float t3[3], t2[3], t1[3], u3[3], u2[3];
+    rot_up<1>(K.k3.cs, K.k3.sn, L.foot, t3);
+    u3[0] = t3[0]; u3[1] = t3[1]; u3[2] = L.rc + t3[2];
+    rot_up<1>(K.k2.cs, K.k2.sn, u3, t2);
+    u2[0] = t2[0]; u2[1] = L.rt + t2[1]; u2[2] = t2[2];
+    rot_up<0>(K.k1.cs, K.k1.sn, u2, t1);
+    const float fbx = L.rh[0] + t1[0], fby = L.rh[1] + t1[1], fbz = t1[2];
+    const float pz = bc[kBcPz] + R[6] * fbx + R[7] * fby + R[8] * fbz;
+    const float depth = S.radius - pz;
+    float F[3] = {0.f, 0.f, 0.f};
+    if (depth > 0.f) {
+      float wxo[3], vc[3], a2[3], a1[3], vb[3], vw[3];
+      cross3(v3.a, L.foot, wxo);
+#pragma unroll
+      for (int i = 0; i < 3; i++) vc[i] = v3.l[i] + wxo[i];
+      rot_up<1>(K.k3.cs, K.k3.sn, vc, a2);
+      rot_up<1>(K.k2.cs, K.k2.sn, a2, a1);
+      rot_up<0>(K.k1.cs, K.k1.sn, a1, vb);
+#pragma unroll
+      for (int i = 0; i < 3; i++) vw[i] = R[3 * i] * vb[0] + R[3 * i + 1] * vb[1] + R[3 * i + 2] * vb[2];
+      float fn = S.kn * depth * (1.f - S.cn * vw[2]);
+      fn = fmaxf(fn, 0.f);
+      const float speed2 = vw[0] * vw[0] + vw[1] * vw[1] + S.veps2;
+      const float coef = fminf(S.dtan, S.mu * fn * rsqrt_fast(speed2));
+      F[0] = -(coef * vw[0]); F[1] = -(coef * vw[1]); F[2] = fn;
+      float fb[3], g1[3], g2[3], fc[3], nc[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) fb[i] = R[i] * F[0] + R[3 + i] * F[1] + R[6 + i] * F[2];
+      rot_down<0>(K.k1.cs, K.k1.sn, fb, g1);
+      rot_down<1>(K.k2.cs, K.k2.sn, g1, g2);
+      rot_down<1>(K.k3.cs, K.k3.sn, g2, fc);
+      cross3(L.foot, fc, nc);
+#pragma unroll
+      for (int i = 0; i < 3; i++) { p3.a[i] -= nc[i]; p3.l[i] -= fc[i]; }
+    }
+    if (foot_force) { foot_force[0] = F[0]; foot_force[1] = F[1]; foot_force[2] = F[2]; }
+  }
+  // inward pass up the leg
+  ABI A2, A1, A0;
+  abi_from_rigid(L.m[1], L.h[1], L.Io[1], A2);
+  calf_inward(L, p3, tau[2], K.k3, A2, p2);
+  abi_from_rigid(L.m[0], L.h[0], L.Io[0], A1);
+  joint_inward<1, kMaskThigh>(A2, p2, tau[1], r1, K.k2, A1, p1);
+  Twist p0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) { A0.I[i] = 0.f; A0.M[i] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < 9; i++) A0.H[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { p0.a[i] = 0.f; p0.l[i] = 0.f; }
+  joint_inward<0, kMaskHip>(A1, p1, tau[0], r0, K.k1, A0, p0);
+#pragma unroll
+  for (int i = 0; i < 6; i++) { out[i] = A0.I[i]; out[15 + i] = A0.M[i]; }
+#pragma unroll
+  for (int i = 0; i < 9; i++) out[6 + i] = A0.H[i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) { out[21 + i] = p0.a[i]; out[24 + i] = p0.l[i]; }
+}
+
+// ---- leg role, phase 2: acceleration pass + semi-implicit Euler of the 3 joints ------------------------------
+WS_HD void leg_phase2(const LegK& L, const float* bc, const LegKeep& K, LegState& s, float h) {
+  Twist a0, a1, a2, a3;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { a0.a[i] = bc[kBcA0 + i]; a0.l[i] = bc[kBcA0 + 3 + i]; }
+  float r0[3], r1[3], r2[3];
+  joint_r(L, 0, r0); joint_r(L, 1, r1); joint_r(L, 2, r2);
+  const float qdd0 = joint_accel<0, kMaskHip>(a0, r0, K.k1.Ua, K.k1.Ul, K.k1.dinv, K.k1, a1);
+  const float qdd1 = joint_accel<1, kMaskThigh>(a1, r1, K.k2.Ua, K.k2.Ul, K.k2.dinv, K.k2, a2);
+  const float qdd2 = joint_accel<1, kMaskCalf>(a2, r2, L.cUa, L.cUl, L.cDinv, K.k3, a3);
+  s.qd[0] += h * qdd0; s.q[0] += h * s.qd[0];
+  s.qd[1] += h * qdd1; s.q[1] += h * s.qd[1];
+  s.qd[2] += h * qdd2; s.q[2] += h * s.qd[2];
+}
+
+// ---- base role ----------------------------------------------------------------------------------------------------
+struct BaseState { float p[3], quat[4], v[3], w[3]; };
+struct BaseInertia { float m; float h[3]; float Io[6]; };
+
+WS_HD void add_point_inertia(BaseInertia& B, float mass, const float* c, const float* Ic) {
+  const float cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+  B.m += mass;
+#pragma unroll
+  for (int i = 0; i < 3; i++) B.h[i] += mass * c[i];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = i; j < 3; j++) B.Io[sidx(i, j)] += Ic[sidx(i, j)] + mass * ((i == j ? cc : 0.f) - c[i] * c[j]);
+}
+
+// rotation matrix (body -> world) and body-frame twist of the base -> bc[R, v0, pz]
+WS_HD void base_publish(const BaseState& s, float* bc) {
+  float* R = bc + kBcR;
+  const float x = s.quat[0], y = s.quat[1], z = s.quat[2], w = s.quat[3];
+  const float xx = 2.f * x * x, yy = 2.f * y * y, zz = 2.f * z * z;
+  const float xy = 2.f * x * y, xz = 2.f * x * z, yz = 2.f * y * z;
+  const float wx = 2.f * w * x, wy = 2.f * w * y, wz = 2.f * w * z;
+  R[0] = 1.f - (yy + zz); R[1] = xy - wz;         R[2] = xz + wy;
+  R[3] = xy + wz;         R[4] = 1.f - (xx + zz); R[5] = yz - wx;
+  R[6] = xz - wy;         R[7] = yz + wx;         R[8] = 1.f - (xx + yy);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    bc[kBcV0 + i] = R[i] * s.w[0] + R[3 + i] * s.w[1] + R[6 + i] * s.w[2];
+    bc[kBcV0 + 3 + i] = R[i] * s.v[0] + R[3 + i] * s.v[1] + R[6 + i] * s.v[2];
+  }
+  bc[kBcPz] = s.p[2];
+}
+
+// 6x6 SPD solve (LDL^T), A given as the articulated inertia blocks, b = -pA
+WS_HD void solve_base(const ABI& A, const Twist& pA, Twist& a0) {
+  float M[6][6];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      M[i][j] = A.I[sidx(i, j)];
+      M[i][3 + j] = A.H[3 * i + j];
+      M[3 + i][j] = A.H[3 * j + i];
+      M[3 + i][3 + j] = A.M[sidx(i, j)];
+    }
+  float L[6][6], D[6], Dinv[6];
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    float d = M[j][j];
+#pragma unroll
+    for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k] * D[k];
+    D[j] = d;
+    Dinv[j] = rcp_fast(d);
+#pragma unroll
+    for (int i = j + 1; i < 6; i++) {
+      float s = M[i][j];
+#pragma unroll
+      for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k] * D[k];
+      L[i][j] = s * Dinv[j];
+    }
+  }
+  float y[6], x[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    float s = (i < 3) ? -pA.a[i] : -pA.l[i - 3];
+#pragma unroll
+    for (int k = 0; k < i; k++) s -= L[i][k] * y[k];
+    y[i] = s;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) y[i] *= Dinv[i];
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    float s = y[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; k++) s -= L[k][i] * x[k];
+    x[i] = s;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) { a0.a[i] = x[i]; a0.l[i] = x[3 + i]; }
+}
+
+// Base role for one sub-step.  legsum[27] = sum over the 4 legs of their phase-1 outputs; bc holds the R / v0
+// published for THIS sub-step.  Solves for the base acceleration, integrates the base by h, then publishes
+// a0 (for the legs' phase 2 of this sub-step) and R / v0 / pz of the NEW state (for phase 1 of the next).
+WS_HD void base_phase(const SimK& S, const BaseInertia& B, const float* legsum, BaseState& s, float h, float* bc) {
+  const float* R = bc + kBcR;
+  Twist v0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { v0.a[i] = bc[kBcV0 + i]; v0.l[i] = bc[kBcV0 + 3 + i]; }
+  ABI A0;
+  Twist p0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) { A0.I[i] = legsum[i] + B.Io[i]; A0.M[i] = legsum[15 + i]; }
+#pragma unroll
+  for (int i = 0; i < 9; i++) A0.H[i] = legsum[6 + i];
+  A0.H[1] -= B.h[2]; A0.H[2] += B.h[1];
+  A0.H[3] += B.h[2]; A0.H[5] -= B.h[0];
+  A0.H[6] -= B.h[1]; A0.H[7] += B.h[0];
+  A0.M[0] += B.m; A0.M[1] += B.m; A0.M[2] += B.m;
+  {
+    float n[3], f[3], hv[3], hw[3], t1[3], t2[3], t3[3];
+    sym_mulv(B.Io, v0.a, n);
+    cross3(B.h, v0.l, hv);
+    cross3(B.h, v0.a, hw);
+#pragma unroll
+    for (int i = 0; i < 3; i++) { n[i] += hv[i]; f[i] = B.m * v0.l[i] - hw[i]; }
+    cross3(v0.a, n, t1);
+    cross3(v0.l, f, t2);
+    cross3(v0.a, f, t3);
+#pragma unroll
+    for (int i = 0; i < 3; i++) { p0.a[i] = legsum[21 + i] + t1[i] + t2[i]; p0.l[i] = legsum[24 + i] + t3[i]; }
+  }
+  Twist a0;
+  solve_base(A0, p0, a0);
+  // gravity enters as a uniform acceleration of every body (RBDA 9.4): classical acc of the base origin
+  float accb[3], wxv[3], Rl[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) Rl[i] = R[i];
+  cross3(v0.a, v0.l, wxv);
+#pragma unroll
+  for (int i = 0; i < 3; i++) accb[i] = a0.l[i] + Rl[6 + i] * S.gz + wxv[i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    s.w[i] += h * (Rl[3 * i] * a0.a[0] + Rl[3 * i + 1] * a0.a[1] + Rl[3 * i + 2] * a0.a[2]);
+    s.v[i] += h * (Rl[3 * i] * accb[0] + Rl[3 * i + 1] * accb[1] + Rl[3 * i + 2] * accb[2]);
+    s.p[i] += h * s.v[i];
+  }
+  const float hx = 0.5f * h;
+  const float x = s.quat[0], y = s.quat[1], z = s.quat[2], w = s.quat[3];
+  const float nx = x + hx * (s.w[0] * w + s.w[1] * z - s.w[2] * y);
+  const float ny = y + hx * (s.w[1] * w + s.w[2] * x - s.w[0] * z);
+  const float nz = z + hx * (s.w[2] * w + s.w[0] * y - s.w[1] * x);
+  const float nw = w - hx * (s.w[0] * x + s.w[1] * y + s.w[2] * z);
+  const float inv = rsqrt_fast(nx * nx + ny * ny + nz * nz + nw * nw);
+  s.quat[0] = nx * inv; s.quat[1] = ny * inv; s.quat[2] = nz * inv; s.quat[3] = nw * inv;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { bc[kBcA0 + i] = a0.a[i]; bc[kBcA0 + 3 + i] = a0.l[i]; }
+  base_publish(s, bc);
+}
+
+// PD law + torque clip + motor model for one leg's 3 joints
+// (legged_robot_base.py:545,557; go2_omni.py:436-437; active_sysid_openloop.py:184-186,356-400)
+WS_HD void leg_torques(const SimK& S, const LegK& L, const float* act /*clipped*/, const float* q, const float* qd,
+                       const float* kp, const float* kd, const float* motor, int motor_model, unsigned flags, float* tau) {
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    float as = act[j] * S.action_scale;
+    if (j == 0 && (flags & SPI_FLAG_HIP_HALF)) as *= 0.5f;
+    float t = kp[j] * (as + L.qdef[j] - q[j]) - kd[j] * qd[j];
+    const float g = motor[j];
+    if (motor_model == SPI_MOTOR_VEC3_TANH && (flags & SPI_FLAG_TANH_BEFORE_CLIP)) {
+      t = g * tanhf((1.0f / g) * t);
+      t = fminf(fmaxf(t, -L.tlim[j]), L.tlim[j]);
+    } else {
+      t = fminf(fmaxf(t, -L.tlim[j]), L.tlim[j]);
+      if (motor_model == SPI_MOTOR_SCALAR) t *= motor[0];
+      else if (motor_model == SPI_MOTOR_VEC3) t *= g;
+      else if (motor_model == SPI_MOTOR_VEC3_TANH) t = g * tanhf((1.0f / g) * t);
+    }
+    tau[j] = t;
+  }
+}
+
+// candidate row -> base rigid inertia (+ head lumps) and motor parameters
+// (isaacgym_active_sysid.py:61-94 setters; mass_opt.py:158-160 mass_scale; DESIGN.md D8/D15 flags)
+struct ParamIdsK { int n; int id[16]; };
+
+WS_HD void apply_candidate(const ModelK& M, const float* row, const ParamIdsK& ids, unsigned flags, BaseInertia& B,
+                           float* motor3) {
+  float rec[10];
+#pragma unroll
+  for (int k = 0; k < 10; k++) rec[k] = M.base_inertial[k];
+  motor3[0] = motor3[1] = motor3[2] = 20.0f;
+  float mass = rec[0];
+  if (row) {
+    for (int p = 0; p < ids.n; p++) {
+      if (ids.id[p] == SPI_PARAM_MASS) mass = row[p];
+      if (ids.id[p] == SPI_PARAM_MASS_SCALE) mass = rec[0] * row[p];
+    }
+  }
+  if (!(flags & SPI_FLAG_INERTIA_KEEP)) {
+    const float sc = mass / rec[0];
+#pragma unroll
+    for (int k = 4; k < 10; k++) rec[k] *= sc;
+  }
+  rec[0] = mass;
+  if (row) {
+    for (int p = 0; p < ids.n; p++) {
+      const float v = row[p];
+      const int id = ids.id[p];
+      if (id >= SPI_PARAM_COMX && id <= SPI_PARAM_INERTIAYZ) {
+        if (id == SPI_PARAM_INERTIAY && (flags & SPI_FLAG_STRICT_INERTIAY)) continue;
+#pragma unroll
+        for (int k = 1; k < 10; k++) if (id == k) rec[k] = v;
+      } else if (id == SPI_PARAM_MOTOR_HIP) motor3[0] = v;
+      else if (id == SPI_PARAM_MOTOR_THIGH) motor3[1] = v;
+      else if (id == SPI_PARAM_MOTOR_CALF) motor3[2] = v;
+    }
+  }
+  B.m = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) B.h[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; i++) B.Io[i] = 0.f;
+  add_point_inertia(B, rec[0], rec + 1, rec + 4);
+  add_point_inertia(B, M.lumps[0][0], M.lumps[0] + 1, M.lumps[0] + 4);
+  add_point_inertia(B, M.lumps[1][0], M.lumps[1] + 1, M.lumps[1] + 4);
+}
+
+// host-side: blob -> ModelK (incl. the constant calf projection).  Returns 0, or a negative code when the
+// blob does not have the Go2-family structure this fast path is compiled for (the caller then uses the
+// generic leg-per-lane kernel): -1 axes, -2 joint-origin sparsity.
+inline int model_from_blob(const float* b, ModelK* M) {
+  M->sim.dt = b[SPI_BLOB_DT]; M->sim.gz = b[SPI_BLOB_GRAVITY_Z];
+  M->sim.action_scale = b[SPI_BLOB_ACTION_SCALE]; M->sim.action_clip = b[SPI_BLOB_ACTION_CLIP];
+  M->sim.kn = b[SPI_BLOB_CONTACT_KN]; M->sim.cn = b[SPI_BLOB_CONTACT_CN]; M->sim.mu = b[SPI_BLOB_CONTACT_MU];
+  M->sim.dtan = b[SPI_BLOB_CONTACT_DT]; M->sim.radius = b[SPI_BLOB_FOOT_RADIUS];
+  M->sim.veps2 = b[SPI_BLOB_CONTACT_VEPS] * b[SPI_BLOB_CONTACT_VEPS];
+  M->sim.nsub = (int)b[SPI_BLOB_NSUB];
+  if (M->sim.nsub < 1) M->sim.nsub = 1;
+  for (int k = 0; k < 10; k++) M->base_inertial[k] = b[SPI_BLOB_BASE_INERTIAL + k];
+  for (int l = 0; l < 2; l++)
+    for (int k = 0; k < 10; k++) M->lumps[l][k] = b[SPI_BLOB_BASE_LUMPS + 10 * l + k];
+  for (int leg = 0; leg < 4; leg++) {
+    LegK& L = M->leg[leg];
+    for (int j = 0; j < 3; j++) {
+      const float* p = b + SPI_BLOB_LEG_BODIES + SPI_LEG_BODY_STRIDE * (3 * leg + j);
+      if ((int)p[13] != (j == 0 ? 0 : 1)) return -1;
+      const float m = p[0];
+      const float c[3] = {p[1], p[2], p[3]};
+      const float cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+      L.m[j] = m;
+      for (int k = 0; k < 3; k++) L.h[j][k] = m * c[k];
+      const float Ic[6] = {p[4], p[5], p[6], p[7], p[8], p[9]};
+      for (int r = 0; r < 3; r++)
+        for (int k = r; k < 3; k++) {
+          const int s = sidx(r, k);
+          L.Io[j][s] = Ic[s] + m * ((r == k ? cc : 0.f) - c[r] * c[k]);
+        }
+      L.qdef[j] = b[SPI_BLOB_Q_DEFAULT + 3 * leg + j];
+      L.tlim[j] = b[SPI_BLOB_TORQUE_LIMIT + 3 * leg + j];
+      const float* r = p + 10;
+      if (j == 0) { if (r[2] != 0.f) return -2; L.rh[0] = r[0]; L.rh[1] = r[1]; }
+      if (j == 1) { if (r[0] != 0.f || r[2] != 0.f) return -2; L.rt = r[1]; }
+      if (j == 2) { if (r[0] != 0.f || r[1] != 0.f) return -2; L.rc = r[2]; }
+    }
+    for (int k = 0; k < 3; k++) L.foot[k] = b[SPI_BLOB_FOOT_OFFSET + 3 * leg + k];
+    // constant projection of the calf joint (axis y: a = 1, b = 2, c = 0)
+    {
+      const int a = 1, bb = 2, cx = 0;
+      ABI A;
+      {
+        const float* h = L.h[2];
+        for (int i = 0; i < 6; i++) A.I[i] = L.Io[2][i];
+        A.H[0] = 0.f; A.H[1] = -h[2]; A.H[2] = h[1]; A.H[3] = h[2]; A.H[4] = 0.f; A.H[5] = -h[0];
+        A.H[6] = -h[1]; A.H[7] = h[0]; A.H[8] = 0.f;
+        A.M[0] = A.M[1] = A.M[2] = L.m[2]; A.M[3] = A.M[4] = A.M[5] = 0.f;
+      }
+      for (int i = 0; i < 3; i++) { L.cUa[i] = A.I[sidx(i, a)]; L.cUl[i] = A.H[3 * a + i]; }
+      L.cDinv = 1.0f / L.cUa[a];
+      float Uad[3], Uld[3];
+      for (int i = 0; i < 3; i++) { Uad[i] = L.cUa[i] * L.cDinv; Uld[i] = L.cUl[i] * L.cDinv; }
+      L.cIbb = A.I[sidx(bb, bb)] - Uad[bb] * L.cUa[bb];
+      L.cIbc = A.I[sidx(bb, cx)] - Uad[bb] * L.cUa[cx];
+      L.cIcc = A.I[sidx(cx, cx)] - Uad[cx] * L.cUa[cx];
+      for (int j = 0; j < 3; j++) {
+        L.cHb[j] = A.H[3 * bb + j] - Uad[bb] * L.cUl[j];
+        L.cHc[j] = A.H[3 * cx + j] - Uad[cx] * L.cUl[j];
+      }
+      for (int i = 0; i < 3; i++)
+        for (int j = i; j < 3; j++) L.cMa[sidx(i, j)] = A.M[sidx(i, j)] - Uld[i] * L.cUl[j];
+    }
+  }
+  for (int j = 0; j < 12; j++) { M->kp[j] = b[SPI_BLOB_KP + j]; M->kd[j] = b[SPI_BLOB_KD + j]; }
+  return 0;
+}
+
+}  // namespace ws

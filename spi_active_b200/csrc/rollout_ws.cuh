@@ -1,0 +1,232 @@
+// rollout_ws.cuh — the warp-specialised fused rollout kernel (see go2_ws.cuh for the role arithmetic and
+// DESIGN.md §4.2 for the mapping).  One CTA = 32 (candidate, segment) rollouts x 5 warps:
+//   4 leg warps (lane = rollout) + 1 base warp; roles rotate with blockIdx so that the base warp of the
+//   CTAs resident on an SM spreads over the 4 SM sub-partitions.
+// Per integrator sub-step:   legs: phase 1 -> smem[27] | barrier | base: sum, 6x6 solve, integrate ->
+//   smem[22] | barrier | legs: phase 2.
+#pragma once
+#include "go2_ws.cuh"
+
+namespace ws {
+
+constexpr int kWsWarps = 5;
+constexpr int kWsThreads = 32 * kWsWarps;
+constexpr int kWsRollouts = 32;
+
+struct WsArgs {
+  ModelK M;
+  const float* params; int C, P; ParamIdsK ids;
+  const float* seg_init; const float* seg_actions; const float* seg_target; const float* seg_gains;
+  const unsigned char* seg_mask;
+  int S, H, decimation, motor_model; unsigned flags;
+  int n_cta_per_cand;
+  int rotate_roles;
+  float* partial;      // [C][n_cta_per_cand][3]
+  float* per_seg;      // [C][S][3] or null
+  int* bad;            // [C]
+  float* out_states;   // [C][S][H][37] (RECORD)
+};
+
+struct WsSmem {
+  float part[4][kLegOut][32];   // leg -> base, per sub-step
+  float bc[kBaseOut][32];       // base -> legs, per sub-step
+  float ej[4][32];              // per-leg squared joint error (end of rollout)
+  int finite[4][32];
+};
+
+__device__ __forceinline__ bool finite_acc(float acc) { return acc == 0.f; }  // NaN/Inf * 0 = NaN
+
+// CTA-wide barrier reached from role-specific code paths: a named barrier with an explicit thread count
+// (every role executes the same number of ws_barrier() calls).
+__device__ __forceinline__ void ws_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kWsThreads) : "memory"); }
+
+// LEG is a warp-uniform run-time value (one code copy for the four legs: four template copies overflow the
+// instruction cache — profiles/README.md, experiment ws-templated); the leg's constants are then fetched through
+// the constant bank with a uniform offset.
+template <bool RECORD>
+__device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, int lane, const int LEG, int c, int seg,
+                                            bool active) {
+  const SimK& S = A.M.sim;
+  const LegK& L = A.M.leg[LEG];
+  // this leg's motor parameters (act2tau_scalar uses one gain for every joint)
+  float motor[3];
+  {
+    float m3[3] = {20.0f, 20.0f, 20.0f};
+    if (A.params) {
+      const float* row = A.params + (size_t)c * A.P;
+      for (int p = 0; p < A.ids.n; p++) {
+        const int id = A.ids.id[p];
+        if (id == SPI_PARAM_MOTOR_HIP) m3[0] = row[p];
+        else if (id == SPI_PARAM_MOTOR_THIGH) m3[1] = row[p];
+        else if (id == SPI_PARAM_MOTOR_CALF) m3[2] = row[p];
+      }
+    }
+    motor[0] = m3[0]; motor[1] = m3[1]; motor[2] = m3[2];
+    if (A.motor_model == SPI_MOTOR_SCALAR) { motor[1] = m3[0]; motor[2] = m3[0]; }
+  }
+  LegState s;
+  float kp[3], kd[3];
+  {
+    const float* row = A.seg_init + (size_t)seg * SPI_STATE_DIM;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      s.q[j] = __ldg(row + 13 + 3 * LEG + j);
+      s.qd[j] = __ldg(row + 25 + 3 * LEG + j);
+      kp[j] = A.seg_gains ? __ldg(A.seg_gains + (size_t)seg * 24 + 3 * LEG + j) : A.M.kp[3 * LEG + j];
+      kd[j] = A.seg_gains ? __ldg(A.seg_gains + (size_t)seg * 24 + 12 + 3 * LEG + j) : A.M.kd[3 * LEG + j];
+    }
+  }
+  const float h = S.dt / (float)S.nsub;
+  const float* act_row = A.seg_actions + (size_t)seg * A.H * 12 + 3 * LEG;
+  LegKeep K;
+  ws_barrier();   // [S0] the base role has published R / v0 / pz of the initial state
+  for (int k = 0; k < A.H; k++) {
+    float act[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) act[j] = fminf(fmaxf(__ldg(act_row + 12 * k + j), -S.action_clip), S.action_clip);
+    for (int d = 0; d < A.decimation; d++) {
+      float tau[3];
+      leg_torques(S, L, act, s.q, s.qd, kp, kd, motor, A.motor_model, A.flags, tau);
+      for (int n = 0; n < S.nsub; n++) {
+        float bc[kBaseOut];
+#pragma unroll
+        for (int i = kBcR; i < kBaseOut; i++) bc[i] = sm.bc[i][lane];
+        float out[kLegOut];
+        leg_phase1(S, L, bc, s, tau, K, out, nullptr);
+#pragma unroll
+        for (int i = 0; i < kLegOut; i++) sm.part[LEG][i][lane] = out[i];
+        ws_barrier();   // [A] leg contributions are in shared memory
+        ws_barrier();   // [B] the base role has published a0 and the new R / v0 / pz
+#pragma unroll
+        for (int i = 0; i < 6; i++) bc[kBcA0 + i] = sm.bc[kBcA0 + i][lane];
+        leg_phase2(L, bc, K, s, h);
+      }
+    }
+    if (RECORD) {
+      if (active) {
+        float* row = A.out_states + (((size_t)c * A.S + seg) * A.H + k) * SPI_STATE_DIM;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { row[13 + 3 * LEG + j] = s.q[j]; row[25 + 3 * LEG + j] = s.qd[j]; }
+      }
+      ws_barrier();   // [R] keeps the barrier count of the base role (which writes its rows here)
+    }
+  }
+  if (RECORD) return;
+  // scripts/eval.py:292 — this leg's share of the squared joint-position error
+  const float* tgt = A.seg_target + (size_t)seg * SPI_TARGET_DIM;
+  float ej = 0.f, acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const float e = s.q[j] - __ldg(tgt + 7 + 3 * LEG + j);
+    ej += e * e;
+    acc += s.q[j] * 0.f + s.qd[j] * 0.f;
+  }
+  sm.ej[LEG][lane] = ej;
+  sm.finite[LEG][lane] = finite_acc(acc) ? 1 : 0;
+  ws_barrier();   // [C]
+}
+
+template <bool RECORD>
+__device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, int lane, int c, int cta_in_cand, int seg,
+                                             bool active) {
+  const SimK& S = A.M.sim;
+  BaseInertia B;
+  {
+    float motor_unused[3];
+    apply_candidate(A.M, A.params ? A.params + (size_t)c * A.P : nullptr, A.ids, A.flags, B, motor_unused);
+  }
+  BaseState s;
+  {
+    const float* row = A.seg_init + (size_t)seg * SPI_STATE_DIM;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { s.p[i] = __ldg(row + i); s.v[i] = __ldg(row + 7 + i); s.w[i] = __ldg(row + 10 + i); }
+#pragma unroll
+    for (int i = 0; i < 4; i++) s.quat[i] = __ldg(row + 3 + i);
+  }
+  float bc[kBaseOut];
+#pragma unroll
+  for (int i = 0; i < 6; i++) bc[i] = 0.f;
+  base_publish(s, bc);
+#pragma unroll
+  for (int i = kBcR; i < kBaseOut; i++) sm.bc[i][lane] = bc[i];
+  ws_barrier();   // [S0]
+  const float h = S.dt / (float)S.nsub;
+  for (int k = 0; k < A.H; k++) {
+    for (int d = 0; d < A.decimation; d++) {
+      for (int n = 0; n < S.nsub; n++) {
+        ws_barrier();   // [A]
+        float legsum[kLegOut];
+#pragma unroll
+        for (int i = 0; i < kLegOut; i++)
+          legsum[i] = (sm.part[0][i][lane] + sm.part[1][i][lane]) + (sm.part[2][i][lane] + sm.part[3][i][lane]);
+        base_phase(S, B, legsum, s, h, bc);
+#pragma unroll
+        for (int i = 0; i < kBaseOut; i++) sm.bc[i][lane] = bc[i];
+        ws_barrier();   // [B]
+      }
+    }
+    if (RECORD) {
+      if (active) {
+        float* row = A.out_states + (((size_t)c * A.S + seg) * A.H + k) * SPI_STATE_DIM;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { row[i] = s.p[i]; row[7 + i] = s.v[i]; row[10 + i] = s.w[i]; }
+#pragma unroll
+        for (int i = 0; i < 4; i++) row[3 + i] = s.quat[i];
+      }
+      ws_barrier();   // [R]
+    }
+  }
+  if (RECORD) return;
+  // scripts/eval.py:287-292 — L2 errors of the final state
+  const float* tgt = A.seg_target + (size_t)seg * SPI_TARGET_DIM;
+  float ep = 0.f, eq = 0.f, acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const float e = s.p[i] - __ldg(tgt + i);
+    ep += e * e;
+    acc += s.p[i] * 0.f + s.v[i] * 0.f + s.w[i] * 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float e = s.quat[i] - __ldg(tgt + 3 + i);
+    eq += e * e;
+    acc += s.quat[i] * 0.f;
+  }
+  ws_barrier();   // [C]
+  const float ej = (sm.ej[0][lane] + sm.ej[1][lane]) + (sm.ej[2][lane] + sm.ej[3][lane]);
+  const bool ok = finite_acc(acc) && (sm.finite[0][lane] & sm.finite[1][lane] & sm.finite[2][lane] & sm.finite[3][lane]);
+  float err[3] = {sqrtf(ep), sqrtf(eq), sqrtf(ej)};
+  if (!ok && active) atomicOr(A.bad + c, 1);
+  if (A.per_seg && active) {
+    float* o = A.per_seg + ((size_t)c * A.S + seg) * 3;
+    o[0] = err[0]; o[1] = err[1]; o[2] = err[2];
+  }
+  const bool counts = active && (A.seg_mask ? (A.seg_mask[seg] != 0) : true);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    float v = counts ? err[i] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    err[i] = v;
+  }
+  if (lane == 0) {
+    float* o = A.partial + ((size_t)c * A.n_cta_per_cand + cta_in_cand) * 3;
+    o[0] = err[0]; o[1] = err[1]; o[2] = err[2];
+  }
+}
+
+template <bool RECORD, int MINB>
+__global__ void __launch_bounds__(kWsThreads, MINB) rollout_ws_kernel(const __grid_constant__ WsArgs A) {
+  __shared__ WsSmem sm;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int role = __shfl_sync(0xffffffffu, A.rotate_roles ? (warp + blockIdx.x) % kWsWarps : warp, 0);  // warp-uniform
+  const int c = blockIdx.x / A.n_cta_per_cand;
+  const int cta_in_cand = blockIdx.x - c * A.n_cta_per_cand;
+  const int seg_raw = cta_in_cand * kWsRollouts + lane;
+  const bool active = seg_raw < A.S;
+  const int seg = active ? seg_raw : A.S - 1;
+  if (role < 4) ws_leg_role<RECORD>(A, sm, lane, role, c, seg, active);
+  else ws_base_role<RECORD>(A, sm, lane, c, cta_in_cand, seg, active);
+}
+
+}  // namespace ws

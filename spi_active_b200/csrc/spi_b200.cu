@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "aba_leg.cuh"
+#include "rollout_ws.cuh"
 
 using namespace spi;
 
@@ -399,6 +400,8 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(int iters, float seed, f
 struct spi_b200_model {
   DeviceModel host_model;
   DeviceModel* d_model = nullptr;
+  ws::ModelK ws_model;      // constants of the warp-specialised fast path (passed as a kernel parameter)
+  bool ws_ok = false;       // the blob has the Go2-family structure the fast path is compiled for
   int device = 0;
   // workspaces (grown on demand)
   float* d_partial = nullptr; size_t partial_cap = 0;
@@ -523,6 +526,65 @@ int timing_drain(spi_b200_model* m) {
   return 0;
 }
 
+// SPI_B200_KERNEL = "lane" forces the generic leg-per-lane kernel; default = warp-specialised fast path when the
+// model qualifies.  SPI_B200_MINB = min CTAs per SM the kernels are compiled for (occupancy experiments).
+int kernel_choice() {
+  static const int v = [] { const char* e = getenv("SPI_B200_KERNEL"); return (e && std::string(e) == "lane") ? 1 : 0; }();
+  return v;
+}
+int minb_choice() {
+  static const int v = [] { const char* e = getenv("SPI_B200_MINB"); return e ? atoi(e) : 0; }();
+  return v;
+}
+
+int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C, int P, const int* param_ids,
+                      const float* seg_init, const float* seg_actions, const float* seg_target, const float* seg_gains,
+                      const unsigned char* seg_mask, int S, int H, int decimation, int motor_model, unsigned flags,
+                      float cost_denominator, float* out_cost, float* out_per_seg, int* out_status, float* out_states,
+                      cudaStream_t st) {
+  ws::WsArgs A;
+  std::memset(&A, 0, sizeof(A));
+  ParamIds ids;
+  if (int rc = make_ids(P, param_ids, &ids)) return rc;
+  A.ids.n = ids.n;
+  for (int i = 0; i < 16; i++) A.ids.id[i] = ids.id[i];
+  A.M = m->ws_model;
+  A.params = (P > 0) ? params : nullptr; A.C = C; A.P = P;
+  A.seg_init = seg_init; A.seg_actions = seg_actions; A.seg_target = seg_target; A.seg_gains = seg_gains;
+  A.seg_mask = seg_mask; A.S = S; A.H = H; A.decimation = decimation; A.motor_model = motor_model; A.flags = flags;
+  A.n_cta_per_cand = (S + ws::kWsRollouts - 1) / ws::kWsRollouts;
+  { static const int rot = getenv("SPI_B200_WS_ROT") ? atoi(getenv("SPI_B200_WS_ROT")) : 1; A.rotate_roles = rot; }
+  const long long n_cta = (long long)C * A.n_cta_per_cand;
+  if (n_cta > 2147483647LL) return fail(-3, "C * ceil(S/32) exceeds the grid limit");
+  const int minb = minb_choice();
+  if (record) {
+    A.out_states = out_states;
+    ws::rollout_ws_kernel<true, 2><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
+    return check_launch("rollout_ws_kernel<record>");
+  }
+  if (int rc = ensure(&m->d_partial, &m->partial_cap, (size_t)C * A.n_cta_per_cand * 3)) return rc;
+  if (int rc = ensure(&m->d_bad, &m->bad_cap, (size_t)C)) return rc;
+  CUDA_OK(cudaMemsetAsync(m->d_bad, 0, (size_t)C * sizeof(int), st));
+  A.partial = m->d_partial; A.bad = m->d_bad; A.per_seg = out_per_seg;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (m->timing) {
+    if (int rc = timing_events(m, &e0, &e1)) return rc;
+    CUDA_OK(cudaEventRecord(e0, st));
+  }
+  if (minb == 2) ws::rollout_ws_kernel<false, 2><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
+  else if (minb == 4) ws::rollout_ws_kernel<false, 4><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
+  else ws::rollout_ws_kernel<false, 3><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
+  if (int rc = check_launch("rollout_ws_kernel")) return rc;
+  if (m->timing) {
+    CUDA_OK(cudaEventRecord(e1, st));
+    m->ev_pending.push_back(e0); m->ev_pending.push_back(e1);
+  }
+  const int n = C * 3;
+  reduce_cost_kernel<<<(n + 127) / 128, 128, 0, st>>>(m->d_partial, m->d_bad, seg_mask, C, S, A.n_cta_per_cand,
+                                                      cost_denominator, out_cost, out_status);
+  return check_launch("reduce_cost_kernel");
+}
+
 int launch_rollout(spi_b200_model* m, bool record, const float* params, int C, int P, const int* param_ids,
                    const float* seg_init, const float* seg_actions, const float* seg_target, const float* seg_gains,
                    const unsigned char* seg_mask, int S, int H, int decimation, int motor_model, unsigned flags,
@@ -535,6 +597,10 @@ int launch_rollout(spi_b200_model* m, bool record, const float* params, int C, i
   if (record && !out_states) return fail(-3, "out_states is NULL");
   if (P > 0 && !params) return fail(-3, "params is NULL");
   if (motor_model < SPI_MOTOR_NONE || motor_model > SPI_MOTOR_VEC3_TANH) return fail(-3, "unknown motor_model");
+  if (m->ws_ok && kernel_choice() != 1)
+    return launch_rollout_ws(m, record, params, C, P, param_ids, seg_init, seg_actions, seg_target, seg_gains, seg_mask,
+                             S, H, decimation, motor_model, flags, cost_denominator, out_cost, out_per_seg, out_status,
+                             out_states, st);
   EvalArgs A;
   std::memset(&A, 0, sizeof(A));
   if (int rc = make_ids(P, param_ids, &A.ids)) return rc;
@@ -556,7 +622,7 @@ int launch_rollout(spi_b200_model* m, bool record, const float* params, int C, i
       if (int rc = timing_events(m, &e0, &e1)) return rc;
       CUDA_OK(cudaEventRecord(e0, st));
     }
-    static const int variant = getenv("SPI_B200_MINB") ? atoi(getenv("SPI_B200_MINB")) : 2;
+    const int variant = minb_choice();
     if (variant == 3) rollout_kernel<false, 3><<<(unsigned)n_cta, kThreads, 0, st>>>(A);
     else if (variant == 4) rollout_kernel<false, 4><<<(unsigned)n_cta, kThreads, 0, st>>>(A);
     else rollout_kernel<false, 2><<<(unsigned)n_cta, kThreads, 0, st>>>(A);
@@ -589,6 +655,8 @@ int spi_b200_model_create(const float* model_blob, int n_floats, spi_b200_model*
   spi_b200_model* m = new (std::nothrow) spi_b200_model();
   if (!m) return fail(-4, "out of host memory");
   if (int rc = blob_to_model(model_blob, n_floats, &m->host_model)) { delete m; return rc; }
+  std::memset(&m->ws_model, 0, sizeof(m->ws_model));
+  m->ws_ok = ws::model_from_blob(model_blob, &m->ws_model) == 0;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
