@@ -351,7 +351,7 @@ def run_b200(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     roofline = {
-        "bound": "fp32", "kernel": "rollout_kernel", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+        "bound": "fp32", "kernel": "rollout_ws_kernel", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
         "frac": achieved_tf / peak_tf, "traffic": ncu_traffic(),
         "peak_source": "FP32 FFMA microbenchmark (spi_b200_fp32_peak) measured in this run on this GPU; "
                        "MEASURED_PEAKS.json holds no FP32 figure",

@@ -226,6 +226,12 @@ int spi_b200_weighted_cost(spi_b200_model* model, const float* cost3, int C,
  * measured TFLOP/s of a register-resident FFMA loop on the current device.                    */
 int spi_b200_fp32_peak(int iters, float* out_tflops, float* out_ms, void* cuda_stream);
 
+/* Rollout-kernel selection for this handle: 0 = automatic (the warp-specialised Go2-family fast path when the
+ * blob has that structure, else the generic leg-per-lane kernel), 1 = force the generic kernel, 2 = require the
+ * fast path (error if the blob does not qualify).  Both are CUDA kernels; there is no CPU path.              */
+enum { SPI_KERNEL_AUTO = 0, SPI_KERNEL_LANE = 1, SPI_KERNEL_WS = 2 };
+int spi_b200_model_set_kernel(spi_b200_model* model, int kernel);
+
 /* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
 long long spi_b200_launch_count(void);
 

@@ -16,7 +16,9 @@ LIB_PATH = Path(os.environ.get("SPI_B200_LIB", _PKG / "libspi_b200.so"))  # over
 SOURCES = [_PKG / "csrc" / "spi_b200.cu"]
 HEADERS = [_PKG / "csrc" / "aba_leg.cuh", _PKG / "csrc" / "go2_ws.cuh", _PKG / "csrc" / "rollout_ws.cuh",
            _PKG.parent / "include" / "spi_b200.h"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+# SPI_WS_FAST_SINCOS: joint sin/cos through MUFU after a 2-constant reduction to [-pi, pi]; measured deviation from
+# the fp64 oracle stays at the fp32 noise floor of the oracle itself (profiles/README.md, tools/dev_accuracy.py)
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-DSPI_WS_FAST_SINCOS",
               "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
 
 _lib = None
@@ -78,6 +80,7 @@ SIGNATURES = {
                                       _V, _V]),
     "spi_b200_weighted_cost": (C.c_int, [_V, _V, C.c_int, C.c_float, C.c_float, C.c_float, _V, _V]),
     "spi_b200_fp32_peak": (C.c_int, [C.c_int, _F, _F, _V]),
+    "spi_b200_model_set_kernel": (C.c_int, [_V, C.c_int]),
     "spi_b200_timing_enable": (C.c_int, [_V, C.c_int]),
     "spi_b200_timing_read": (C.c_int, [_V, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),
 }

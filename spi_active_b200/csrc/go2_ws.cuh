@@ -555,14 +555,29 @@ WS_HD void solve_base(const ABI& A, const Twist& pA, Twist& a0) {
   for (int i = 0; i < 3; i++) { a0.a[i] = x[i]; a0.l[i] = x[3 + i]; }
 }
 
-// Base role for one sub-step.  legsum[27] = sum over the 4 legs of their phase-1 outputs; bc holds the R / v0
-// published for THIS sub-step.  Solves for the base acceleration, integrates the base by h, then publishes
-// a0 (for the legs' phase 2 of this sub-step) and R / v0 / pz of the NEW state (for phase 1 of the next).
-WS_HD void base_phase(const SimK& S, const BaseInertia& B, const float* legsum, BaseState& s, float h, float* bc) {
-  const float* R = bc + kBcR;
+// Base role, split in two so that the legs' acceleration pass overlaps the base integration:
+//   base_bias    (off the critical path, right after the state is known): velocity-product bias of the base body
+//   base_solve   (critical: between the legs' phase 1 and phase 2): sum of the legs + base -> 6x6 solve -> a0
+//   base_advance (overlaps the legs' phase 2): semi-implicit Euler of the base, publish R / v0 / pz of the NEW
+//                state for phase 1 of the next sub-step
+WS_HD void base_bias(const BaseInertia& B, const float* bc, float* pb /*[6]*/) {
   Twist v0;
 #pragma unroll
   for (int i = 0; i < 3; i++) { v0.a[i] = bc[kBcV0 + i]; v0.l[i] = bc[kBcV0 + 3 + i]; }
+  float n[3], f[3], hv[3], hw[3], t1[3], t2[3], t3[3];
+  sym_mulv(B.Io, v0.a, n);
+  cross3(B.h, v0.l, hv);
+  cross3(B.h, v0.a, hw);
+#pragma unroll
+  for (int i = 0; i < 3; i++) { n[i] += hv[i]; f[i] = B.m * v0.l[i] - hw[i]; }
+  cross3(v0.a, n, t1);
+  cross3(v0.l, f, t2);
+  cross3(v0.a, f, t3);
+#pragma unroll
+  for (int i = 0; i < 3; i++) { pb[i] = t1[i] + t2[i]; pb[3 + i] = t3[i]; }
+}
+
+WS_HD void base_solve(const BaseInertia& B, const float* legsum, const float* pb, float* a0_out /*[6]*/) {
   ABI A0;
   Twist p0;
 #pragma unroll
@@ -573,25 +588,24 @@ WS_HD void base_phase(const SimK& S, const BaseInertia& B, const float* legsum, 
   A0.H[3] += B.h[2]; A0.H[5] -= B.h[0];
   A0.H[6] -= B.h[1]; A0.H[7] += B.h[0];
   A0.M[0] += B.m; A0.M[1] += B.m; A0.M[2] += B.m;
-  {
-    float n[3], f[3], hv[3], hw[3], t1[3], t2[3], t3[3];
-    sym_mulv(B.Io, v0.a, n);
-    cross3(B.h, v0.l, hv);
-    cross3(B.h, v0.a, hw);
 #pragma unroll
-    for (int i = 0; i < 3; i++) { n[i] += hv[i]; f[i] = B.m * v0.l[i] - hw[i]; }
-    cross3(v0.a, n, t1);
-    cross3(v0.l, f, t2);
-    cross3(v0.a, f, t3);
-#pragma unroll
-    for (int i = 0; i < 3; i++) { p0.a[i] = legsum[21 + i] + t1[i] + t2[i]; p0.l[i] = legsum[24 + i] + t3[i]; }
-  }
+  for (int i = 0; i < 3; i++) { p0.a[i] = legsum[21 + i] + pb[i]; p0.l[i] = legsum[24 + i] + pb[3 + i]; }
   Twist a0;
   solve_base(A0, p0, a0);
-  // gravity enters as a uniform acceleration of every body (RBDA 9.4): classical acc of the base origin
-  float accb[3], wxv[3], Rl[9];
 #pragma unroll
-  for (int i = 0; i < 9; i++) Rl[i] = R[i];
+  for (int i = 0; i < 3; i++) { a0_out[i] = a0.a[i]; a0_out[3 + i] = a0.l[i]; }
+}
+
+// bc holds R / v0 of the CURRENT state on entry and of the NEW state on return; bc[a0] is left untouched.
+WS_HD void base_advance(const SimK& S, const float* a0v, BaseState& s, float h, float* bc) {
+  Twist v0, a0;
+  float Rl[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++) { v0.a[i] = bc[kBcV0 + i]; v0.l[i] = bc[kBcV0 + 3 + i]; a0.a[i] = a0v[i]; a0.l[i] = a0v[3 + i]; }
+#pragma unroll
+  for (int i = 0; i < 9; i++) Rl[i] = bc[kBcR + i];
+  // gravity enters as a uniform acceleration of every body (RBDA 9.4): classical acc of the base origin
+  float accb[3], wxv[3];
   cross3(v0.a, v0.l, wxv);
 #pragma unroll
   for (int i = 0; i < 3; i++) accb[i] = a0.l[i] + Rl[6 + i] * S.gz + wxv[i];
@@ -609,8 +623,6 @@ WS_HD void base_phase(const SimK& S, const BaseInertia& B, const float* legsum, 
   const float nw = w - hx * (s.w[0] * x + s.w[1] * y + s.w[2] * z);
   const float inv = rsqrt_fast(nx * nx + ny * ny + nz * nz + nw * nw);
   s.quat[0] = nx * inv; s.quat[1] = ny * inv; s.quat[2] = nz * inv; s.quat[3] = nw * inv;
-#pragma unroll
-  for (int i = 0; i < 3; i++) { bc[kBcA0 + i] = a0.a[i]; bc[kBcA0 + 3 + i] = a0.l[i]; }
   base_publish(s, bc);
 }
 

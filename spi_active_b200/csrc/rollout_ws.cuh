@@ -1,9 +1,12 @@
 // rollout_ws.cuh — the warp-specialised fused rollout kernel (see go2_ws.cuh for the role arithmetic and
 // DESIGN.md §4.2 for the mapping).  One CTA = 32 (candidate, segment) rollouts x 5 warps:
-//   4 leg warps (lane = rollout) + 1 base warp; roles rotate with blockIdx so that the base warp of the
-//   CTAs resident on an SM spreads over the 4 SM sub-partitions.
+//   4 leg warps (lane = rollout) + 1 base warp.  The base role sits on the HIGHEST warp id of the CTA: it is the
+//   critical path between the two leg phases and the sub-partition arbiter favours high warp ids (measured:
+//   +8.6 % over rotating the roles with blockIdx, profiles/README.md).  5-warp CTAs spread over the 4
+//   sub-partitions by themselves.
 // Per integrator sub-step:   legs: phase 1 -> smem[27] | barrier | base: sum, 6x6 solve, integrate ->
-//   smem[22] | barrier | legs: phase 2.
+//   a0 -> smem[6] | barrier | legs: phase 2, overlapped with base: integrate, publish R / v0 / pz -> smem[16],
+//   bias force of the next sub-step | barrier.
 #pragma once
 #include "go2_ws.cuh"
 
@@ -95,11 +98,12 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, int lan
         leg_phase1(S, L, bc, s, tau, K, out, nullptr);
 #pragma unroll
         for (int i = 0; i < kLegOut; i++) sm.part[LEG][i][lane] = out[i];
-        ws_barrier();   // [A] leg contributions are in shared memory
-        ws_barrier();   // [B] the base role has published a0 and the new R / v0 / pz
+        ws_barrier();   // [A]  leg contributions are in shared memory
+        ws_barrier();   // [B1] the base role has published a0
 #pragma unroll
         for (int i = 0; i < 6; i++) bc[kBcA0 + i] = sm.bc[kBcA0 + i][lane];
         leg_phase2(L, bc, K, s, h);
+        ws_barrier();   // [B2] the base role has published R / v0 / pz of the new state
       }
     }
     if (RECORD) {
@@ -149,6 +153,8 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, int la
   base_publish(s, bc);
 #pragma unroll
   for (int i = kBcR; i < kBaseOut; i++) sm.bc[i][lane] = bc[i];
+  float pb[6];
+  base_bias(B, bc, pb);
   ws_barrier();   // [S0]
   const float h = S.dt / (float)S.nsub;
   for (int k = 0; k < A.H; k++) {
@@ -159,10 +165,16 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, int la
 #pragma unroll
         for (int i = 0; i < kLegOut; i++)
           legsum[i] = (sm.part[0][i][lane] + sm.part[1][i][lane]) + (sm.part[2][i][lane] + sm.part[3][i][lane]);
-        base_phase(S, B, legsum, s, h, bc);
+        float a0[6];
+        base_solve(B, legsum, pb, a0);
 #pragma unroll
-        for (int i = 0; i < kBaseOut; i++) sm.bc[i][lane] = bc[i];
-        ws_barrier();   // [B]
+        for (int i = 0; i < 6; i++) sm.bc[kBcA0 + i][lane] = a0[i];
+        ws_barrier();   // [B1] the legs start their acceleration pass
+        base_advance(S, a0, s, h, bc);
+#pragma unroll
+        for (int i = kBcR; i < kBaseOut; i++) sm.bc[i][lane] = bc[i];
+        base_bias(B, bc, pb);   // velocity-product bias of the next sub-step, off the critical path
+        ws_barrier();   // [B2]
       }
     }
     if (RECORD) {

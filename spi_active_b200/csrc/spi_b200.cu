@@ -402,6 +402,7 @@ struct spi_b200_model {
   DeviceModel* d_model = nullptr;
   ws::ModelK ws_model;      // constants of the warp-specialised fast path (passed as a kernel parameter)
   bool ws_ok = false;       // the blob has the Go2-family structure the fast path is compiled for
+  int kernel = SPI_KERNEL_AUTO;
   int device = 0;
   // workspaces (grown on demand)
   float* d_partial = nullptr; size_t partial_cap = 0;
@@ -553,7 +554,7 @@ int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C
   A.seg_init = seg_init; A.seg_actions = seg_actions; A.seg_target = seg_target; A.seg_gains = seg_gains;
   A.seg_mask = seg_mask; A.S = S; A.H = H; A.decimation = decimation; A.motor_model = motor_model; A.flags = flags;
   A.n_cta_per_cand = (S + ws::kWsRollouts - 1) / ws::kWsRollouts;
-  { static const int rot = getenv("SPI_B200_WS_ROT") ? atoi(getenv("SPI_B200_WS_ROT")) : 1; A.rotate_roles = rot; }
+  { static const int rot = getenv("SPI_B200_WS_ROT") ? atoi(getenv("SPI_B200_WS_ROT")) : 0; A.rotate_roles = rot; }
   const long long n_cta = (long long)C * A.n_cta_per_cand;
   if (n_cta > 2147483647LL) return fail(-3, "C * ceil(S/32) exceeds the grid limit");
   const int minb = minb_choice();
@@ -572,8 +573,9 @@ int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C
     CUDA_OK(cudaEventRecord(e0, st));
   }
   if (minb == 2) ws::rollout_ws_kernel<false, 2><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
-  else if (minb == 4) ws::rollout_ws_kernel<false, 4><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
-  else ws::rollout_ws_kernel<false, 3><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
+  else if (minb == 3) ws::rollout_ws_kernel<false, 3><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
+  else if (minb == 5) ws::rollout_ws_kernel<false, 5><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
+  else ws::rollout_ws_kernel<false, 4><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
   if (int rc = check_launch("rollout_ws_kernel")) return rc;
   if (m->timing) {
     CUDA_OK(cudaEventRecord(e1, st));
@@ -597,7 +599,8 @@ int launch_rollout(spi_b200_model* m, bool record, const float* params, int C, i
   if (record && !out_states) return fail(-3, "out_states is NULL");
   if (P > 0 && !params) return fail(-3, "params is NULL");
   if (motor_model < SPI_MOTOR_NONE || motor_model > SPI_MOTOR_VEC3_TANH) return fail(-3, "unknown motor_model");
-  if (m->ws_ok && kernel_choice() != 1)
+  if (m->kernel == SPI_KERNEL_WS && !m->ws_ok) return fail(-6, "the model blob does not have the Go2-family structure of the fast path");
+  if (m->ws_ok && m->kernel != SPI_KERNEL_LANE && (m->kernel == SPI_KERNEL_WS || kernel_choice() != 1))
     return launch_rollout_ws(m, record, params, C, P, param_ids, seg_init, seg_actions, seg_target, seg_gains, seg_mask,
                              S, H, decimation, motor_model, flags, cost_denominator, out_cost, out_per_seg, out_status,
                              out_states, st);
@@ -686,6 +689,14 @@ int spi_b200_model_destroy(spi_b200_model* m) {
   for (auto e : m->ev_pool) cudaEventDestroy(e);
   for (auto e : m->ev_pending) cudaEventDestroy(e);
   delete m;
+  return 0;
+}
+
+int spi_b200_model_set_kernel(spi_b200_model* m, int kernel) {
+  if (!m) return fail(-1, "model handle is NULL");
+  if (kernel < SPI_KERNEL_AUTO || kernel > SPI_KERNEL_WS) return fail(-3, "unknown kernel id");
+  if (kernel == SPI_KERNEL_WS && !m->ws_ok) return fail(-6, "the model blob does not have the Go2-family structure of the fast path");
+  m->kernel = kernel;
   return 0;
 }
 

@@ -253,6 +253,11 @@ class RolloutEngine:
         _lib.check(rc, "spi_b200_fp32_peak")
         return float(tf.value), float(ms.value)
 
+    def set_kernel(self, kernel: str = "auto") -> None:
+        """'auto' | 'lane' (generic leg-per-lane kernel) | 'ws' (warp-specialised Go2-family fast path)."""
+        kid = {"auto": 0, "lane": 1, "ws": 2}[kernel]
+        _lib.check(self.lib.spi_b200_model_set_kernel(self._handle, kid), "spi_b200_model_set_kernel")
+
     def timing_enable(self, on: bool = True) -> None:
         """Bracket every rollout-kernel launch with CUDA events on its stream (roofline instrumentation)."""
         _lib.check(self.lib.spi_b200_timing_enable(self._handle, int(bool(on))), "spi_b200_timing_enable")

@@ -33,10 +33,14 @@ def oracle_lib():
     return orc
 
 
-@pytest.fixture(scope="session")
-def engine():
+@pytest.fixture(scope="session", params=["ws", "lane"])
+def engine(request):
+    """One engine per rollout kernel: the warp-specialised fast path and the generic leg-per-lane kernel run the
+    whole GPU suite."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from spi_active_b200.engine import RolloutEngine
-    return RolloutEngine()
+    eng = RolloutEngine()
+    eng.set_kernel(request.param)
+    return eng

@@ -36,6 +36,8 @@ extern "C" int ws_emulate_rollout(const float* blob, const float* params, int P,
   float bc[kBaseOut];
   for (int i = 0; i < kBaseOut; i++) bc[i] = 0.f;
   base_publish(bs, bc);
+  float pb[6];
+  base_bias(B, bc, pb);
   const float h = M.sim.dt / (float)M.sim.nsub;
   LegKeep K[4];
   float part[4][kLegOut], ff[4][3];
@@ -52,7 +54,11 @@ extern "C" int ws_emulate_rollout(const float* blob, const float* params, int P,
         for (int leg = 0; leg < 4; leg++) leg_phase1(M.sim, M.leg[leg], bc, ls[leg], tau[leg], K[leg], part[leg], ff[leg]);
         float legsum[kLegOut];
         for (int i = 0; i < kLegOut; i++) legsum[i] = (part[0][i] + part[1][i]) + (part[2][i] + part[3][i]);
-        base_phase(M.sim, B, legsum, bs, h, bc);
+        base_solve(B, legsum, pb, bc + kBcA0);      // between barriers A and B1
+        float a0[6];
+        for (int i = 0; i < 6; i++) a0[i] = bc[kBcA0 + i];
+        base_advance(M.sim, a0, bs, h, bc);         // between barriers B1 and B2 (legs run phase 2 meanwhile)
+        base_bias(B, bc, pb);
         for (int leg = 0; leg < 4; leg++) leg_phase2(M.leg[leg], bc, K[leg], ls[leg], h);
       }
     }

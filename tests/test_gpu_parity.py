@@ -1,11 +1,13 @@
 """GPU parity: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
 
 Tolerances (fp32 kernel vs fp64 oracle, both integrating the same 40 sub-steps per H=5 rollout):
-  per-step states   |d| <= 2e-4 absolute (positions m, quaternion, joint rad), 5e-3 on velocities
-  per-sample errors |d| <= 2e-4 absolute
-  mean costs        rel 2e-4 + abs 2e-5
-The fp32-vs-fp64 noise floor of the oracle itself (float instantiation) is asserted to be of the
-same order, so the tolerance is a statement about fp32, not about the kernel.
+  per-step states   |d| <= 2e-5 absolute (positions m, quaternion, joint rad), 2e-3 on velocities
+  per-sample errors |d| <= 2e-5 absolute
+  mean costs        rel 5e-5 + abs 2e-6
+Measured on B200 over the whole `all` dataset x 16 ten-parameter candidates (tools/dev_accuracy.py): the kernel
+deviates from the fp64 oracle by at most 1.5e-7 / 2.5e-7 / 2.7e-6 (pos / quat / joint per-sample errors), the
+oracle's OWN float instantiation by 1.4e-7 / 1.7e-7 / 1.7e-6 — the kernel sits on the fp32 noise floor; the
+tolerances are ~10x that floor, so they are a statement about fp32, not about the kernel.
 """
 import numpy as np
 import pytest
@@ -40,8 +42,8 @@ def test_eval_candidates_matches_oracle(engine, oracle_lib, blob, config, H):
     ref_cost, ref_status, ref_per = oracle_lib.eval_candidates(blob, params, [0], init, act, tgt, gains, mask,
                                                                cost_denominator=denom, return_per_seg=True)
     assert status.cpu().numpy().sum() == 0 and ref_status.sum() == 0
-    np.testing.assert_allclose(per.cpu().numpy(), ref_per, atol=2e-4, rtol=0)
-    np.testing.assert_allclose(cost.cpu().numpy(), ref_cost, rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(per.cpu().numpy(), ref_per, atol=2e-5, rtol=0)
+    np.testing.assert_allclose(cost.cpu().numpy(), ref_cost, rtol=5e-5, atol=2e-6)
     # same argmin of the weighted landscape
     w = np.array([10.0, 5.0, 1.0])
     assert int(np.argmin(cost.cpu().numpy() @ w)) == int(np.argmin(ref_cost @ w))
@@ -55,7 +57,7 @@ def test_fp32_noise_floor_of_oracle(oracle_lib, blob):
                                              return_per_seg=True)
     c32, _, p32 = oracle_lib.eval_candidates(blob, params, [0], init, act, tgt, gains, mask, cost_denominator=denom,
                                              precision=32, return_per_seg=True)
-    assert np.abs(p64 - p32).max() < 2e-4
+    assert np.abs(p64 - p32).max() < 2e-5
 
 
 def test_rollout_states_per_step(engine, oracle_lib, blob):
@@ -68,10 +70,10 @@ def test_rollout_states_per_step(engine, oracle_lib, blob):
                                torch.from_numpy(act[sel]), torch.from_numpy(gains[sel])).cpu().numpy()
     ref = oracle_lib.rollout_states(blob, params, [gm.PARAM_IDS[n] for n in names], init[sel], act[sel], gains[sel])
     assert st.shape == ref.shape
-    np.testing.assert_allclose(st[..., :7], ref[..., :7], atol=2e-4, rtol=0)       # pos, quat
-    np.testing.assert_allclose(st[..., 13:25], ref[..., 13:25], atol=2e-4, rtol=0)  # joint pos
-    np.testing.assert_allclose(st[..., 7:13], ref[..., 7:13], atol=5e-3, rtol=0)    # base vel
-    np.testing.assert_allclose(st[..., 25:37], ref[..., 25:37], atol=2e-2, rtol=0)  # joint vel
+    np.testing.assert_allclose(st[..., :7], ref[..., :7], atol=2e-5, rtol=0)       # pos, quat
+    np.testing.assert_allclose(st[..., 13:25], ref[..., 13:25], atol=2e-5, rtol=0)  # joint pos
+    np.testing.assert_allclose(st[..., 7:13], ref[..., 7:13], atol=2e-3, rtol=0)    # base vel
+    np.testing.assert_allclose(st[..., 25:37], ref[..., 25:37], atol=1e-2, rtol=0)  # joint vel
 
 
 @pytest.mark.parametrize("motor,flags", [("act2tau_scalar", 0), ("act2tau_vec3", 0), ("act2tau_vec3_tanh", 0),
@@ -89,7 +91,7 @@ def test_motor_models_in_rollout(engine, oracle_lib, blob, motor, flags):
     init, act, tgt, gains, mask, denom = synth.pack_numpy(ds)
     ref, _ = oracle_lib.eval_candidates(blob, params, [gm.PARAM_IDS[n] for n in names], init, act, tgt, gains, mask,
                                         motor_model=gm.MOTOR_MODELS[motor], flags=flags, cost_denominator=denom)
-    np.testing.assert_allclose(cost.cpu().numpy(), ref, rtol=3e-4, atol=3e-5)
+    np.testing.assert_allclose(cost.cpu().numpy(), ref, rtol=5e-5, atol=2e-6)
 
 
 def test_full_parameter_vector(engine, oracle_lib, blob):
@@ -111,7 +113,7 @@ def test_full_parameter_vector(engine, oracle_lib, blob):
     ref, ref_status = oracle_lib.eval_candidates(blob, params, ids, init, act, tgt, gains, mask, motor_model=3,
                                                  cost_denominator=denom)
     assert status.cpu().numpy().sum() == 0
-    np.testing.assert_allclose(cost.cpu().numpy(), ref, rtol=3e-4, atol=3e-5)
+    np.testing.assert_allclose(cost.cpu().numpy(), ref, rtol=5e-5, atol=2e-6)
 
 
 def test_host_entry_point_matches_device(engine):
@@ -148,7 +150,7 @@ def test_mask_and_ragged_sizes(engine, oracle_lib, blob):
         params = np.array([[6.0], [8.0], [7.0]], np.float32)
         cost = engine.evaluate_candidates(torch.from_numpy(params), ["mass"], segs).cpu().numpy()
         ref, _ = oracle_lib.eval_candidates(blob, params, [0], init[:n], act[:n], tgt[:n], gains[:n], m)
-        np.testing.assert_allclose(cost, ref, rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(cost, ref, rtol=5e-5, atol=2e-6)
 
 
 def test_nonfinite_candidate_flagged(engine):
