@@ -1,0 +1,153 @@
+"""`simulator=b200` plugin (boundary B1): host logic on CPU with an oracle-backed stand-in for the CUDA engine, and
+on the GPU the stepwise path (set state -> H x decimation x (torque, simulate) -> errors, i.e. what the reference's
+evaluate_batch does through BaseSimulator) against the fused operator on the same inputs."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from spi_active_b200 import dataset as dsmod
+from spi_active_b200 import go2_model as gm
+from spi_active_b200.simulator import B200Sim
+
+import synth
+
+
+class OracleBackend:
+    """Same two-method shape as RolloutEngine (sim_step, close), physics by the CPU oracle — test infrastructure."""
+
+    def __init__(self, blob):
+        self.blob = blob
+
+    def sim_step(self, state, torques, n_steps=1, params=None, param_names=(), flags=0, foot_force=None):
+        from oracle import oracle as orc
+        ids = [gm.PARAM_IDS[n] for n in param_names]
+        new, ff = orc.sim_step(self.blob, state.numpy().astype(np.float64), torques.numpy().astype(np.float64), n_steps,
+                               params=None if params is None else params.numpy(), param_ids=ids, flags=flags,
+                               return_foot_force=True)
+        state.copy_(torch.from_numpy(new.astype(np.float32)))
+        if foot_force is not None:
+            foot_force.copy_(torch.from_numpy(ff.astype(np.float32)))
+        return state
+
+    def close(self):
+        pass
+
+
+def _config(num_envs, params_dict=None):
+    m = gm.go2_nominal()
+    return SimpleNamespace(
+        num_envs=num_envs, headless=True, params_dict=params_dict,
+        simulator=SimpleNamespace(config=SimpleNamespace(sim=SimpleNamespace(fps=200, control_decimation=4, substeps=1))),
+        robot=SimpleNamespace(dof_names=list(gm.DOF_NAMES), body_names=list(gm.BODY_NAMES),
+                              dof_vel_limit_list=list(m.qd_limit), dof_effort_limit_list=list(m.torque_limit)),
+        rewards=SimpleNamespace(reward_limit=SimpleNamespace(soft_dof_pos_limit=0.9)),
+        termination_scales=SimpleNamespace(termination_close_to_dof_pos_limit=0.98),
+        terrain=SimpleNamespace(mesh_type="plane"))
+
+
+def _make_sim(num_envs, device, backend=None, params_dict=None):
+    sim = B200Sim(config=_config(num_envs, params_dict), device=device, backend=backend)
+    sim.set_headless(True)
+    sim.setup()
+    sim.setup_terrain("plane")
+    sim.load_assets()
+    init = torch.tensor([0, 0, 0.34, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0], dtype=torch.float32)
+    sim.create_envs(num_envs, torch.zeros(num_envs, 3), init)
+    limits = sim.get_dof_limits_properties()
+    sim.prepare_sim()
+    return sim, limits
+
+
+def _replay(sim, ds, H, model, base_mass=None):
+    """evaluate_batch's body for one chunk (scripts/eval.py:243-296) + LeggedRobotBase.step's control path
+    (legged_robot_base.py:185-209, 545, 557), written against the BaseSimulator surface only."""
+    N, dev = sim.num_envs, sim.all_root_states.device
+    t = lambda a: torch.as_tensor(a, dtype=torch.float32, device=dev)
+    if base_mass is not None:   # apply_base_mass (scripts/eval.py:204-214) through the gym shim
+        ref = model.body_masses_isaac_order()
+        for env_ptr, actor in zip(sim.envs, sim.robot_handles):
+            props = sim.gym.get_actor_rigid_body_properties(env_ptr, actor)
+            for idx, prop in enumerate(props):
+                prop.mass = float(ref[idx]) if idx else float(base_mass)
+            sim.gym.set_actor_rigid_body_properties(env_ptr, actor, props, recomputeInertia=True)
+        sim.gym.refresh_mass_matrix_tensors(sim.sim)
+    env_ids = torch.arange(N, device=dev)
+    root = sim.robot_root_states.clone()
+    root[:, 0:3], root[:, 3:7] = t(ds["init_base_pos"]), t(ds["init_base_ori"])
+    root[:, 7:10], root[:, 10:13] = t(ds["init_base_lin_vel"]), t(ds["init_base_ang_vel"])
+    sim.set_actor_root_state_tensor(env_ids, root)
+    dof = sim.dof_state.view(N, 12, 2)
+    dof[:, :, 0], dof[:, :, 1] = t(ds["init_joint_pos"]), t(ds["init_joint_vel"])     # in-place view write (eval.py:261-266)
+    sim.set_dof_state_tensor(env_ids, sim.dof_state)
+    sim.refresh_sim_tensors()
+    kp, kd = t(ds["pd_gain_kp"][0]), t(ds["pd_gain_kd"][0])
+    qdef, tlim = t(model.q_default), t(model.torque_limit)
+    acts = t(ds["action_sequences"])
+    for k in range(H):
+        a = torch.clip(acts[:, k], -model.action_clip, model.action_clip)
+        for _ in range(model.control_decimation):
+            tau = kp * (a * model.action_scale + qdef - sim.dof_pos) - kd * sim.dof_vel
+            sim.apply_torques_at_dof(torch.clip(tau, -tlim, tlim))
+            sim.simulate_at_each_physics_step()
+        sim.refresh_sim_tensors()
+    e_pos = torch.norm(sim.robot_root_states[:, 0:3] - t(ds["target_base_pos"]), dim=1)
+    e_quat = torch.norm(sim.robot_root_states[:, 3:7] - t(ds["target_base_ori"]), dim=1)
+    e_joint = torch.norm(sim.dof_pos - t(ds["target_joint_pos"]), dim=1)
+    return torch.stack([e_pos, e_quat, e_joint], dim=1).cpu().numpy()
+
+
+def test_plugin_surface_and_limits(blob, nominal_model):
+    sim, (pos_lim, vel_lim, tau_lim) = _make_sim(5, "cpu", OracleBackend(blob))
+    assert (sim.num_dof, sim.num_bodies) == (12, 19) and sim.sim_dt == 0.005 and sim.device == "cpu"
+    assert sim.find_rigid_body_indice("FR_foot") == 8 and sim.find_rigid_body_indice("RR_foot") == 18
+    np.testing.assert_allclose(tau_lim.numpy(), nominal_model.torque_limit)
+    mid = (np.asarray(nominal_model.q_lower) + np.asarray(nominal_model.q_upper)) / 2
+    rng = np.asarray(nominal_model.q_upper) - np.asarray(nominal_model.q_lower)
+    np.testing.assert_allclose(pos_lim[:, 0].numpy(), mid - 0.45 * rng, rtol=1e-6)        # soft limits (isaacgym.py:343-346)
+    np.testing.assert_allclose(sim.dof_pos_limits_termination[:, 1].numpy(), mid + 0.49 * rng, rtol=1e-6)
+    # tensor attributes share storage the way the env layer relies on (eval.py:261-266)
+    sim.dof_state.view(5, 12, 2)[:, :, 0] = 0.25
+    assert float(sim.dof_pos[3, 7]) == 0.25 and sim.base_quat.data_ptr() == sim.robot_root_states[:, 3:7].data_ptr()
+    assert sim.contact_forces.shape == (5, 19, 3) and sim._rigid_body_pos.shape == (5, 19, 3)
+    props = sim.gym.get_actor_rigid_body_properties(sim.envs[0], sim.robot_handles[0])
+    assert len(props) == 19 and abs(sum(p.mass for p in props) - 15.019) < 1e-3 and abs(props[0].com.x - 0.021112) < 1e-7
+    with pytest.raises(NotImplementedError):
+        sim.setup_viewer()
+    with pytest.raises(NotImplementedError):
+        sim.setup_terrain("trimesh")
+    with pytest.raises(AssertionError):
+        bad = B200Sim(config=_config(1), device="cpu", backend=OracleBackend(blob)); bad.robot_config.dof_names[0] = "x"; bad.load_assets()
+
+
+def test_params_dict_overrides(blob):
+    """isaacgym_active_sysid.py:39-94: per-env values; `inertiaiy` (sic) accepted; strict flag drops inertiay."""
+    pd = {"mass": {"body_name": "base", "value": [9.39, 9.49]}, "comx": {"body_name": "base", "value": [0.0, 0.1]},
+          "inertiaiy": {"body_name": "base", "value": [0.005, 0.105]}, "motor_model_hip_a": {"value": [20.0, 20.1]}}
+    sim, _ = _make_sim(2, "cpu", OracleBackend(blob), params_dict=pd)
+    np.testing.assert_allclose(sim._params_host[:, 0], [9.39, 9.49])
+    np.testing.assert_allclose(sim._params_host[:, 1], [0.0, 0.1])
+    np.testing.assert_allclose(sim._params_host[:, 5], [0.005, 0.105])
+
+
+def test_stepwise_replay_on_oracle_backend_matches_fused_oracle(oracle_lib, blob, nominal_model):
+    S, ds = synth.dataset("sine", 5, steps=30)
+    sim, _ = _make_sim(S, "cpu", OracleBackend(blob))
+    per = _replay(sim, ds, 5, nominal_model, base_mass=8.5)
+    init, act, tgt, gains, mask, denom = synth.pack_numpy(ds)
+    _, _, ref = oracle_lib.eval_candidates(blob, np.array([[8.5]], np.float32), [0], init, act, tgt, gains, mask,
+                                           return_per_seg=True)
+    np.testing.assert_allclose(per, ref[0], atol=2e-6)     # fp32 tensors between steps vs fp64 throughout
+    assert float(sim.contact_forces[:, [4, 8, 14, 18], 2].sum()) > 0
+
+
+@pytest.mark.gpu
+def test_stepwise_replay_on_gpu_matches_fused_operator(engine, nominal_model):
+    S, ds = synth.dataset("jump", 5, steps=60)
+    sim, _ = _make_sim(S, str(engine.device))
+    per = _replay(sim, ds, 5, nominal_model, base_mass=8.5)
+    segs = dsmod.pack_segments(dsmod.to_device(ds, engine.device))
+    _, fused = engine.evaluate_candidates(torch.tensor([[8.5]]), ["mass"], segs, return_per_seg=True)
+    np.testing.assert_allclose(per, fused[0].cpu().numpy(), atol=2e-5)
+    assert float(sim.contact_forces[:, [4, 8, 14, 18], 2].abs().sum()) > 0
