@@ -50,6 +50,20 @@ WS_HD float rsqrt_fast(float x) {
   return 1.0f / std::sqrt(x);
 #endif
 }
+// (off by default: measured neutral on B200, profiles/README.md)  tanh through one ex2 and one reciprocal: |abs error| <= ~2e-7 (the motor model a * tanh(tau / a) only needs an
+// absolute accuracy: 2e-7 * a ~ 4e-6 N m).  tanh(x) = sign(x) (1 - 2 / (exp(2|x|) + 1))
+WS_HD float tanh_fast(float x) {
+#if defined(__CUDA_ARCH__) && defined(SPI_WS_FAST_TANH)
+  const float ax = fminf(fabsf(x), 15.0f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * 2.8853900817779268f));
+  const float r = fmaf(-2.0f, rcp_fast(e + 1.0f), 1.0f);
+  return copysignf(r, x);
+#else
+  return tanhf(x);
+#endif
+}
+
 WS_HD void sincos_joint(float q, float* s, float* c) {
 #if defined(__CUDA_ARCH__)
 #if defined(SPI_WS_FAST_SINCOS)
@@ -637,13 +651,13 @@ WS_HD void leg_torques(const SimK& S, const LegK& L, const float* act /*clipped*
     float t = kp[j] * (as + L.qdef[j] - q[j]) - kd[j] * qd[j];
     const float g = motor[j];
     if (motor_model == SPI_MOTOR_VEC3_TANH && (flags & SPI_FLAG_TANH_BEFORE_CLIP)) {
-      t = g * tanhf((1.0f / g) * t);
+      t = g * tanh_fast(rcp_fast(g) * t);
       t = fminf(fmaxf(t, -L.tlim[j]), L.tlim[j]);
     } else {
       t = fminf(fmaxf(t, -L.tlim[j]), L.tlim[j]);
       if (motor_model == SPI_MOTOR_SCALAR) t *= motor[0];
       else if (motor_model == SPI_MOTOR_VEC3) t *= g;
-      else if (motor_model == SPI_MOTOR_VEC3_TANH) t = g * tanhf((1.0f / g) * t);
+      else if (motor_model == SPI_MOTOR_VEC3_TANH) t = g * tanh_fast(rcp_fast(g) * t);
     }
     tau[j] = t;
   }

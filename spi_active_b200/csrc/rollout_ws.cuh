@@ -227,8 +227,8 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, int la
   }
 }
 
-template <bool RECORD, int MINB>
-__global__ void __launch_bounds__(kWsThreads, MINB) rollout_ws_kernel(const __grid_constant__ WsArgs A) {
+template <bool RECORD>
+__device__ __forceinline__ void rollout_ws_body(const WsArgs& A) {
   __shared__ WsSmem sm;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int role = __shfl_sync(0xffffffffu, A.rotate_roles ? (warp + blockIdx.x) % kWsWarps : warp, 0);  // warp-uniform
@@ -240,5 +240,11 @@ __global__ void __launch_bounds__(kWsThreads, MINB) rollout_ws_kernel(const __gr
   if (role < 4) ws_leg_role<RECORD>(A, sm, lane, role, c, seg, active);
   else ws_base_role<RECORD>(A, sm, lane, c, cta_in_cand, seg, active);
 }
+
+template <bool RECORD, int MINB>
+__global__ void __launch_bounds__(kWsThreads, MINB) rollout_ws_kernel(const __grid_constant__ WsArgs A) {
+  rollout_ws_body<RECORD>(A);
+}
+
 
 }  // namespace ws

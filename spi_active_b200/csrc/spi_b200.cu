@@ -574,7 +574,6 @@ int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C
   }
   if (minb == 2) ws::rollout_ws_kernel<false, 2><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
   else if (minb == 3) ws::rollout_ws_kernel<false, 3><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
-  else if (minb == 5) ws::rollout_ws_kernel<false, 5><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
   else ws::rollout_ws_kernel<false, 4><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
   if (int rc = check_launch("rollout_ws_kernel")) return rc;
   if (m->timing) {
