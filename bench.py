@@ -219,7 +219,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -384,20 +384,48 @@ def run_b200(args):
         "gpu_launches": int(launches), "clocks": clocks,
         "best": {"cost": float(best[-1]), "base_mass_kg": float(best[0])},
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+class _StdoutGuard:
+    """Everything the process (python or C libraries such as NCCL's version banner) writes to fd 1 goes to stderr;
+    the one JSON line of the contract is written to the real stdout with emit()."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+
+_GUARD = None
+
+
+def emit(obj):
+    line = json.dumps(obj)
+    if _GUARD is not None:
+        _GUARD.emit(line)
+    else:
+        print(line, flush=True)
+
+
 def main():
+    global _GUARD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
+    if not (args.gpus > 1 and "WORLD_SIZE" not in os.environ and args.impl != "reference"):
+        _GUARD = _StdoutGuard()
     if args.impl == "reference":
         return run_reference(args)
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:

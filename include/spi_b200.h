@@ -184,6 +184,15 @@ int spi_b200_sim_step(spi_b200_model* model,
                       float* state, const float* torques, int N, int n_steps,
                       float* out_foot_force, void* cuda_stream);
 
+/* One CONTROL step of N independent envs, each with its own parameter row (the closed-loop / active-exploration path:
+ * LeggedRobotBase.step without the observation / reward bookkeeping, legged_robot_base.py:169-209, with the torque law
+ * of the env in use, go2_omni.py:423-465 + active_sysid_openloop.py:174-187): clip the action, then `decimation` x
+ * (PD + motor model from the fresh q, qd -> one physics step).
+ *   params [N,P] or NULL, state [N,37] in/out, actions [N,12], gains [N,24] or NULL -> blob defaults               */
+int spi_b200_env_step(spi_b200_model* model, const float* params, int P, const int* param_ids, float* state,
+                      const float* actions, const float* gains, int N, int decimation, int motor_model,
+                      unsigned flags, void* cuda_stream);
+
 /* Motor-model + PD torque operator on its own (parity hook for
  * legged_robot_base.py:545,557 and active_sysid_openloop.py:356-400):
  *   tau[N,12] = motor(clip(kp*(scale*a + q_default - q) - kd*qd))                             */

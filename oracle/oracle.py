@@ -107,6 +107,27 @@ def sim_step(blob, state, torques, n_steps=1, params=None, param_ids=None, flags
     return (state, ff) if return_foot_force else state
 
 
+def env_step(blob, state, actions, params=None, param_ids=None, gains=None, decimation=4, motor_model=0, flags=0):
+    """One control step of N independent envs (own parameter row each): state[N,37] float64 (copied) -> new state."""
+    blob = _f32(blob)
+    state = np.array(state, dtype=np.float64, order="C").reshape(-1, 37)
+    actions = _f32(actions).reshape(-1, 12)
+    N = state.shape[0]
+    P = 0
+    ids = np.zeros(1, dtype=np.int32)
+    if params is not None:
+        params = _f32(params).reshape(N, -1)
+        P = params.shape[1]
+        ids = np.ascontiguousarray(param_ids, dtype=np.int32)
+    gains = _f32(gains)
+    rc = lib().spi_oracle_env_step(_ptr(blob), C.c_int(blob.size), _ptr(params), C.c_int(P), _ptr(ids, C.c_int),
+                                   _ptr(state, C.c_double), _ptr(actions), _ptr(gains), C.c_int(N), C.c_int(decimation),
+                                   C.c_int(motor_model), C.c_uint(flags))
+    if rc != 0:
+        raise RuntimeError(f"spi_oracle_env_step failed: {rc}")
+    return state
+
+
 def forward_dynamics(blob, state, tau, params=None, param_ids=None, flags=0, with_contact=True, with_gravity=True):
     """-> base spatial accel in base coords [ang3, lin3], qdd[12], foot_force[4,3]"""
     blob = _f32(blob)

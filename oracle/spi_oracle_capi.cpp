@@ -159,6 +159,38 @@ int spi_oracle_sim_step(const float* blob, int n_floats, const float* params, in
   return 0;
 }
 
+// one CONTROL step of N independent envs, each with its own parameter row (closed-loop / active-exploration path):
+// LeggedRobotBase.step's control path (legged_robot_base.py:185-209) in double precision, state in/out
+int spi_oracle_env_step(const float* blob, int n_floats, const float* params, int P, const int* ids, double* state,
+                        const float* actions, const float* gains, int N, int decimation, int motor_model,
+                        unsigned flags) {
+  Model<double> M;
+  if (!M.load(blob, n_floats)) return -1;
+  parallel_for(N, 0, 8, [&](long long e) {
+    Candidate<double> cand = apply_params(M, params ? params + (size_t)e * P : nullptr, params ? P : 0, ids, flags);
+    Bodies<double> Ib = make_bodies(M, cand);
+    State<double> st;
+    double* sp = state + (size_t)e * SPI_STATE_DIM;
+    st.p = V3<double>(sp[0], sp[1], sp[2]);
+    for (int k = 0; k < 4; k++) st.quat[k] = sp[3 + k];
+    st.v = V3<double>(sp[7], sp[8], sp[9]);
+    st.w = V3<double>(sp[10], sp[11], sp[12]);
+    for (int j = 0; j < 12; j++) { st.q[j] = sp[13 + j]; st.qd[j] = sp[25 + j]; }
+    double kp[12], kd[12], a[12], tau[12];
+    for (int j = 0; j < 12; j++) {
+      kp[j] = gains ? (double)gains[(size_t)e * 24 + j] : M.kp[j];
+      kd[j] = gains ? (double)gains[(size_t)e * 24 + 12 + j] : M.kd[j];
+      a[j] = s_clip((double)actions[(size_t)e * 12 + j], -M.action_clip, M.action_clip);
+    }
+    for (int d = 0; d < decimation; d++) {
+      compute_torques(M, a, st.q, st.qd, kp, kd, cand.motor, motor_model, flags, tau);
+      physics_step(M, Ib, st, tau);
+    }
+    st.to(sp);
+  });
+  return 0;
+}
+
 // forward dynamics of one state (for the CRBA/RNEA cross-check and the invariants tests):
 // out_acc = base spatial acceleration in base coords [ang3, lin3] (gravity included if requested),
 // out_qdd[12], out_foot[4,3] world contact forces

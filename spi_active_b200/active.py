@@ -1,0 +1,463 @@
+"""Active exploration (BASELINE config 5): finite-difference Fisher-information rollouts of command trajectories
+under a trained locomotion policy, on the B200 engine.
+
+Mirrors (same names, argument meaning, results):
+  * spigym/envs/sysid/active_sysid_openloop.py:29-80     (1 main + P aux) env groups, +delta on one parameter each,
+                                                         `params_dict`, main_idx / aux_idx layout
+  * :116-131, 196-201                                    reset_all(main_commands) / open-loop command playback
+  * :174-187 + go2_omni.py:423-465                        torque law: hip x0.5 -> PD -> clip -> act2tau_* (fused in
+                                                         spi_b200_env_step)
+  * :203-252                                             _post_physics_step order: commands <- step_idx, termination,
+                                                         reward, observations, history push, k-step aux <- main sync
+  * :259-272                                             group-wise termination OR
+  * :402-426                                             _reward_fisher_information_matrix (spi_b200_fim_reward)
+  * spigym/envs/locomotion/go2_omni.py:348-377           _step_contact_targets (gait clock)
+  * :627-642                                             eval-mode command_body_height oscillator
+  * spigym/envs/legged_base_task/legged_robot_base.py:261-269, 336-339, 511-527, 819-829
+                                                         projected gravity / base ang vel, gravity termination,
+                                                         sorted-key observation concat, short_history layout
+  * spigym/envs/env_utils/history_handler.py:36-44       newest-first history push
+  * spigym/utils/helpers.py:77-94                        obs = getter * scale (+ noise, scales are 0 here)
+  * spigym/config/obs/loco/go2_omni.yaml                 keys, dims, scales, 14-frame history  -> 900-dim actor input
+  * spigym/agents/modules/modules.py:47-63, config/algo/ppo.yaml:32-40   actor MLP 900-512-256-128-12, ELU
+  * spigym/agents/sysid/active_sysid.py:528-600          evaluate_policy (1248 steps, zero actions / zero reward for
+                                                         terminated groups, mean over steps)
+  * :259-400                                             command samplers (constant / polynomial / bezier)
+  * :165-242                                             optimize (ask M trials -> evaluate -> tell -reward)
+
+The layer is device-agnostic torch around two engine calls (`env_step`, `fim_reward`), so the host logic runs on a CPU
+box against the oracle in tests; the product path is CUDA: physics = spi_b200_env_step, policy = cuBLAS GEMMs, FIM =
+spi_b200_fim_reward, one CUDA graph per control step.
+
+Reference quirks: D10 absolute delta (default) — `relative_delta=True` for the documented
+"10 %"; D11 the reference's k-step sync never reaches the simulator — here it does (the intent), `ksync_steps=0`
+disables it; D8 `inertiay` is applied.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import go2_model as gm
+
+# ---- observation layout (go2_omni.yaml; keys concatenated in SORTED order, legged_robot_base.py:521-527) -------------
+OBS_DIMS = dict(actions=12, base_ang_vel=3, clock_inputs=4, command_ang_vel=1, command_body_attitude=2,
+                command_body_height=1, command_footswing_height=1, command_gait_freq=1, command_gait_phase=4,
+                command_lin_vel=2, command_stance=2, dof_pos=12, dof_vel=12, projected_gravity=3)
+OBS_SCALES = dict(actions=1.0, base_ang_vel=0.25, clock_inputs=1.0, command_ang_vel=1.0, command_body_attitude=0.3,
+                  command_body_height=2.0, command_footswing_height=0.15, command_gait_freq=1.0, command_gait_phase=1.0,
+                  command_lin_vel=1.0, command_stance=1.0, dof_pos=1.0, dof_vel=0.05, projected_gravity=1.0)
+OBS_KEYS = sorted(OBS_DIMS)
+FRAME_DIM = sum(OBS_DIMS.values())          # 60
+HISTORY_LEN = 14
+ACTOR_OBS_DIM = FRAME_DIM * (1 + HISTORY_LEN)   # 900
+CLIP_OBSERVATIONS = 100.0                   # config/env/legged_base.yaml:19-21
+BODY_HEIGHT_LIMIT = (-0.25, 0.15)           # obs.commands.limit_body_height
+TERMINATION_GRAVITY = (0.8, 0.8)            # config/env/go2_omni.yaml:33-35
+
+# default command vector and ranges: config/algo/active_sysid.yaml:24-45
+DEFAULT_COMMAND = [0.5, 0.5, 0.5, 0.0, 3.0, 0.0, 0.5, 0.5, 0.5, 0.03, 0.0, 0.0, 0.3, 0.4]
+COMMAND_RANGES = [[-1.0, 1.0], [-1.0, 1.0], [-1.0, 1.0], [-0.25, 0.15], [2.0, 4.0], [0.0, 1.0], [0.0, 1.0], [0.0, 1.0],
+                  [0.5, 0.5], [0.03, 0.035], [-0.4, 0.4], [-0.0, 0.0], [0.1, 0.45], [0.35, 0.45]]
+COMMAND_SAMPLING_IDXS = [0, 2, 5]
+# default parameter set of the env: config/env/active_sysid_openloop.yaml:17-27
+DEFAULT_PARAM = dict(mass=9.39, comx=0.0, comy=0.0, comz=0.0, inertiax=0.005, inertiay=0.005, inertiaz=0.005,
+                     motor_model_hip_a=20.0, motor_model_thigh_a=20.0, motor_model_calf_a=20.0)
+
+
+def _history_gather_index() -> torch.Tensor:
+    """short_history = for key in sorted(keys): history[key][:, :14].reshape(N, 14 * dim) concatenated
+    (legged_robot_base.py:819-829).  With the frames stored as [N, 14, 60] (newest first, sorted-key order inside a
+    frame) that is a fixed gather of the flattened [14 * 60] axis."""
+    idx, off = [], 0
+    for key in OBS_KEYS:
+        d = OBS_DIMS[key]
+        for t in range(HISTORY_LEN):
+            idx.extend(t * FRAME_DIM + off + j for j in range(d))
+        off += d
+    return torch.tensor(idx, dtype=torch.long)
+
+
+def quat_rotate_inverse(q: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """spigym/utils/torch_utils.py:83-92 (q = xyzw)."""
+    q_w = q[:, 3:4]
+    q_vec = q[:, :3]
+    a = v * (2.0 * q_w ** 2 - 1.0)
+    b = torch.cross(q_vec, v, dim=-1) * q_w * 2.0
+    c = q_vec * (q_vec * v).sum(dim=1, keepdim=True) * 2.0
+    return a - b + c
+
+
+def step_contact_targets(gait_indices: torch.Tensor, commands: torch.Tensor, dt: float):
+    """go2_omni.py:348-377: advance the gait phase, warp the four foot phases by the stance duration, clock = sin.
+    Returns (new gait_indices[N], clock_inputs[N,4])."""
+    frequencies, phases, offsets, bounds, durations = (commands[:, 4], commands[:, 5], commands[:, 6], commands[:, 7],
+                                                       commands[:, 8])
+    gait_indices = torch.remainder(gait_indices + dt * frequencies, 1.0)
+    foot = torch.stack([gait_indices + phases + offsets + bounds, gait_indices + offsets, gait_indices + bounds,
+                        gait_indices + phases], dim=1)
+    r = torch.remainder(foot, 1.0)
+    d = durations[:, None]
+    stance, swing = r < d, r > d
+    warped = torch.where(stance, r * (0.5 / d), foot)
+    warped = torch.where(swing, 0.5 + (r - d) * (0.5 / (1 - d)), warped)
+    return gait_indices, torch.sin(2 * math.pi * warped)
+
+
+def build_frame(state: torch.Tensor, actions: torch.Tensor, commands: torch.Tensor, clock: torch.Tensor,
+                gait_indices: torch.Tensor, q_default: torch.Tensor) -> torch.Tensor:
+    """The 60 scaled per-step observation terms in sorted-key order (what the policy sees first and what is pushed
+    into the history)."""
+    quat = state[:, 3:7]
+    ang = quat_rotate_inverse(quat, state[:, 10:13])
+    grav = torch.zeros_like(ang)
+    grav[:, 2] = -1.0
+    pg = quat_rotate_inverse(quat, grav)
+    height = torch.clamp(commands[:, 3:4] + 0.20 * torch.sin(2 * math.pi * gait_indices[:, None]),
+                         min=BODY_HEIGHT_LIMIT[0], max=BODY_HEIGHT_LIMIT[1])        # go2_omni.py:627-642 (eval mode)
+    terms = dict(actions=actions, base_ang_vel=ang, clock_inputs=clock, command_ang_vel=commands[:, 2:3],
+                 command_body_attitude=commands[:, 10:12], command_body_height=height,
+                 command_footswing_height=commands[:, 9:10], command_gait_freq=commands[:, 4:5],
+                 command_gait_phase=commands[:, 5:9], command_lin_vel=commands[:, 0:2], command_stance=commands[:, 12:14],
+                 dof_pos=state[:, 13:25] - q_default, dof_vel=state[:, 25:37], projected_gravity=pg)
+    return torch.cat([terms[k] * OBS_SCALES[k] for k in OBS_KEYS], dim=1)
+
+
+class PolicyMLP:
+    """actor: Linear(900,512) ELU Linear(512,256) ELU Linear(256,128) ELU Linear(128,12); inference = mean action
+    (agents/modules/ppo_modules.py:73-75)."""
+
+    def __init__(self, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor]):
+        self.weights = [w.contiguous() for w in weights]
+        self.biases = [b.contiguous() for b in biases]
+
+    @classmethod
+    def random(cls, device, seed: int = 0, dims=(ACTOR_OBS_DIM, 512, 256, 128, 12), gain: float = 0.5):
+        g = torch.Generator().manual_seed(seed)
+        ws, bs = [], []
+        for i in range(len(dims) - 1):
+            ws.append((torch.randn(dims[i + 1], dims[i], generator=g) * gain / math.sqrt(dims[i])).to(device))
+            bs.append(torch.zeros(dims[i + 1]).to(device))
+        return cls(ws, bs)
+
+    @classmethod
+    def from_checkpoint(cls, path, device):
+        """PPO checkpoint: `actor_model_state_dict` (agents/ppo/ppo.py:138-143), Sequential keys `...module.{0,2,4,6}`."""
+        sd = torch.load(path, map_location="cpu")["actor_model_state_dict"]
+        w = sorted((k for k in sd if k.endswith(".weight")), key=lambda k: int(k.split(".")[-2]))
+        b = sorted((k for k in sd if k.endswith(".bias")), key=lambda k: int(k.split(".")[-2]))
+        return cls([sd[k].float().to(device) for k in w], [sd[k].float().to(device) for k in b])
+
+    def __call__(self, obs: torch.Tensor) -> torch.Tensor:
+        x = obs
+        n = len(self.weights)
+        for i, (w, b) in enumerate(zip(self.weights, self.biases)):
+            x = torch.addmm(b, x, w.t())
+            if i < n - 1:
+                x = torch.nn.functional.elu(x)
+        return x
+
+
+@dataclass
+class ActiveConfig:
+    exploration_params: List[str] = field(default_factory=lambda: ["mass"])
+    default_param: Dict[str, float] = field(default_factory=lambda: dict(DEFAULT_PARAM))
+    delta_param: float = 0.1
+    relative_delta: bool = False          # quirk D10
+    ksync_steps: int = 5
+    motor_model: str = "act2tau_vec3_tanh"
+    rollout_length: float = 25.0          # s  -> total_steps = 1250
+    action_clip: float = 20.0
+    termination_rew: float = 0.0
+    randomize_reset: bool = True          # legged_robot_base.py:737-784 reset distribution
+    seed: int = 0
+
+
+class ActiveExploration:
+    """(1 main + P aux) env groups on the engine; evaluate_policy(commands[M,T,14]) -> FIM rewards."""
+
+    PARAM_ORDER = ["mass", "comx", "comy", "comz", "inertiax", "inertiay", "inertiaz", "motor_model_hip_a",
+                   "motor_model_thigh_a", "motor_model_calf_a"]
+
+    def __init__(self, backend, policy: PolicyMLP, num_main_envs: int, cfg: Optional[ActiveConfig] = None,
+                 device=None, model: Optional[gm.Go2Model] = None):
+        self.backend, self.policy, self.cfg = backend, policy, cfg or ActiveConfig()
+        self.model = model or getattr(backend, "model", None) or gm.go2_nominal()
+        self.device = torch.device(device if device is not None else getattr(backend, "device", "cpu"))
+        c = self.cfg
+        self.param_dim = len(c.exploration_params)
+        self.num_main_envs = int(num_main_envs)
+        self.num_envs = self.num_main_envs * (self.param_dim + 1)
+        self.dt = self.model.dt * self.model.control_decimation
+        self.total_steps = int(c.rollout_length / self.dt)
+        # per-env parameter table (active_sysid_openloop.py:51-68): env (i + 1) mod (P + 1) gets +delta on parameter i
+        names = [n for n in self.PARAM_ORDER if n in c.default_param]
+        self.param_names = names
+        table = np.tile(np.array([c.default_param[n] for n in names], dtype=np.float64)[None], (self.num_envs, 1))
+        slot = np.arange(self.num_envs) % (self.param_dim + 1)
+        self.deltas = []
+        for i, p in enumerate(c.exploration_params):
+            col = names.index(p)
+            d = c.delta_param * abs(c.default_param[p]) if c.relative_delta else c.delta_param
+            table[slot == i + 1, col] += d
+            self.deltas.append(d)
+        self.params = torch.tensor(table, dtype=torch.float32, device=self.device)
+        self.params_dict = {n: {"value": table[:, j].tolist()} for j, n in enumerate(names)}   # reference layout
+        idx = torch.arange(self.num_envs, device=self.device).view(self.num_main_envs, self.param_dim + 1)
+        self.main_idx, self.aux_idx = idx[:, 0:1], idx[:, 1:]
+        self.q_default = torch.tensor(self.model.q_default, dtype=torch.float32, device=self.device)
+        self.hist_index = _history_gather_index().to(self.device)
+        N = self.num_envs
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)
+        self.state, self.actions, self.obs = z(N, gm.STATE_DIM), z(N, 12), z(N, ACTOR_OBS_DIM)
+        self.history, self.gait_indices, self.clock = z(N, HISTORY_LEN, FRAME_DIM), z(N), z(N, 4)
+        self.commands, self.next_commands = z(N, 14), z(N, 14)
+        self.done = torch.zeros(N, dtype=torch.bool, device=self.device)
+        self.total_reward, self.step_reward = z(N), z(N)
+        self.jtj = z(self.num_main_envs, self.param_dim, self.param_dim)
+        self.sync_flag = torch.zeros((), dtype=torch.bool, device=self.device)
+        self._graph = None
+
+    # ---- physics / reward through the engine -------------------------------------------------------------------------
+    def _physics(self):
+        self.backend.env_step(self.state, self.actions, params=self.params, param_names=self.param_names,
+                              motor_model=self.cfg.motor_model, flags=gm.FLAG_HIP_HALF)
+
+    def _fim(self):
+        """rew[N] = trace(J^T J) of the group, repeated to its P + 1 envs (active_sysid_openloop.py:402-426).  The
+        finite-difference divisor is the single configured delta, as in the reference (:412, :417)."""
+        M, P1 = self.num_main_envs, self.param_dim + 1
+        states = self.state[:, :25].reshape(M, P1, 25).contiguous()      # root13 (origins are 0) + q12
+        jtj, trace = self.backend.fim_reward(states, float(self.cfg.delta_param))
+        return trace.repeat_interleave(P1), jtj
+
+    # ---- one control step (everything between two policy evaluations) -------------------------------------------------------
+    def _env_step(self, actions: torch.Tensor):
+        c = self.cfg
+        # go2_omni.step: gait clock first, with the commands of the current step_idx
+        self.gait_indices, self.clock = step_contact_targets(self.gait_indices, self.commands, self.dt)
+        self.actions.copy_(torch.clip(actions, -c.action_clip, c.action_clip))     # _pre_physics_step
+        self._physics()                                                           # _physics_step
+        # _post_physics_step
+        self.commands.copy_(self.next_commands)                                   # _update_tasks_callback
+        grav = torch.zeros_like(self.state[:, 0:3]); grav[:, 2] = -1.0
+        pg = quat_rotate_inverse(self.state[:, 3:7], grav)
+        reset = (pg[:, 0].abs() > TERMINATION_GRAVITY[0]) | (pg[:, 1].abs() > TERMINATION_GRAVITY[1])
+        reset = reset | ~torch.isfinite(self.state).all(dim=1)
+        group = reset.view(self.num_main_envs, -1).any(dim=1, keepdim=True)        # _update_reset_buf group OR
+        self.done.copy_(group.expand(-1, self.param_dim + 1).reshape(-1))
+        rew, jtj = self._fim()                                                    # _compute_reward
+        frame = build_frame(self.state, self.actions, self.commands, self.clock, self.gait_indices, self.q_default)
+        hist_flat = self.history.reshape(self.num_envs, HISTORY_LEN * FRAME_DIM)
+        obs = torch.cat([frame, hist_flat[:, self.hist_index]], dim=1)             # _compute_observations
+        self.obs.copy_(torch.clip(obs, -CLIP_OBSERVATIONS, CLIP_OBSERVATIONS))
+        self.history.copy_(torch.cat([frame[:, None, :], self.history[:, :-1, :]], dim=1))   # history_handler.add
+        # k-step synchronisation aux <- main (the intent of :247-252, 316-330; quirk D11)
+        grp = self.state.view(self.num_main_envs, self.param_dim + 1, gm.STATE_DIM)
+        synced = grp[:, 0:1, :].expand(-1, self.param_dim + 1, -1).reshape(self.num_envs, gm.STATE_DIM)
+        self.state.copy_(torch.where(self.sync_flag, synced, self.state))
+        # active_sysid.py:567-577: terminated groups score termination_rew
+        rew = torch.where(self.done, torch.full_like(rew, c.termination_rew), torch.nan_to_num(rew, nan=0.0, posinf=0.0))
+        self.step_reward.copy_(rew)
+        self.total_reward.add_(rew)
+        live = (~self.done.view(self.num_main_envs, -1)[:, 0]).to(jtj.dtype)
+        self.jtj.add_(torch.nan_to_num(jtj) * live[:, None, None])
+
+    def _policy_step(self):
+        actions = self.policy(self.obs)
+        actions = torch.where(self.done[:, None], torch.zeros_like(actions), actions)   # active_sysid.py:559-562
+        self._env_step(actions)
+
+    # ---- reset ---------------------------------------------------------------------------------------------------------------
+    def reset_all(self, main_commands: torch.Tensor):
+        """active_sysid_openloop.py:116-131 + base_task.py:90-100: reset, then ONE env step with zero actions."""
+        c, N, P1 = self.cfg, self.num_envs, self.param_dim + 1
+        self.expanded_main_commands = main_commands.to(self.device, torch.float32).repeat_interleave(P1, dim=0)
+        self.step_idx = 0
+        self.commands.copy_(self.expanded_main_commands[:, 0, :])
+        g = torch.Generator().manual_seed(c.seed)
+        M = self.num_main_envs
+        s = torch.zeros(M, gm.STATE_DIM)
+        s[:, 2], s[:, 6] = 0.34, 1.0                                       # go2.yaml:52-55
+        s[:, 13:25] = torch.tensor(self.model.q_default)
+        if c.randomize_reset:                                              # legged_robot_base.py:737-784
+            s[:, 7:13] = torch.rand(M, 6, generator=g) - 0.5
+            s[:, 13:25] *= 0.5 + torch.rand(M, 12, generator=g)
+        self.state.copy_(s.repeat_interleave(P1, dim=0).to(self.device))    # every env of a group starts from the main's draw
+        for t in (self.actions, self.history, self.gait_indices, self.clock, self.total_reward, self.jtj, self.step_reward):
+            t.zero_()
+        self.done.zero_()
+        self._advance_inputs()
+        self._env_step(torch.zeros(N, 12, device=self.device))
+        return self.obs
+
+    def _advance_inputs(self):
+        """Host-side per-step inputs of the captured step: next command row and the k-sync flag."""
+        self.step_idx += 1                                                  # _pre_physics_step increments step_idx
+        t = min(self.step_idx, self.expanded_main_commands.shape[1] - 1)
+        self.next_commands.copy_(self.expanded_main_commands[:, t, :])
+        k = self.cfg.ksync_steps
+        sync = (k == 1) or (k > 1 and self.step_idx % k == 1)
+        self.sync_flag.fill_(bool(sync))
+
+    # ---- evaluate_policy -------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def evaluate_policy(self, commands: torch.Tensor, total_steps: Optional[int] = None, use_cuda_graph: Optional[bool] = None):
+        """commands[M, T, 14] -> {"total_reward": [N] mean FIM reward per step (main env j at j * (P + 1)),
+        "fim": [M, P, P] accumulated J J^T / steps}  (active_sysid.py:528-600)."""
+        total_steps = int(total_steps or self.total_steps)
+        assert commands.shape[0] == self.num_main_envs and commands.shape[2] == 14
+        self.reset_all(commands)
+        self.total_reward.zero_(); self.jtj.zero_()
+        graph_ok = self.device.type == "cuda" if use_cuda_graph is None else use_cuda_graph
+        step = 1
+        if graph_ok and self._graph is None:
+            self._capture()
+        for _ in range(1, total_steps - 1):
+            self._advance_inputs()
+            if graph_ok:
+                self._graph.replay()
+            else:
+                self._policy_step()
+            step += 1
+        return {"total_reward": (self.total_reward / step).cpu().numpy(), "fim": (self.jtj / step).cpu().numpy(),
+                "steps": step}
+
+    def _capture(self):
+        """One control step (policy + clock + physics + reward + observation + sync) as a CUDA graph."""
+        saved = [t.clone() for t in (self.state, self.actions, self.obs, self.history, self.gait_indices, self.clock,
+                                     self.commands, self.total_reward, self.jtj, self.step_reward)]
+        saved_done = self.done.clone()
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._policy_step()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._policy_step()
+        for t, v in zip((self.state, self.actions, self.obs, self.history, self.gait_indices, self.clock, self.commands,
+                         self.total_reward, self.jtj, self.step_reward), saved):
+            t.copy_(v)
+        self.done.copy_(saved_done)
+
+
+# ---- command samplers (active_sysid.py:259-400) ------------------------------------------------------------------------------
+def expand_commands(sampled: np.ndarray, sampling_idxs=COMMAND_SAMPLING_IDXS, default_command=DEFAULT_COMMAND) -> np.ndarray:
+    """sampled[T, len(idxs)] -> full[T, 14] with the defaults elsewhere (:284-293)."""
+    full = np.zeros((sampled.shape[0], len(default_command)), dtype=np.float32)
+    full[:, :] = np.asarray(default_command, dtype=np.float32)
+    for i, idx in enumerate(sampling_idxs):
+        full[:, idx] = sampled[:, i]
+    return full
+
+
+def commands_constant(values: np.ndarray, num_steps_per_update: int) -> np.ndarray:
+    """values[num_updates, dims] -> [num_updates * steps, dims]: one scalar per update window (:295-314)."""
+    return np.repeat(np.asarray(values, dtype=np.float32), num_steps_per_update, axis=0)
+
+
+def commands_polynomial(coeffs: np.ndarray, ranges: np.ndarray, num_steps_per_update: int) -> np.ndarray:
+    """coeffs[num_updates, dims, degree + 1] in [-2, 2]: per window a polynomial in t in [0, 1], squashed by tanh to
+    [-1, 1] and mapped linearly onto the range (:316-360)."""
+    t = np.linspace(0.0, 1.0, num_steps_per_update, dtype=np.float32)
+    powers = np.stack([t ** k for k in range(coeffs.shape[2])], axis=1)          # [steps, deg+1]
+    out = []
+    for u in range(coeffs.shape[0]):
+        y = np.tanh(powers @ coeffs[u].T)                                         # [steps, dims]
+        lo, hi = ranges[:, 0][None], ranges[:, 1][None]
+        out.append(lo + (y + 1.0) * 0.5 * (hi - lo))
+    return np.concatenate(out, axis=0).astype(np.float32)
+
+
+def commands_bezier(points: np.ndarray, num_steps: int) -> np.ndarray:
+    """points[num_points, dims] control points (already inside the ranges) -> Bernstein curve over the rollout
+    (:362-400)."""
+    n = points.shape[0] - 1
+    t = np.linspace(0.0, 1.0, num_steps, dtype=np.float64)
+    out = np.zeros((num_steps, points.shape[1]))
+    for i in range(n + 1):
+        out += (math.comb(n, i) * (t ** i) * ((1 - t) ** (n - i)))[:, None] * points[i][None]
+    return out.astype(np.float32)
+
+
+class CmaEs:
+    """Minimal (mu/mu_w, lambda)-CMA-ES with box clipping: stand-in for optuna.samplers.CmaEsSampler
+    (config/algo/active_sysid.yaml:19-21), same ask/tell shape as the study loop of active_sysid.py:196-217."""
+
+    def __init__(self, lo, hi, seed: int = 0, sigma0: float = 0.3):
+        self.lo, self.hi = np.asarray(lo, float), np.asarray(hi, float)
+        self.n = self.lo.size
+        self.rng = np.random.default_rng(seed)
+        self.mean = 0.5 * (self.lo + self.hi)
+        self.sigma = sigma0
+        self.C = np.eye(self.n)
+        self.pc, self.ps = np.zeros(self.n), np.zeros(self.n)
+        self.gen = 0
+        self.best = (None, np.inf)
+
+    def _scale(self):
+        return np.maximum(self.hi - self.lo, 1e-12)
+
+    def ask(self, lam: int) -> np.ndarray:
+        A = np.linalg.cholesky(self.C + 1e-12 * np.eye(self.n))
+        self._z = self.rng.standard_normal((lam, self.n)) @ A.T
+        x = self.mean[None] + self.sigma * self._z * self._scale()[None]
+        self._x = np.clip(x, self.lo, self.hi)
+        return self._x
+
+    def tell(self, values: np.ndarray):
+        lam, n = self._x.shape[0], self.n
+        order = np.argsort(values, kind="stable")
+        if values[order[0]] < self.best[1]:
+            self.best = (self._x[order[0]].copy(), float(values[order[0]]))
+        mu = max(1, lam // 2)
+        w = np.log(mu + 0.5) - np.log(np.arange(1, mu + 1)); w /= w.sum()
+        mueff = 1.0 / (w ** 2).sum()
+        cc, cs = (4 + mueff / n) / (n + 4 + 2 * mueff / n), (mueff + 2) / (n + mueff + 5)
+        c1 = 2 / ((n + 1.3) ** 2 + mueff)
+        cmu = min(1 - c1, 2 * (mueff - 2 + 1 / mueff) / ((n + 2) ** 2 + mueff))
+        damps = 1 + 2 * max(0.0, math.sqrt((mueff - 1) / (n + 1)) - 1) + cs
+        y = (self._x[order[:mu]] - self.mean[None]) / (self.sigma * self._scale()[None])
+        yw = (w[:, None] * y).sum(axis=0)
+        self.mean = np.clip(self.mean + self.sigma * self._scale() * yw, self.lo, self.hi)
+        Cinv_sqrt = np.linalg.inv(np.linalg.cholesky(self.C + 1e-12 * np.eye(n)))
+        self.ps = (1 - cs) * self.ps + math.sqrt(cs * (2 - cs) * mueff) * (Cinv_sqrt @ yw)
+        self.gen += 1
+        chi = math.sqrt(n) * (1 - 1 / (4 * n) + 1 / (21 * n * n))
+        hs = float(np.linalg.norm(self.ps) / math.sqrt(1 - (1 - cs) ** (2 * self.gen)) < (1.4 + 2 / (n + 1)) * chi)
+        self.pc = (1 - cc) * self.pc + hs * math.sqrt(cc * (2 - cc) * mueff) * yw
+        self.C = ((1 - c1 - cmu) * self.C + c1 * (np.outer(self.pc, self.pc) + (1 - hs) * cc * (2 - cc) * self.C)
+                  + cmu * (y.T * w) @ y)
+        self.C = 0.5 * (self.C + self.C.T)
+        self.sigma *= math.exp((cs / damps) * (np.linalg.norm(self.ps) / chi - 1))
+        self.sigma = float(np.clip(self.sigma, 1e-4, 1.0))
+
+
+def optimize_commands(explorer: ActiveExploration, iterations: int = 5, rollout_length: float = 25.0,
+                      horizon_length: float = 5.0, seed: int = 0, total_steps: Optional[int] = None):
+    """The study loop of active_sysid.py:165-242 in `constant` sampling mode: M trials per iteration, 3 sampled command
+    dims x (rollout / horizon) update windows each; objective = -total_reward of the main env."""
+    dt = explorer.dt
+    n_updates = int(rollout_length // horizon_length)
+    steps_per_update = int(horizon_length / dt)
+    ranges = np.asarray(COMMAND_RANGES, dtype=np.float32)[COMMAND_SAMPLING_IDXS]
+    lo = np.tile(ranges[:, 0], n_updates); hi = np.tile(ranges[:, 1], n_updates)
+    es = CmaEs(lo, hi, seed=seed)
+    M, P1 = explorer.num_main_envs, explorer.param_dim + 1
+    history = []
+    for it in range(iterations):
+        x = es.ask(M)                                                     # [M, n_updates * dims]
+        cmds = np.stack([expand_commands(commands_constant(xi.reshape(n_updates, -1), steps_per_update)) for xi in x])
+        out = explorer.evaluate_policy(torch.from_numpy(cmds), total_steps=total_steps)
+        main_reward = out["total_reward"][::P1]
+        es.tell(-main_reward)
+        history.append(float(main_reward.max()))
+    best_x, best_v = es.best
+    best_commands = expand_commands(commands_constant(best_x.reshape(n_updates, -1), steps_per_update))
+    return {"best_commands": best_commands, "best_value": -best_v, "history": history}

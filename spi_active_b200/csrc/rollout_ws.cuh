@@ -24,6 +24,7 @@ struct WsArgs {
   int S, H, decimation, motor_model; unsigned flags;
   int n_cta_per_cand;
   int rotate_roles;
+  int paired;          // 1: rollout r uses candidate row r AND segment r (one env per rollout; C == 1 for the grid)
   float* partial;      // [C][n_cta_per_cand][3]
   float* per_seg;      // [C][S][3] or null
   int* bad;            // [C]
@@ -108,7 +109,7 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, int lan
     }
     if (RECORD) {
       if (active) {
-        float* row = A.out_states + (((size_t)c * A.S + seg) * A.H + k) * SPI_STATE_DIM;
+        float* row = A.out_states + (((size_t)(A.paired ? 0 : c) * A.S + seg) * A.H + k) * SPI_STATE_DIM;
 #pragma unroll
         for (int j = 0; j < 3; j++) { row[13 + 3 * LEG + j] = s.q[j]; row[25 + 3 * LEG + j] = s.qd[j]; }
       }
@@ -179,7 +180,7 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, int la
     }
     if (RECORD) {
       if (active) {
-        float* row = A.out_states + (((size_t)c * A.S + seg) * A.H + k) * SPI_STATE_DIM;
+        float* row = A.out_states + (((size_t)(A.paired ? 0 : c) * A.S + seg) * A.H + k) * SPI_STATE_DIM;
 #pragma unroll
         for (int i = 0; i < 3; i++) { row[i] = s.p[i]; row[7 + i] = s.v[i]; row[10 + i] = s.w[i]; }
 #pragma unroll
@@ -232,11 +233,12 @@ __device__ __forceinline__ void rollout_ws_body(const WsArgs& A) {
   __shared__ WsSmem sm;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int role = __shfl_sync(0xffffffffu, A.rotate_roles ? (warp + blockIdx.x) % kWsWarps : warp, 0);  // warp-uniform
-  const int c = blockIdx.x / A.n_cta_per_cand;
-  const int cta_in_cand = blockIdx.x - c * A.n_cta_per_cand;
+  const int cg = blockIdx.x / A.n_cta_per_cand;
+  const int cta_in_cand = blockIdx.x - cg * A.n_cta_per_cand;
   const int seg_raw = cta_in_cand * kWsRollouts + lane;
   const bool active = seg_raw < A.S;
   const int seg = active ? seg_raw : A.S - 1;
+  const int c = A.paired ? seg : cg;
   if (role < 4) ws_leg_role<RECORD>(A, sm, lane, role, c, seg, active);
   else ws_base_role<RECORD>(A, sm, lane, c, cta_in_cand, seg, active);
 }

@@ -32,6 +32,7 @@ struct EvalArgs {
   const unsigned char* seg_mask;
   int S, H, decimation, motor_model; unsigned flags;
   int n_cta_per_cand, n_warp_per_cand;
+  int paired;
   float* partial;      // [C][n_warp_per_cand][3]
   float* per_seg;      // [C][S][3] or null
   int* bad;            // [C]
@@ -89,11 +90,12 @@ __global__ void __launch_bounds__(kThreads, MINB) rollout_kernel(const EvalArgs 
   const DeviceModel& M = *A.model;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int leg = lane & 3;
-  const int c = blockIdx.x / A.n_cta_per_cand;
-  const int cta_in_cand = blockIdx.x - c * A.n_cta_per_cand;
+  const int cg = blockIdx.x / A.n_cta_per_cand;
+  const int cta_in_cand = blockIdx.x - cg * A.n_cta_per_cand;
   const int seg_raw = cta_in_cand * kRolloutsPerCta + (threadIdx.x >> 2);
   const bool active = seg_raw < A.S;
   const int seg = active ? seg_raw : A.S - 1;
+  const int c = A.paired ? seg : cg;
 
   SimConst S = M.sim;
   LegConst L;
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(kThreads, MINB) rollout_kernel(const EvalArgs 
       for (int n = 0; n < S.nsub; n++) substep(S, L, B, s, tau, h, nullptr);
     }
     if (RECORD) {
-      if (active) store_lane_state(A.out_states + (((size_t)c * A.S + seg) * A.H + k) * SPI_STATE_DIM, leg, s);
+      if (active) store_lane_state(A.out_states + (((size_t)(A.paired ? 0 : c) * A.S + seg) * A.H + k) * SPI_STATE_DIM, leg, s);
     }
   }
   if (RECORD) return;
@@ -542,7 +544,7 @@ int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C
                       const float* seg_init, const float* seg_actions, const float* seg_target, const float* seg_gains,
                       const unsigned char* seg_mask, int S, int H, int decimation, int motor_model, unsigned flags,
                       float cost_denominator, float* out_cost, float* out_per_seg, int* out_status, float* out_states,
-                      cudaStream_t st) {
+                      cudaStream_t st, int paired) {
   ws::WsArgs A;
   std::memset(&A, 0, sizeof(A));
   ParamIds ids;
@@ -554,6 +556,7 @@ int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C
   A.seg_init = seg_init; A.seg_actions = seg_actions; A.seg_target = seg_target; A.seg_gains = seg_gains;
   A.seg_mask = seg_mask; A.S = S; A.H = H; A.decimation = decimation; A.motor_model = motor_model; A.flags = flags;
   A.n_cta_per_cand = (S + ws::kWsRollouts - 1) / ws::kWsRollouts;
+  A.paired = paired;
   { static const int rot = getenv("SPI_B200_WS_ROT") ? atoi(getenv("SPI_B200_WS_ROT")) : 0; A.rotate_roles = rot; }
   const long long n_cta = (long long)C * A.n_cta_per_cand;
   if (n_cta > 2147483647LL) return fail(-3, "C * ceil(S/32) exceeds the grid limit");
@@ -590,7 +593,7 @@ int launch_rollout(spi_b200_model* m, bool record, const float* params, int C, i
                    const float* seg_init, const float* seg_actions, const float* seg_target, const float* seg_gains,
                    const unsigned char* seg_mask, int S, int H, int decimation, int motor_model, unsigned flags,
                    float cost_denominator, float* out_cost, float* out_per_seg, int* out_status, float* out_states,
-                   cudaStream_t st) {
+                   cudaStream_t st, int paired = 0) {
   if (!m) return fail(-1, "model handle is NULL");
   if (C <= 0 || S <= 0 || H <= 0 || decimation <= 0) return fail(-3, "C, S, H, decimation must be positive");
   if (!seg_init || !seg_actions) return fail(-3, "seg_init / seg_actions is NULL");
@@ -602,7 +605,7 @@ int launch_rollout(spi_b200_model* m, bool record, const float* params, int C, i
   if (m->ws_ok && m->kernel != SPI_KERNEL_LANE && (m->kernel == SPI_KERNEL_WS || kernel_choice() != 1))
     return launch_rollout_ws(m, record, params, C, P, param_ids, seg_init, seg_actions, seg_target, seg_gains, seg_mask,
                              S, H, decimation, motor_model, flags, cost_denominator, out_cost, out_per_seg, out_status,
-                             out_states, st);
+                             out_states, st, paired);
   EvalArgs A;
   std::memset(&A, 0, sizeof(A));
   if (int rc = make_ids(P, param_ids, &A.ids)) return rc;
@@ -612,6 +615,7 @@ int launch_rollout(spi_b200_model* m, bool record, const float* params, int C, i
   A.seg_mask = seg_mask; A.S = S; A.H = H; A.decimation = decimation; A.motor_model = motor_model; A.flags = flags;
   A.n_cta_per_cand = (S + kRolloutsPerCta - 1) / kRolloutsPerCta;
   A.n_warp_per_cand = A.n_cta_per_cand * (kThreads / 32);
+  A.paired = paired;
   const long long n_cta = (long long)C * A.n_cta_per_cand;
   if (n_cta > 2147483647LL) return fail(-3, "C * ceil(S/32) exceeds the grid limit");
   if (!record) {
@@ -784,6 +788,18 @@ int spi_b200_eval_candidates_host(spi_b200_model* m, const float* params, int C,
   std::memcpy(out_cost, m->h_stage + o_cost, (size_t)C * 3 * 4);
   if (out_status) std::memcpy(out_status, m->h_stage + o_stat, (size_t)C * 4);
   return 0;
+}
+
+int spi_b200_env_step(spi_b200_model* m, const float* params, int P, const int* param_ids, float* state,
+                      const float* actions, const float* gains, int N, int decimation, int motor_model, unsigned flags,
+                      void* cuda_stream) {
+  if (!m) return fail(-1, "model handle is NULL");
+  if (N <= 0 || decimation <= 0) return fail(-3, "N and decimation must be positive");
+  if (!state || !actions) return fail(-3, "state / actions is NULL");
+  // one control step of N independent envs = the RECORD rollout kernel with H = 1 in paired mode (env e uses
+  // parameter row e and state row e); every lane reads its row before it writes it, so in-place is safe
+  return launch_rollout(m, true, params, 1, params ? P : 0, param_ids, state, actions, nullptr, gains, nullptr, N, 1,
+                        decimation, motor_model, flags, 0.f, nullptr, nullptr, nullptr, state, (cudaStream_t)cuda_stream, 1);
 }
 
 int spi_b200_sim_step(spi_b200_model* m, const float* params, int P, const int* param_ids, unsigned flags, float* state,

@@ -177,6 +177,27 @@ class RolloutEngine:
         _lib.check(rc, "spi_b200_sim_step")
         return state
 
+    def env_step(self, state: torch.Tensor, actions: torch.Tensor, params=None, param_names=(), gains=None,
+                 decimation: Optional[int] = None, motor_model="none", flags: int = 0) -> torch.Tensor:
+        """One control step of N independent envs IN PLACE: state[N,37], actions[N,12], per-env params[N,P]."""
+        assert state.is_cuda and state.dtype == torch.float32 and state.is_contiguous()
+        actions = self._f32(actions).reshape(-1, 12)
+        N = state.shape[0]
+        P = 0
+        ids = np.zeros(1, dtype=np.int32)
+        if params is not None:
+            params = self._f32(params).reshape(N, -1)
+            P = params.shape[1]
+            ids = _ids(param_names)
+        gains = self._f32(gains)
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_env_step(self._handle, _ptr(params), P, ids.ctypes.data_as(C.POINTER(C.c_int)),
+                                            _ptr(state), _ptr(actions), _ptr(gains), N,
+                                            int(decimation or self.model.control_decimation),
+                                            motor_model_id(motor_model), int(flags), self._stream())
+        _lib.check(rc, "spi_b200_env_step")
+        return state
+
     def compute_torques(self, actions, q, qd, gains=None, motor_params=None, motor_model="none", flags: int = 0):
         actions = self._f32(actions).reshape(-1, 12)
         q = self._f32(q).reshape(-1, 12)

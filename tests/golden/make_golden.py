@@ -19,6 +19,11 @@ reference's real, unmodified code object, called with plain torch tensors:
   fim.npz            ActiveSysId_OpenLoop._reward_fisher_information_matrix (:402-426)
   cost.npz           scripts/mass_opt.py:62-76 compute_cost; mass_landscape.py COST_COEFF / argmin (:162-171)
   quat.npz           spigym/utils/torch_utils.py quat_rotate_inverse / quat_rotate (:49-92)
+  active_obs.npz     the 900-dim actor observation of the active-exploration env over 18 steps: real
+                     go2_omni._step_contact_targets (:348-377), every _get_obs_* getter (go2_omni.py:627-657,
+                     legged_robot_base.py:801-844), _pre_compute_observations_callback (:261-269),
+                     _compute_observations / _post_config_observation_callback (:511-527), helpers.parse_observation,
+                     env_utils/history_handler.HistoryHandler
   mass_sweep.npz     scripts/mass_landscape.py:111-128 mass_sweep -> scripts/eval.py:204-214 apply_base_mass
                      -> :217-310 evaluate_batch -> LeggedRobotBase._pre_physics_step/_physics_step/
                      _apply_force_in_physics_step/_compute_torques, all real, driving tests/oracle_sim.OracleSim
@@ -284,6 +289,79 @@ def gen_mass_sweep(R, rng):
     np.savez(HERE / "mass_sweep.npz", **out)
 
 
+def gen_active_obs(R, rng):
+    """The 900-dim actor observation of the active-exploration env over a few steps, produced by the reference's real
+    go2_omni._step_contact_targets, LeggedRobotBase._pre_compute_observations_callback / _compute_observations /
+    _post_config_observation_callback, every _get_obs_* getter, helpers.parse_observation and HistoryHandler."""
+    from spigym.envs.env_utils.history_handler import HistoryHandler
+    from spi_active_b200 import active as act, go2_model as gm
+    N, T = 7, 18
+    keys = list(act.OBS_DIMS)
+    obs_cfg = SimpleNamespace(
+        obs_dict={"actor_obs": ["base_ang_vel", "projected_gravity", "command_lin_vel", "command_ang_vel",
+                                "command_body_height", "command_gait_freq", "command_gait_phase",
+                                "command_footswing_height", "command_body_attitude", "command_stance", "clock_inputs",
+                                "dof_pos", "dof_vel", "actions", "short_history"]},
+        obs_auxiliary={"short_history": {k: 14 for k in ["base_ang_vel", "projected_gravity", "dof_pos", "dof_vel", "actions",
+                                                         "command_lin_vel", "command_ang_vel", "command_body_height",
+                                                         "command_gait_freq", "command_gait_phase", "command_footswing_height",
+                                                         "command_body_attitude", "command_stance", "clock_inputs"]}},
+        obs_scales=dict(act.OBS_SCALES, short_history=1.0), noise_scales={k: 0.0 for k in keys + ["short_history"]},
+        commands=SimpleNamespace(limit_body_height=[-0.25, 0.15], num_commands=14))
+
+    class Stub:
+        pass
+    for name in dir(R.go2_omni):
+        if name.startswith("_get_obs_"):
+            setattr(Stub, name, getattr(R.go2_omni, name))
+    Stub._step_contact_targets = R.go2_omni._step_contact_targets
+    Stub._pre_compute_observations_callback = R.LeggedRobotBase._pre_compute_observations_callback
+    Stub._compute_observations = R.LeggedRobotBase._compute_observations
+    Stub._post_config_observation_callback = R.LeggedRobotBase._post_config_observation_callback
+    self = Stub()
+    self.config = SimpleNamespace(obs=obs_cfg)
+    self.is_evaluating, self.dt, self.device, self.num_envs = True, 0.02, "cpu", N
+    z = lambda *s: torch.zeros(*s, dtype=torch.float32)
+    self.gait_indices, self.clock_inputs = z(N), z(N, 4)
+    self.doubletime_clock_inputs, self.halftime_clock_inputs, self.desired_contact_states = z(N, 4), z(N, 4), z(N, 4)
+    self.simulator = SimpleNamespace(robot_root_states=z(N, 13), dof_pos=z(N, 12), dof_vel=z(N, 12))
+    self.simulator.base_quat = self.simulator.robot_root_states[:, 3:7]
+    self.base_quat, self.rpy = z(N, 4), z(N, 3)
+    self.base_lin_vel, self.base_ang_vel, self.projected_gravity = z(N, 3), z(N, 3), z(N, 3)
+    self.gravity_vec = torch.tensor([0.0, 0.0, -1.0]).repeat(N, 1)
+    self.default_dof_pos = torch.tensor(gm.go2_nominal().q_default, dtype=torch.float32).unsqueeze(0)
+    self.history_handler = HistoryHandler(N, obs_cfg.obs_auxiliary, dict(act.OBS_DIMS), "cpu")
+    ranges = np.asarray(act.COMMAND_RANGES)
+    out = dict(states=[], actions=[], commands_clock=[], commands_obs=[], actor_obs=[], clock=[], gait=[])
+    for t in range(T):
+        cmd_clock = rng.uniform(ranges[:, 0], ranges[:, 1], (N, 14)).astype(np.float32)
+        cmd_clock[:, 8] = rng.uniform(0.3, 0.7, N)            # exercise the stance / swing warp with durations != 0.5
+        cmd_obs = rng.uniform(ranges[:, 0], ranges[:, 1], (N, 14)).astype(np.float32)
+        state = rng.standard_normal((N, 37)).astype(np.float32)
+        state[:, 3:7] /= np.linalg.norm(state[:, 3:7], axis=1, keepdims=True)
+        if t == 5:
+            state[:, 25:37] *= 3000.0                          # exercise the +-100 observation clip
+        actions = rng.uniform(-3, 3, (N, 12)).astype(np.float32)
+        self.commands = torch.from_numpy(cmd_clock.copy())
+        self._step_contact_targets()
+        self.simulator.robot_root_states[:] = torch.from_numpy(state[:, :13])
+        self.simulator.dof_pos[:] = torch.from_numpy(state[:, 13:25])
+        self.simulator.dof_vel[:] = torch.from_numpy(state[:, 25:37])
+        self.actions = torch.from_numpy(actions.copy())
+        self.commands = torch.from_numpy(cmd_obs.copy())       # _update_tasks_callback runs before the observations
+        self._pre_compute_observations_callback()
+        self._compute_observations()
+        obs = torch.clip(self.obs_buf_dict["actor_obs"], -100.0, 100.0)
+        for key in self.history_handler.history.keys():       # legged_robot_base.py:249-250
+            self.history_handler.add(key, self.hist_obs_dict[key])
+        for k, v in (("states", state), ("actions", actions), ("commands_clock", cmd_clock), ("commands_obs", cmd_obs),
+                     ("actor_obs", obs.numpy().copy()), ("clock", self.clock_inputs.numpy().copy()),
+                     ("gait", self.gait_indices.numpy().copy())):
+            out[k].append(v)
+    np.savez(HERE / "active_obs.npz", **{k: np.stack(v) for k, v in out.items()})
+    print("active_obs.npz", np.stack(out["actor_obs"]).shape)
+
+
 def main():
     R = import_reference()
     rng = np.random.default_rng(20251017)
@@ -293,6 +371,7 @@ def main():
     gen_cost(R, rng)
     gen_quat(R, rng)
     gen_mass_sweep(R, rng)
+    gen_active_obs(R, np.random.default_rng(7))
 
 
 if __name__ == "__main__":
