@@ -210,6 +210,15 @@ int spi_b200_compute_torques(spi_b200_model* model,
 int spi_b200_fim_reward(spi_b200_model* model, const float* states, int M, int P, float delta,
                         int accumulate, float* out_JtJ, float* out_trace, void* cuda_stream);
 
+/* Accumulated Fisher information of whole rollouts on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 split =
+ * fp32-accurate): the sum over control steps of the per-step J J^T that active_sysid_openloop.py:402-426 forms and
+ * active_sysid.py:567-590 accumulates (terminated groups contribute termination_rew = 0 -> `live`).
+ *   hist [T,M,(P+1),25] the per-step `states` of spi_b200_fim_reward stacked over T control steps;
+ *   live [T,M] bytes (1 = the group's step counts) or NULL -> all 1;  P <= 16;
+ *   out_JtJ [M,P,P] = sum_t live * J_t J_t^T (+= if accumulate != 0), out_trace [M] = its trace (the summed reward). */
+int spi_b200_fim_contract(spi_b200_model* model, const float* hist, const unsigned char* live, int T, int M, int P,
+                          float delta, int accumulate, float* out_JtJ, float* out_trace, void* cuda_stream);
+
 /* CEM elite selection + refit on device.
  *   params [C,P], cost [C] (weighted), n_elite; out_mean [P], out_std [P] updated in place:
  *   mean <- (1-alpha)*mean + alpha*elite_mean, std likewise; out_best [P+1] = best params, cost */

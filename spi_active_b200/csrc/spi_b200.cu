@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "aba_leg.cuh"
+#include "fim_tc.cuh"
 #include "rollout_ws.cuh"
 
 using namespace spi;
@@ -840,6 +841,27 @@ int spi_b200_fim_reward(spi_b200_model* m, const float* states, int Mn, int P, f
   fim_reward_kernel<<<(Mn + warps_per_cta - 1) / warps_per_cta, threads, 0, (cudaStream_t)cuda_stream>>>(
       states, Mn, P, delta, accumulate, out_JtJ, out_trace);
   return check_launch("fim_reward_kernel");
+}
+
+int spi_b200_fim_contract(spi_b200_model* m, const float* hist, const unsigned char* live, int T, int Mn, int P,
+                          float delta, int accumulate, float* out_JtJ, float* out_trace, void* cuda_stream) {
+  if (!m) return fail(-1, "model handle is NULL");
+  if (T <= 0 || Mn <= 0 || P <= 0) return fail(-3, "T, M and P must be positive");
+  if (P > fimtc::kSlots) return fail(-3, "P must be <= 16");
+  if (!hist || (!out_JtJ && !out_trace)) return fail(-3, "NULL buffer");
+  if (!(delta != 0.f)) return fail(-3, "delta must be non-zero");
+  static std::atomic<int> attr_done{0};
+  if (!attr_done.load()) {
+    CUDA_OK(cudaFuncSetAttribute(fimtc::fim_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 fimtc::kSmemBytes));
+    attr_done.store(1);
+  }
+  fimtc::FimArgs A;
+  A.hist = hist; A.live = live; A.T = T; A.M = Mn; A.P = P; A.inv_delta = 1.0f / delta; A.accumulate = accumulate;
+  A.out_JtJ = out_JtJ; A.out_trace = out_trace;
+  const int n_cta = (Mn + fimtc::kEnvsPerCta - 1) / fimtc::kEnvsPerCta;
+  fimtc::fim_contract_kernel<<<n_cta, fimtc::kRows, fimtc::kSmemBytes, (cudaStream_t)cuda_stream>>>(A);
+  return check_launch("fim_contract_kernel");
 }
 
 int spi_b200_weighted_cost(spi_b200_model* m, const float* cost3, int C, float w_pos, float w_quat, float w_joint,

@@ -231,6 +231,28 @@ class RolloutEngine:
         _lib.check(rc, "spi_b200_fim_reward")
         return out_JtJ, out_trace
 
+    def fim_contract(self, hist: torch.Tensor, delta: float, live: Optional[torch.Tensor] = None,
+                     out_JtJ: Optional[torch.Tensor] = None, out_trace: Optional[torch.Tensor] = None,
+                     accumulate: bool = False):
+        """hist[T,M,P+1,25] (the per-step `states` of fim_reward stacked over T control steps), live[T,M] (bool/u8) ->
+        (sum_t live * J_t J_t^T [M,P,P], its trace [M]) on the tensor cores (spi_b200_fim_contract, 3xTF32)."""
+        hist = self._f32(hist)
+        T, Mn, P1, D = hist.shape
+        assert D == 25 and P1 >= 2
+        P = P1 - 1
+        if live is not None:
+            live = torch.as_tensor(live, device=self.device).to(torch.uint8).contiguous()
+            assert tuple(live.shape) == (T, Mn)
+        if out_JtJ is None:
+            out_JtJ = torch.zeros((Mn, P, P), device=self.device, dtype=torch.float32)
+        if out_trace is None:
+            out_trace = torch.zeros((Mn,), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_fim_contract(self._handle, _ptr(hist), _ptr(live), T, Mn, P, float(delta),
+                                                int(accumulate), _ptr(out_JtJ), _ptr(out_trace), self._stream())
+        _lib.check(rc, "spi_b200_fim_contract")
+        return out_JtJ, out_trace
+
     # ---- optimiser pieces -------------------------------------------------------------------------
     def weighted_cost(self, cost3: torch.Tensor, w=(10.0, 5.0, 1.0), out: Optional[torch.Tensor] = None):
         cost3 = self._f32(cost3)
