@@ -175,6 +175,10 @@ class ActiveConfig:
     termination_rew: float = 0.0
     randomize_reset: bool = True          # legged_robot_base.py:737-784 reset distribution
     seed: int = 0
+    # "step": J J^T per control step on CUDA cores (spi_b200_fim_reward); "tensor": the states of `fim_chunk` steps are
+    # kept on device and contracted on the tensor cores (spi_b200_fim_contract); "auto": tensor on a CUDA backend
+    fim_mode: str = "auto"
+    fim_chunk: int = 64
 
 
 class ActiveExploration:
@@ -221,6 +225,23 @@ class ActiveExploration:
         self.jtj = z(self.num_main_envs, self.param_dim, self.param_dim)
         self.sync_flag = torch.zeros((), dtype=torch.bool, device=self.device)
         self._graph = None
+        mode = c.fim_mode
+        if mode == "auto":
+            mode = "tensor" if (self.device.type == "cuda" and hasattr(backend, "fim_contract")) else "step"
+        if mode not in ("step", "tensor"):
+            raise ValueError(f"fim_mode must be 'auto', 'step' or 'tensor', not {c.fim_mode!r}")
+        if mode == "tensor" and not hasattr(backend, "fim_contract"):
+            raise ValueError("fim_mode='tensor' needs a backend with fim_contract")
+        if mode == "tensor" and self.param_dim > 16:
+            raise ValueError("fim_mode='tensor' supports at most 16 exploration parameters")
+        self.fim_mode = mode
+        if mode == "tensor":
+            K = max(1, int(c.fim_chunk))
+            self.hist = z(K, self.num_main_envs, self.param_dim + 1, 25)
+            self.live_hist = torch.zeros(K, self.num_main_envs, dtype=torch.uint8, device=self.device)
+            self.slot = torch.zeros(1, dtype=torch.long, device=self.device)
+            self.trace_acc, self.dead_steps = z(self.num_main_envs), z(N)
+            self._hist_count = 0
 
     # ---- physics / reward through the engine -------------------------------------------------------------------------
     def _physics(self):
@@ -250,7 +271,11 @@ class ActiveExploration:
         reset = reset | ~torch.isfinite(self.state).all(dim=1)
         group = reset.view(self.num_main_envs, -1).any(dim=1, keepdim=True)        # _update_reset_buf group OR
         self.done.copy_(group.expand(-1, self.param_dim + 1).reshape(-1))
-        rew, jtj = self._fim()                                                    # _compute_reward
+        if self.fim_mode == "tensor":                                            # _compute_reward, deferred:
+            self._record_fim_inputs(group)                                        # contracted every fim_chunk steps
+            rew = jtj = None
+        else:
+            rew, jtj = self._fim()
         frame = build_frame(self.state, self.actions, self.commands, self.clock, self.gait_indices, self.q_default)
         hist_flat = self.history.reshape(self.num_envs, HISTORY_LEN * FRAME_DIM)
         obs = torch.cat([frame, hist_flat[:, self.hist_index]], dim=1)             # _compute_observations
@@ -260,12 +285,32 @@ class ActiveExploration:
         grp = self.state.view(self.num_main_envs, self.param_dim + 1, gm.STATE_DIM)
         synced = grp[:, 0:1, :].expand(-1, self.param_dim + 1, -1).reshape(self.num_envs, gm.STATE_DIM)
         self.state.copy_(torch.where(self.sync_flag, synced, self.state))
+        if self.fim_mode == "tensor":
+            return
         # active_sysid.py:567-577: terminated groups score termination_rew
         rew = torch.where(self.done, torch.full_like(rew, c.termination_rew), torch.nan_to_num(rew, nan=0.0, posinf=0.0))
         self.step_reward.copy_(rew)
         self.total_reward.add_(rew)
         live = (~self.done.view(self.num_main_envs, -1)[:, 0]).to(jtj.dtype)
         self.jtj.add_(torch.nan_to_num(jtj) * live[:, None, None])
+
+    # ---- tensor-core FIM: record now, contract later ---------------------------------------------------------------------
+    def _record_fim_inputs(self, group_done: torch.Tensor):
+        """Slot `self.slot` of the history ring <- this step's (root13, q12) of every env and the group's live flag.
+        Runs inside the captured step; the slot index is a device scalar the host advances between replays."""
+        M, P1 = self.num_main_envs, self.param_dim + 1
+        self.hist.index_copy_(0, self.slot, self.state[:, :25].reshape(1, M, P1, 25))
+        self.live_hist.index_copy_(0, self.slot, (~group_done).reshape(1, M).to(torch.uint8))
+        self.dead_steps.add_(self.done.to(self.dead_steps.dtype))
+
+    def _flush_fim(self):
+        """sum over the recorded steps of live * J J^T -> self.jtj, trace -> self.trace_acc (spi_b200_fim_contract)."""
+        n = self._hist_count
+        if n == 0:
+            return
+        self.backend.fim_contract(self.hist[:n], float(self.cfg.delta_param), live=self.live_hist[:n],
+                                  out_JtJ=self.jtj, out_trace=self.trace_acc, accumulate=True)
+        self._hist_count = 0
 
     def _policy_step(self):
         actions = self.policy(self.obs)
@@ -303,6 +348,8 @@ class ActiveExploration:
         k = self.cfg.ksync_steps
         sync = (k == 1) or (k > 1 and self.step_idx % k == 1)
         self.sync_flag.fill_(bool(sync))
+        if self.fim_mode == "tensor":
+            self.slot.fill_(self._hist_count)
 
     # ---- evaluate_policy -------------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -313,6 +360,10 @@ class ActiveExploration:
         assert commands.shape[0] == self.num_main_envs and commands.shape[2] == 14
         self.reset_all(commands)
         self.total_reward.zero_(); self.jtj.zero_()
+        tensor = self.fim_mode == "tensor"
+        if tensor:
+            self.trace_acc.zero_(); self.dead_steps.zero_()
+            self._hist_count = 0                      # the reset step's record is dropped, like its reward (:545-548)
         graph_ok = self.device.type == "cuda" if use_cuda_graph is None else use_cuda_graph
         step = 1
         if graph_ok and self._graph is None:
@@ -324,13 +375,24 @@ class ActiveExploration:
             else:
                 self._policy_step()
             step += 1
+            if tensor:
+                self._hist_count += 1
+                if self._hist_count == self.hist.shape[0]:
+                    self._flush_fim()
+        if tensor:
+            self._flush_fim()
+            self.total_reward.copy_(self.trace_acc.repeat_interleave(self.param_dim + 1)
+                                    + self.cfg.termination_rew * self.dead_steps)
         return {"total_reward": (self.total_reward / step).cpu().numpy(), "fim": (self.jtj / step).cpu().numpy(),
                 "steps": step}
 
     def _capture(self):
         """One control step (policy + clock + physics + reward + observation + sync) as a CUDA graph."""
-        saved = [t.clone() for t in (self.state, self.actions, self.obs, self.history, self.gait_indices, self.clock,
-                                     self.commands, self.total_reward, self.jtj, self.step_reward)]
+        live = [self.state, self.actions, self.obs, self.history, self.gait_indices, self.clock, self.commands,
+                self.total_reward, self.jtj, self.step_reward]
+        if self.fim_mode == "tensor":
+            live += [self.dead_steps]                 # hist / live_hist slots are rewritten before they are read
+        saved = [t.clone() for t in live]
         saved_done = self.done.clone()
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
@@ -341,8 +403,7 @@ class ActiveExploration:
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._policy_step()
-        for t, v in zip((self.state, self.actions, self.obs, self.history, self.gait_indices, self.clock, self.commands,
-                         self.total_reward, self.jtj, self.step_reward), saved):
+        for t, v in zip(live, saved):
             t.copy_(v)
         self.done.copy_(saved_done)
 
@@ -439,25 +500,57 @@ class CmaEs:
         self.sigma = float(np.clip(self.sigma, 1e-4, 1.0))
 
 
+def gather_main_results(main_reward: torch.Tensor, fim: Optional[torch.Tensor], world: int, group=None):
+    """All-gather the per-trial rewards [M_local] (and Fisher blocks [M_local, P, P]) of every rank's shard of command
+    trajectories into rank order (one small collective per iteration; NCCL on CUDA tensors, gloo on CPU)."""
+    if world == 1:
+        return main_reward, fim
+    import torch.distributed as dist
+
+    def gather(x):
+        x = x.contiguous()
+        out = torch.empty((world,) + tuple(x.shape), dtype=x.dtype, device=x.device)
+        if x.is_cuda:
+            dist.all_gather_into_tensor(out, x, group=group)
+        else:
+            dist.all_gather(list(out.unbind(0)), x, group=group)
+        return out.reshape((-1,) + tuple(x.shape[1:]))
+    return gather(main_reward), (None if fim is None else gather(fim))
+
+
 def optimize_commands(explorer: ActiveExploration, iterations: int = 5, rollout_length: float = 25.0,
-                      horizon_length: float = 5.0, seed: int = 0, total_steps: Optional[int] = None):
+                      horizon_length: float = 5.0, seed: int = 0, total_steps: Optional[int] = None,
+                      rank: int = 0, world: int = 1, group=None):
     """The study loop of active_sysid.py:165-242 in `constant` sampling mode: M trials per iteration, 3 sampled command
-    dims x (rollout / horizon) update windows each; objective = -total_reward of the main env."""
+    dims x (rollout / horizon) update windows each; objective = -total_reward of the main env.
+
+    Multi-GPU (world > 1): the M = world * explorer.num_main_envs trials of an iteration are sharded contiguously over
+    the ranks; every rank runs the same seeded sampler, rolls out its own slice and all-gathers the [M_local] rewards
+    and [M_local, P, P] Fisher blocks, so `tell` sees the full population on every rank (no broadcast)."""
     dt = explorer.dt
     n_updates = int(rollout_length // horizon_length)
     steps_per_update = int(horizon_length / dt)
     ranges = np.asarray(COMMAND_RANGES, dtype=np.float32)[COMMAND_SAMPLING_IDXS]
     lo = np.tile(ranges[:, 0], n_updates); hi = np.tile(ranges[:, 1], n_updates)
     es = CmaEs(lo, hi, seed=seed)
-    M, P1 = explorer.num_main_envs, explorer.param_dim + 1
-    history = []
+    M_local, P1 = explorer.num_main_envs, explorer.param_dim + 1
+    M = M_local * world
+    history, best_fim = [], None
     for it in range(iterations):
-        x = es.ask(M)                                                     # [M, n_updates * dims]
-        cmds = np.stack([expand_commands(commands_constant(xi.reshape(n_updates, -1), steps_per_update)) for xi in x])
+        x = es.ask(M)                                                     # [M, n_updates * dims], identical on every rank
+        mine = x[rank * M_local:(rank + 1) * M_local]
+        cmds = np.stack([expand_commands(commands_constant(xi.reshape(n_updates, -1), steps_per_update)) for xi in mine])
         out = explorer.evaluate_policy(torch.from_numpy(cmds), total_steps=total_steps)
-        main_reward = out["total_reward"][::P1]
+        dev = explorer.device
+        local_r = torch.from_numpy(np.ascontiguousarray(out["total_reward"][::P1])).to(dev)
+        local_f = torch.from_numpy(out["fim"]).to(dev)
+        main_reward, fim = gather_main_results(local_r, local_f, world, group)
+        main_reward, fim = main_reward.cpu().numpy(), fim.cpu().numpy()
+        prev_best = es.best[1]
         es.tell(-main_reward)
+        if es.best[1] < prev_best:
+            best_fim = fim[int(np.argmax(main_reward))]
         history.append(float(main_reward.max()))
     best_x, best_v = es.best
     best_commands = expand_commands(commands_constant(best_x.reshape(n_updates, -1), steps_per_update))
-    return {"best_commands": best_commands, "best_value": -best_v, "history": history}
+    return {"best_commands": best_commands, "best_value": -best_v, "history": history, "best_fim": best_fim}

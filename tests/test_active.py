@@ -40,6 +40,23 @@ class OracleActiveBackend:
                 torch.from_numpy((J * J).sum(axis=(1, 2)).astype(np.float32)))
 
 
+class OracleTensorBackend(OracleActiveBackend):
+    """+ fim_contract with the signature of RolloutEngine.fim_contract (fp64 einsum): host logic of the deferred FIM."""
+
+    def fim_contract(self, hist, delta, live=None, out_JtJ=None, out_trace=None, accumulate=False):
+        h = hist.numpy().astype(np.float64)
+        J = (h[:, :, 0:1, :] - h[:, :, 1:, :]) / float(delta)
+        if live is not None:
+            J = np.where(live.numpy().astype(bool)[:, :, None, None], J, 0.0)
+        jtj = torch.from_numpy(np.einsum("tmpd,tmqd->mpq", J, J).astype(np.float32))
+        tr = torch.from_numpy((J * J).sum(axis=(0, 2, 3)).astype(np.float32))
+        if accumulate:
+            out_JtJ.add_(jtj); out_trace.add_(tr)
+        else:
+            out_JtJ.copy_(jtj); out_trace.copy_(tr)
+        return out_JtJ, out_trace
+
+
 def test_observation_layout_matches_reference():
     g = np.load(GOLD / "active_obs.npz")
     T, N = g["states"].shape[:2]
@@ -100,6 +117,40 @@ def test_evaluate_policy_on_oracle_backend(blob, nominal_model):
     np.testing.assert_array_equal(r2, out["total_reward"])
 
 
+def test_deferred_tensor_fim_equals_per_step_fim(blob, nominal_model):
+    """fim_mode='tensor' (record states, contract every fim_chunk steps) gives the per-step accumulation's numbers,
+    including a group that terminates mid-rollout (its later steps score termination_rew = 0)."""
+    cmds = _commands(4, 40)
+
+    def run(mode, backend_cls, tip=True, **kw):
+        cfg = act.ActiveConfig(exploration_params=["mass", "comx", "motor_model_calf_a"], ksync_steps=5, seed=3,
+                               fim_mode=mode, **kw)
+        ex = act.ActiveExploration(backend_cls(blob, nominal_model), act.PolicyMLP.random("cpu", seed=1), 4, cfg)
+        orig = ex._policy_step
+        calls = {"n": 0}
+
+        def tipping_step():            # roll group 1's main env over at step 12 -> terminated from then on
+            calls["n"] += 1
+            if tip and calls["n"] == 12:
+                ex.state[4, 3:7] = torch.tensor([0.70710678, 0.0, 0.0, 0.70710678])
+            orig()
+        ex._policy_step = tipping_step
+        return ex.evaluate_policy(cmds, total_steps=30, use_cuda_graph=False)
+
+    a = run("step", OracleActiveBackend)
+    for chunk in (7, 64):
+        b = run("tensor", OracleTensorBackend, fim_chunk=chunk)
+        assert b["steps"] == a["steps"]
+        np.testing.assert_allclose(b["total_reward"], a["total_reward"], rtol=2e-5)
+        np.testing.assert_allclose(b["fim"], a["fim"], rtol=2e-5, atol=1e-6 * np.abs(a["fim"]).max())
+    r, r0 = a["total_reward"].reshape(4, 4), run("step", OracleActiveBackend, tip=False)["total_reward"].reshape(4, 4)
+    assert r[1, 0] < 0.95 * r0[1, 0]                            # the tipped group stopped collecting reward
+    np.testing.assert_array_equal(np.delete(r, 1, axis=0), np.delete(r0, 1, axis=0))
+    with pytest.raises(ValueError):
+        act.ActiveExploration(OracleActiveBackend(blob, nominal_model), act.PolicyMLP.random("cpu"), 2,
+                              act.ActiveConfig(fim_mode="tensor"))
+
+
 def test_terminated_groups_score_zero(blob, nominal_model):
     be = OracleActiveBackend(blob, nominal_model)
     ex = act.ActiveExploration(be, act.PolicyMLP.random("cpu", seed=1), 2, act.ActiveConfig(seed=0, randomize_reset=False))
@@ -123,6 +174,44 @@ def test_command_samplers():
     assert p.shape == (1250, 3) and (p >= r[:, 0] - 1e-6).all() and (p <= r[:, 1] + 1e-6).all()
     b = act.commands_bezier(np.array([[0.0], [1.0], [1.0], [0.0]]), 101)
     assert abs(b[0, 0]) < 1e-7 and abs(b[-1, 0]) < 1e-7 and abs(b[50, 0] - 0.75) < 1e-6
+
+
+def _active_gloo_worker(rank, world, port, out_dir):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from spi_active_b200 import go2_model as gm2
+    model = gm2.go2_nominal()
+    be = OracleActiveBackend(gm2.build_model_blob(model), model)
+    ex = act.ActiveExploration(be, act.PolicyMLP.random("cpu", seed=1), 4 // world,
+                               act.ActiveConfig(exploration_params=["mass", "comx"], seed=3, randomize_reset=False))
+    res = act.optimize_commands(ex, iterations=2, rollout_length=0.4, horizon_length=0.2, seed=0, total_steps=12,
+                                rank=rank, world=world)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), history=res["history"], best=res["best_commands"],
+             fim=res["best_fim"])
+    dist.destroy_process_group()
+
+
+def test_sharded_command_search_over_gloo_matches_single_process(tmp_path):
+    """Config 5 at world_size 2 (gloo, CPU oracle physics): trials sharded over ranks, rewards + Fisher blocks
+    all-gathered; every rank ends with the single-process result."""
+    import socket
+    import torch.multiprocessing as mp
+    outs = {}
+    for world in (1, 2):
+        d = tmp_path / f"w{world}"
+        d.mkdir()
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+        mp.spawn(_active_gloo_worker, args=(world, port, str(d)), nprocs=world, join=True)
+        outs[world] = [np.load(d / f"rank{r}.npz") for r in range(world)]
+    a, b0, b1 = outs[1][0], outs[2][0], outs[2][1]
+    for k in ("history", "best", "fim"):
+        np.testing.assert_array_equal(b0[k], b1[k])
+        # the policy GEMMs see a different batch size per rank: fp32 summation order differs, the closed loop amplifies it
+        np.testing.assert_allclose(b0[k], a[k], rtol=5e-4)
+    assert a["fim"].shape == (2, 2) and a["history"].shape == (2,) and (a["history"] > 0).all()
 
 
 def test_cma_es_minimises():
@@ -166,8 +255,17 @@ def test_evaluate_policy_gpu_matches_oracle_loop(engine, blob, nominal_model):
     cmds = _commands(6, 40)
     ref = act.ActiveExploration(OracleActiveBackend(blob, nominal_model), act.PolicyMLP.random("cpu", seed=1), 6, cfg)
     r_ref = ref.evaluate_policy(cmds, total_steps=20, use_cuda_graph=False)
+    import dataclasses
     for graph in (False, True):
-        ex = act.ActiveExploration(engine, act.PolicyMLP.random(engine.device, seed=1), 6, cfg)
-        r = ex.evaluate_policy(cmds, total_steps=20, use_cuda_graph=graph)
-        np.testing.assert_allclose(r["total_reward"], r_ref["total_reward"], rtol=2e-2)
-        np.testing.assert_allclose(r["fim"], r_ref["fim"], rtol=5e-2, atol=1e-3 * np.abs(r_ref["fim"]).max())
+        res = {}
+        for mode in ("step", "tensor"):
+            ex = act.ActiveExploration(engine, act.PolicyMLP.random(engine.device, seed=1), 6,
+                                       dataclasses.replace(cfg, fim_mode=mode, fim_chunk=8))
+            assert ex.fim_mode == mode
+            r = res[mode] = ex.evaluate_policy(cmds, total_steps=20, use_cuda_graph=graph)
+            np.testing.assert_allclose(r["total_reward"], r_ref["total_reward"], rtol=2e-2)
+            np.testing.assert_allclose(r["fim"], r_ref["fim"], rtol=5e-2, atol=1e-3 * np.abs(r_ref["fim"]).max())
+        # same physics, two FIM kernels (CUDA cores per step vs tcgen05 over the recorded states): fp32-tight
+        np.testing.assert_allclose(res["tensor"]["total_reward"], res["step"]["total_reward"], rtol=1e-5)
+        np.testing.assert_allclose(res["tensor"]["fim"], res["step"]["fim"], rtol=1e-4,
+                                   atol=1e-5 * np.abs(res["step"]["fim"]).max())

@@ -10,7 +10,8 @@ from spi_active_b200.engine import RolloutEngine
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1250
 eng = RolloutEngine()
-cfg = act.ActiveConfig(exploration_params=list(act.ActiveExploration.PARAM_ORDER))
+mode = sys.argv[3] if len(sys.argv) > 3 else "auto"
+cfg = act.ActiveConfig(exploration_params=list(act.ActiveExploration.PARAM_ORDER), fim_mode=mode)
 ex = act.ActiveExploration(eng, act.PolicyMLP.random(eng.device, seed=0, gain=0.3), M, cfg)
 rng = np.random.default_rng(0)
 r = np.asarray(act.COMMAND_RANGES)
@@ -25,5 +26,5 @@ for graph in (True, False):
         out = ex.evaluate_policy(cmds, total_steps=steps, use_cuda_graph=True)
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
     rew = out["total_reward"][::ex.param_dim + 1]
-    print(f"graph={graph} M={M} P={ex.param_dim} envs={ex.num_envs} steps={out['steps']}: {dt:.3f} s  -> "
+    print(f"fim={ex.fim_mode} graph={graph} M={M} P={ex.param_dim} envs={ex.num_envs} steps={out['steps']}: {dt:.3f} s  -> "
           f"{ex.num_envs * out['steps'] / dt:.3e} env-steps/s; reward mean {rew.mean():.4g} alive {(rew > 0).mean():.2f}")
