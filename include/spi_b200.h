@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SPI_B200_VERSION 100 /* major*100 + minor */
+#define SPI_B200_VERSION 101 /* major*100 + minor */
 
 /* ------------------------------------------------------------------------------------------
  * Model blob layout (fp32[SPI_BLOB_SIZE]).  Built on the host from the URDF
@@ -188,10 +188,12 @@ int spi_b200_sim_step(spi_b200_model* model,
  * LeggedRobotBase.step without the observation / reward bookkeeping, legged_robot_base.py:169-209, with the torque law
  * of the env in use, go2_omni.py:423-465 + active_sysid_openloop.py:174-187): clip the action, then `decimation` x
  * (PD + motor model from the fresh q, qd -> one physics step).
- *   params [N,P] or NULL, state [N,37] in/out, actions [N,12], gains [N,24] or NULL -> blob defaults               */
+ *   params [N,P] or NULL, state [N,37] in/out, actions [N,12], gains [N,24] or NULL -> blob defaults;
+ *   zero_action_mask [N] bytes or NULL: 1 = the env's action is replaced by 0 before the clip (the driver zeroes the
+ *   actions of terminated envs, agents/sysid/active_sysid.py:559-562)                                              */
 int spi_b200_env_step(spi_b200_model* model, const float* params, int P, const int* param_ids, float* state,
-                      const float* actions, const float* gains, int N, int decimation, int motor_model,
-                      unsigned flags, void* cuda_stream);
+                      const float* actions, const unsigned char* zero_action_mask, const float* gains, int N,
+                      int decimation, int motor_model, unsigned flags, void* cuda_stream);
 
 /* Motor-model + PD torque operator on its own (parity hook for
  * legged_robot_base.py:545,557 and active_sysid_openloop.py:356-400):
@@ -209,6 +211,26 @@ int spi_b200_compute_torques(spi_b200_model* model,
  *   out_JtJ [M,P,P] (+= if accumulate != 0) and out_trace [M] = ||J||_F^2 (the reward).       */
 int spi_b200_fim_reward(spi_b200_model* model, const float* states, int M, int P, float delta,
                         int accumulate, float* out_JtJ, float* out_trace, void* cuda_stream);
+
+/* Everything the env classes do AFTER the physics of one control step of the active-exploration rollout, fused:
+ * command playback (active_sysid_openloop.py:196-201), gravity termination OR-ed over each (1 main + P aux) group
+ * (legged_robot_base.py:336-339, active_sysid_openloop.py:259-272), the FIM inputs of the step (:402-426) into the
+ * history ring of spi_b200_fim_contract, the 900-dim actor observation (legged_robot_base.py:240-250, 511-527, 819-829,
+ * config/obs/loco/go2_omni.yaml) + history push (env_utils/history_handler.py:36-44), the k-step aux <- main sync
+ * (:247-252, 316-330) and the gait clock of the next step (go2_omni.py:348-377).  N = M * P1 envs, group-major.
+ *   state [N,37] in/out; raw_actions [N,12] = policy output the physics of this step used; done [N] bytes in: flags of
+ *   the previous step (those envs ran with a zero action), out: new flags; main_commands [M,T,14];
+ *   commands [N,14], actions [N,12] out; gait [N], clock [N,4], history [N,14,60] in/out; obs [N,900] out;
+ *   hist_index [840] device ints (short_history gather); fim_hist [K,M,P1,25] + fim_live [K,M] or NULL;
+ *   dead_steps [N] or NULL (+= done); schedule [steps,4] device ints (command row, sync flag, FIM slot, unused),
+ *   counter [1] / ctrl [4] device ints: ctrl <- schedule[counter++] on the device before the step;
+ *   q_default [12] HOST.  1 <= P1 <= 17.                                                                          */
+int spi_b200_active_post_step(spi_b200_model* model, float* state, const float* raw_actions, unsigned char* done,
+                              const float* main_commands, int T, float* commands, float* actions, float* gait,
+                              float* clock, float* history, float* obs, const int* hist_index, float* fim_hist,
+                              unsigned char* fim_live, float* dead_steps, const int* schedule, int* counter, int* ctrl,
+                              int M, int P1, float dt, float action_clip, float clip_obs, float grav_x, float grav_y,
+                              const float* q_default, void* cuda_stream);
 
 /* Accumulated Fisher information of whole rollouts on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 split =
  * fp32-accurate): the sum over control steps of the per-step J J^T that active_sysid_openloop.py:402-426 forms and

@@ -179,6 +179,9 @@ class ActiveConfig:
     # kept on device and contracted on the tensor cores (spi_b200_fim_contract); "auto": tensor on a CUDA backend
     fim_mode: str = "auto"
     fim_chunk: int = 64
+    # "torch": the post-physics bookkeeping of a step as ~130 torch ops (device-agnostic statement, runs on the CPU
+    # oracle in tests); "fused": one CUDA kernel (spi_b200_active_post_step, needs fim_mode tensor); "auto": fused on CUDA
+    step_impl: str = "auto"
 
 
 class ActiveExploration:
@@ -242,6 +245,19 @@ class ActiveExploration:
             self.slot = torch.zeros(1, dtype=torch.long, device=self.device)
             self.trace_acc, self.dead_steps = z(self.num_main_envs), z(N)
             self._hist_count = 0
+        impl = c.step_impl
+        if impl == "auto":
+            impl = "fused" if (mode == "tensor" and hasattr(backend, "active_post_step")) else "torch"
+        if impl not in ("torch", "fused"):
+            raise ValueError(f"step_impl must be 'auto', 'torch' or 'fused', not {c.step_impl!r}")
+        if impl == "fused" and not (mode == "tensor" and hasattr(backend, "active_post_step")):
+            raise ValueError("step_impl='fused' needs fim_mode='tensor' and a backend with active_post_step")
+        self.step_impl = impl
+        if impl == "fused":
+            self.hist_index_i32 = self.hist_index.to(torch.int32).contiguous()
+            self.counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.ctrl = torch.zeros(4, dtype=torch.int32, device=self.device)
+            self.zero_actions = z(N, 12)
 
     # ---- physics / reward through the engine -------------------------------------------------------------------------
     def _physics(self):
@@ -313,17 +329,54 @@ class ActiveExploration:
         self._hist_count = 0
 
     def _policy_step(self):
+        if self.step_impl == "fused":
+            return self._fused_step(self.policy(self.obs))
         actions = self.policy(self.obs)
         actions = torch.where(self.done[:, None], torch.zeros_like(actions), actions)   # active_sysid.py:559-562
         self._env_step(actions)
 
+    # ---- fused CUDA step: policy output -> physics (terminated envs run with a zero action) -> one post-step kernel -----------
+    def _fused_step(self, raw_actions: torch.Tensor):
+        c = self.cfg
+        self.backend.env_step(self.state, raw_actions, params=self.params, param_names=self.param_names,
+                              motor_model=c.motor_model, flags=gm.FLAG_HIP_HALF, zero_action_mask=self.done)
+        self.backend.active_post_step(self.state, raw_actions, self.done, self.main_commands, self.commands,
+                                      self.actions, self.gait_indices, self.clock, self.history, self.obs,
+                                      self.hist_index_i32, self.hist, self.live_hist, self.dead_steps, self.schedule,
+                                      self.counter, self.ctrl, self.dt, c.action_clip, CLIP_OBSERVATIONS,
+                                      TERMINATION_GRAVITY, self.model.q_default)
+
+    def _build_schedule(self, n_calls: int, T: int):
+        """Row i = the host inputs of the (i + 1)-th env step after a reset: (command row, k-sync flag, FIM ring slot)
+        — what _advance_inputs computes step by step, uploaded once."""
+        k, K = self.cfg.ksync_steps, self.hist.shape[0]
+        n_rows = n_calls + 4              # + the rows the graph warm-up / capture steps read past the end
+        rows = np.zeros((n_rows, 4), dtype=np.int32)
+        for i in range(n_rows):
+            idx = i + 1                                                  # step_idx after the increment
+            rows[i, 0] = min(idx, T - 1)
+            rows[i, 1] = int((k == 1) or (k > 1 and idx % k == 1))
+            rows[i, 2] = 0 if i == 0 else (i - 1) % K                    # call 0 is the reset step (dropped)
+        if getattr(self, "schedule", None) is None or self.schedule.shape[0] < n_rows:
+            self.schedule = torch.zeros((n_rows, 4), dtype=torch.int32, device=self.device)
+            self._graph = None            # a captured step holds the old buffer's address
+        self.schedule[:n_rows].copy_(torch.from_numpy(rows))
+        self.counter.zero_()
+
     # ---- reset ---------------------------------------------------------------------------------------------------------------
-    def reset_all(self, main_commands: torch.Tensor):
+    def reset_all(self, main_commands: torch.Tensor, total_steps: Optional[int] = None):
         """active_sysid_openloop.py:116-131 + base_task.py:90-100: reset, then ONE env step with zero actions."""
         c, N, P1 = self.cfg, self.num_envs, self.param_dim + 1
-        self.expanded_main_commands = main_commands.to(self.device, torch.float32).repeat_interleave(P1, dim=0)
+        mc = main_commands.to(self.device, torch.float32)
+        if getattr(self, "main_commands", None) is None or self.main_commands.shape != mc.shape:
+            self.main_commands = torch.empty_like(mc, memory_format=torch.contiguous_format)
+            self._graph = None            # persistent buffer: a captured step reads the command rows from it
+        self.main_commands.copy_(mc)
+        fused = self.step_impl == "fused"
+        if not fused:
+            self.expanded_main_commands = self.main_commands.repeat_interleave(P1, dim=0)
         self.step_idx = 0
-        self.commands.copy_(self.expanded_main_commands[:, 0, :])
+        self.commands.copy_(self.main_commands[:, 0, :].repeat_interleave(P1, dim=0))
         g = torch.Generator().manual_seed(c.seed)
         M = self.num_main_envs
         s = torch.zeros(M, gm.STATE_DIM)
@@ -336,6 +389,14 @@ class ActiveExploration:
         for t in (self.actions, self.history, self.gait_indices, self.clock, self.total_reward, self.jtj, self.step_reward):
             t.zero_()
         self.done.zero_()
+        if fused:
+            self._build_schedule(int(total_steps or self.total_steps), self.main_commands.shape[1])
+            # the gait clock of the first step (go2_omni.step); afterwards the post-step kernel advances it
+            g, clk = step_contact_targets(self.gait_indices, self.commands, self.dt)
+            self.gait_indices.copy_(g); self.clock.copy_(clk)
+            self.step_idx += 1
+            self._fused_step(self.zero_actions)
+            return self.obs
         self._advance_inputs()
         self._env_step(torch.zeros(N, 12, device=self.device))
         return self.obs
@@ -358,9 +419,10 @@ class ActiveExploration:
         "fim": [M, P, P] accumulated J J^T / steps}  (active_sysid.py:528-600)."""
         total_steps = int(total_steps or self.total_steps)
         assert commands.shape[0] == self.num_main_envs and commands.shape[2] == 14
-        self.reset_all(commands)
+        self.reset_all(commands, total_steps)
         self.total_reward.zero_(); self.jtj.zero_()
         tensor = self.fim_mode == "tensor"
+        fused = self.step_impl == "fused"
         if tensor:
             self.trace_acc.zero_(); self.dead_steps.zero_()
             self._hist_count = 0                      # the reset step's record is dropped, like its reward (:545-548)
@@ -369,7 +431,10 @@ class ActiveExploration:
         if graph_ok and self._graph is None:
             self._capture()
         for _ in range(1, total_steps - 1):
-            self._advance_inputs()
+            if fused:
+                self.step_idx += 1
+            else:
+                self._advance_inputs()
             if graph_ok:
                 self._graph.replay()
             else:
@@ -392,6 +457,8 @@ class ActiveExploration:
                 self.total_reward, self.jtj, self.step_reward]
         if self.fim_mode == "tensor":
             live += [self.dead_steps]                 # hist / live_hist slots are rewritten before they are read
+        if self.step_impl == "fused":
+            live += [self.counter]                    # the warm-up / capture steps must not consume schedule rows
         saved = [t.clone() for t in live]
         saved_done = self.done.clone()
         s = torch.cuda.Stream(device=self.device)

@@ -29,6 +29,7 @@ struct WsArgs {
   float* per_seg;      // [C][S][3] or null
   int* bad;            // [C]
   float* out_states;   // [C][S][H][37] (RECORD)
+  const unsigned char* zero_mask;   // paired mode: [S] 1 = this env's action is replaced by 0 (terminated group), or null
 };
 
 struct WsSmem {
@@ -83,11 +84,13 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, int lan
   const float h = S.dt / (float)S.nsub;
   const float* act_row = A.seg_actions + (size_t)seg * A.H * 12 + 3 * LEG;
   LegKeep K;
+  const bool zero_act = A.zero_mask && A.zero_mask[seg] != 0;
   ws_barrier();   // [S0] the base role has published R / v0 / pz of the initial state
   for (int k = 0; k < A.H; k++) {
     float act[3];
 #pragma unroll
-    for (int j = 0; j < 3; j++) act[j] = fminf(fmaxf(__ldg(act_row + 12 * k + j), -S.action_clip), S.action_clip);
+    for (int j = 0; j < 3; j++)
+      act[j] = zero_act ? 0.f : fminf(fmaxf(__ldg(act_row + 12 * k + j), -S.action_clip), S.action_clip);
     for (int d = 0; d < A.decimation; d++) {
       float tau[3];
       leg_torques(S, L, act, s.q, s.qd, kp, kd, motor, A.motor_model, A.flags, tau);

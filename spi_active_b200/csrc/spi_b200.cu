@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "aba_leg.cuh"
+#include "active_step.cuh"
 #include "fim_tc.cuh"
 #include "rollout_ws.cuh"
 
@@ -38,6 +39,7 @@ struct EvalArgs {
   float* per_seg;      // [C][S][3] or null
   int* bad;            // [C]
   float* out_states;   // [C][S][H][37] (RECORD)
+  const unsigned char* zero_mask;   // paired mode: [S] 1 = action replaced by 0, or null
 };
 
 SPI_DEV void load_leg_const(const DeviceModel& M, int leg, LegConst& L) {
@@ -120,10 +122,12 @@ __global__ void __launch_bounds__(kThreads, MINB) rollout_kernel(const EvalArgs 
   }
   const float h = S.dt / (float)S.nsub;
   const float* act_row = A.seg_actions + (size_t)seg * A.H * 12 + 3 * leg;
+  const bool zero_act = A.zero_mask && A.zero_mask[seg] != 0;
   for (int k = 0; k < A.H; k++) {
     float act[3];
 #pragma unroll
-    for (int j = 0; j < 3; j++) act[j] = fminf(fmaxf(__ldg(act_row + 12 * k + j), -S.action_clip), S.action_clip);
+    for (int j = 0; j < 3; j++)
+      act[j] = zero_act ? 0.f : fminf(fmaxf(__ldg(act_row + 12 * k + j), -S.action_clip), S.action_clip);
     for (int d = 0; d < A.decimation; d++) {
       float tau[3];
       lane_torques(S, L, act, s.q, s.qd, kp, kd, motor, A.motor_model, A.flags, tau);
@@ -545,7 +549,7 @@ int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C
                       const float* seg_init, const float* seg_actions, const float* seg_target, const float* seg_gains,
                       const unsigned char* seg_mask, int S, int H, int decimation, int motor_model, unsigned flags,
                       float cost_denominator, float* out_cost, float* out_per_seg, int* out_status, float* out_states,
-                      cudaStream_t st, int paired) {
+                      cudaStream_t st, int paired, const unsigned char* zero_mask) {
   ws::WsArgs A;
   std::memset(&A, 0, sizeof(A));
   ParamIds ids;
@@ -557,7 +561,7 @@ int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C
   A.seg_init = seg_init; A.seg_actions = seg_actions; A.seg_target = seg_target; A.seg_gains = seg_gains;
   A.seg_mask = seg_mask; A.S = S; A.H = H; A.decimation = decimation; A.motor_model = motor_model; A.flags = flags;
   A.n_cta_per_cand = (S + ws::kWsRollouts - 1) / ws::kWsRollouts;
-  A.paired = paired;
+  A.paired = paired; A.zero_mask = zero_mask;
   { static const int rot = getenv("SPI_B200_WS_ROT") ? atoi(getenv("SPI_B200_WS_ROT")) : 0; A.rotate_roles = rot; }
   const long long n_cta = (long long)C * A.n_cta_per_cand;
   if (n_cta > 2147483647LL) return fail(-3, "C * ceil(S/32) exceeds the grid limit");
@@ -594,7 +598,7 @@ int launch_rollout(spi_b200_model* m, bool record, const float* params, int C, i
                    const float* seg_init, const float* seg_actions, const float* seg_target, const float* seg_gains,
                    const unsigned char* seg_mask, int S, int H, int decimation, int motor_model, unsigned flags,
                    float cost_denominator, float* out_cost, float* out_per_seg, int* out_status, float* out_states,
-                   cudaStream_t st, int paired = 0) {
+                   cudaStream_t st, int paired = 0, const unsigned char* zero_mask = nullptr) {
   if (!m) return fail(-1, "model handle is NULL");
   if (C <= 0 || S <= 0 || H <= 0 || decimation <= 0) return fail(-3, "C, S, H, decimation must be positive");
   if (!seg_init || !seg_actions) return fail(-3, "seg_init / seg_actions is NULL");
@@ -606,7 +610,7 @@ int launch_rollout(spi_b200_model* m, bool record, const float* params, int C, i
   if (m->ws_ok && m->kernel != SPI_KERNEL_LANE && (m->kernel == SPI_KERNEL_WS || kernel_choice() != 1))
     return launch_rollout_ws(m, record, params, C, P, param_ids, seg_init, seg_actions, seg_target, seg_gains, seg_mask,
                              S, H, decimation, motor_model, flags, cost_denominator, out_cost, out_per_seg, out_status,
-                             out_states, st, paired);
+                             out_states, st, paired, zero_mask);
   EvalArgs A;
   std::memset(&A, 0, sizeof(A));
   if (int rc = make_ids(P, param_ids, &A.ids)) return rc;
@@ -616,7 +620,7 @@ int launch_rollout(spi_b200_model* m, bool record, const float* params, int C, i
   A.seg_mask = seg_mask; A.S = S; A.H = H; A.decimation = decimation; A.motor_model = motor_model; A.flags = flags;
   A.n_cta_per_cand = (S + kRolloutsPerCta - 1) / kRolloutsPerCta;
   A.n_warp_per_cand = A.n_cta_per_cand * (kThreads / 32);
-  A.paired = paired;
+  A.paired = paired; A.zero_mask = zero_mask;
   const long long n_cta = (long long)C * A.n_cta_per_cand;
   if (n_cta > 2147483647LL) return fail(-3, "C * ceil(S/32) exceeds the grid limit");
   if (!record) {
@@ -792,15 +796,16 @@ int spi_b200_eval_candidates_host(spi_b200_model* m, const float* params, int C,
 }
 
 int spi_b200_env_step(spi_b200_model* m, const float* params, int P, const int* param_ids, float* state,
-                      const float* actions, const float* gains, int N, int decimation, int motor_model, unsigned flags,
-                      void* cuda_stream) {
+                      const float* actions, const unsigned char* zero_action_mask, const float* gains, int N,
+                      int decimation, int motor_model, unsigned flags, void* cuda_stream) {
   if (!m) return fail(-1, "model handle is NULL");
   if (N <= 0 || decimation <= 0) return fail(-3, "N and decimation must be positive");
   if (!state || !actions) return fail(-3, "state / actions is NULL");
   // one control step of N independent envs = the RECORD rollout kernel with H = 1 in paired mode (env e uses
   // parameter row e and state row e); every lane reads its row before it writes it, so in-place is safe
   return launch_rollout(m, true, params, 1, params ? P : 0, param_ids, state, actions, nullptr, gains, nullptr, N, 1,
-                        decimation, motor_model, flags, 0.f, nullptr, nullptr, nullptr, state, (cudaStream_t)cuda_stream, 1);
+                        decimation, motor_model, flags, 0.f, nullptr, nullptr, nullptr, state, (cudaStream_t)cuda_stream, 1,
+                        zero_action_mask);
 }
 
 int spi_b200_sim_step(spi_b200_model* m, const float* params, int P, const int* param_ids, unsigned flags, float* state,
@@ -841,6 +846,38 @@ int spi_b200_fim_reward(spi_b200_model* m, const float* states, int Mn, int P, f
   fim_reward_kernel<<<(Mn + warps_per_cta - 1) / warps_per_cta, threads, 0, (cudaStream_t)cuda_stream>>>(
       states, Mn, P, delta, accumulate, out_JtJ, out_trace);
   return check_launch("fim_reward_kernel");
+}
+
+int spi_b200_active_post_step(spi_b200_model* m, float* state, const float* raw_actions, unsigned char* done,
+                              const float* main_commands, int T, float* commands, float* actions, float* gait,
+                              float* clock, float* history, float* obs, const int* hist_index, float* fim_hist,
+                              unsigned char* fim_live, float* dead_steps, const int* schedule, int* counter, int* ctrl,
+                              int Mn, int P1, float dt, float action_clip, float clip_obs, float grav_x, float grav_y,
+                              const float* q_default, void* cuda_stream) {
+  if (!m) return fail(-1, "model handle is NULL");
+  if (Mn <= 0 || P1 < 1 || P1 > activestep::kMaxGroup || T <= 0) return fail(-3, "bad M / group size / T");
+  if (!state || !raw_actions || !done || !main_commands || !commands || !actions || !gait || !clock || !history ||
+      !obs || !hist_index || !schedule || !counter || !ctrl || !q_default)
+    return fail(-3, "NULL buffer");
+  if (fim_hist && !fim_live) return fail(-3, "fim_live is NULL");
+  static std::atomic<int> attr_done{0};
+  if (!attr_done.load()) {
+    CUDA_OK(cudaFuncSetAttribute(activestep::active_post_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)activestep::smem_bytes(activestep::kMaxGroup)));
+    attr_done.store(1);
+  }
+  activestep::Args A;
+  A.state = state; A.raw_actions = raw_actions; A.done = done; A.main_commands = main_commands; A.commands = commands;
+  A.actions = actions; A.gait = gait; A.clock = clock; A.history = history; A.obs = obs; A.hist_index = hist_index;
+  A.fim_hist = fim_hist; A.fim_live = fim_live; A.dead_steps = dead_steps; A.ctrl = ctrl;
+  A.M = Mn; A.P1 = P1; A.T = T; A.dt = dt; A.action_clip = action_clip; A.clip_obs = clip_obs;
+  A.grav_x = grav_x; A.grav_y = grav_y;
+  for (int j = 0; j < 12; j++) A.q_default[j] = q_default[j];
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  activestep::tick_kernel<<<1, 1, 0, st>>>(schedule, counter, ctrl);
+  if (int rc = check_launch("tick_kernel")) return rc;
+  activestep::active_post_step_kernel<<<Mn, 32 * P1, activestep::smem_bytes(P1), st>>>(A);
+  return check_launch("active_post_step_kernel");
 }
 
 int spi_b200_fim_contract(spi_b200_model* m, const float* hist, const unsigned char* live, int T, int Mn, int P,

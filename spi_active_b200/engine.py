@@ -178,8 +178,10 @@ class RolloutEngine:
         return state
 
     def env_step(self, state: torch.Tensor, actions: torch.Tensor, params=None, param_names=(), gains=None,
-                 decimation: Optional[int] = None, motor_model="none", flags: int = 0) -> torch.Tensor:
-        """One control step of N independent envs IN PLACE: state[N,37], actions[N,12], per-env params[N,P]."""
+                 decimation: Optional[int] = None, motor_model="none", flags: int = 0,
+                 zero_action_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One control step of N independent envs IN PLACE: state[N,37], actions[N,12], per-env params[N,P];
+        zero_action_mask[N] (bool / uint8): envs whose action is replaced by 0."""
         assert state.is_cuda and state.dtype == torch.float32 and state.is_contiguous()
         actions = self._f32(actions).reshape(-1, 12)
         N = state.shape[0]
@@ -190,9 +192,12 @@ class RolloutEngine:
             P = params.shape[1]
             ids = _ids(param_names)
         gains = self._f32(gains)
+        if zero_action_mask is not None:
+            assert zero_action_mask.is_cuda and zero_action_mask.element_size() == 1 and zero_action_mask.numel() == N
+            zero_action_mask = zero_action_mask.contiguous()
         with torch.cuda.device(self.device):
             rc = self.lib.spi_b200_env_step(self._handle, _ptr(params), P, ids.ctypes.data_as(C.POINTER(C.c_int)),
-                                            _ptr(state), _ptr(actions), _ptr(gains), N,
+                                            _ptr(state), _ptr(actions), _ptr(zero_action_mask), _ptr(gains), N,
                                             int(decimation or self.model.control_decimation),
                                             motor_model_id(motor_model), int(flags), self._stream())
         _lib.check(rc, "spi_b200_env_step")
@@ -230,6 +235,29 @@ class RolloutEngine:
                                               _ptr(out_JtJ), _ptr(out_trace), self._stream())
         _lib.check(rc, "spi_b200_fim_reward")
         return out_JtJ, out_trace
+
+    def active_post_step(self, state, raw_actions, done, main_commands, commands, actions, gait, clock, history, obs,
+                         hist_index, fim_hist, fim_live, dead_steps, schedule, counter, ctrl, dt: float,
+                         action_clip: float, clip_obs: float, grav_xy, q_default):
+        """The fused post-physics step of the active-exploration rollout (spi_b200_active_post_step); every tensor is
+        updated in place.  state[N,37], main_commands[M,T,14], N = M * P1."""
+        Mn, T = int(main_commands.shape[0]), int(main_commands.shape[1])
+        N = int(state.shape[0])
+        P1 = N // Mn
+        assert N == Mn * P1 and main_commands.shape[2] == 14 and done.element_size() == 1
+        for t in (state, raw_actions, done, main_commands, commands, actions, gait, clock, history, obs, hist_index,
+                  schedule, counter, ctrl):
+            assert t.is_cuda and t.is_contiguous()
+        assert hist_index.dtype == torch.int32 and schedule.dtype == torch.int32 and counter.dtype == torch.int32
+        qd = np.ascontiguousarray(q_default, dtype=np.float32)
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_active_post_step(
+                self._handle, _ptr(state), _ptr(raw_actions), _ptr(done), _ptr(main_commands), T, _ptr(commands),
+                _ptr(actions), _ptr(gait), _ptr(clock), _ptr(history), _ptr(obs), _ptr(hist_index), _ptr(fim_hist),
+                _ptr(fim_live), _ptr(dead_steps), _ptr(schedule), _ptr(counter), _ptr(ctrl), Mn, P1, float(dt),
+                float(action_clip), float(clip_obs), float(grav_xy[0]), float(grav_xy[1]),
+                qd.ctypes.data_as(C.POINTER(C.c_float)), self._stream())
+        _lib.check(rc, "spi_b200_active_post_step")
 
     def fim_contract(self, hist: torch.Tensor, delta: float, live: Optional[torch.Tensor] = None,
                      out_JtJ: Optional[torch.Tensor] = None, out_trace: Optional[torch.Tensor] = None,
