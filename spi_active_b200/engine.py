@@ -54,6 +54,7 @@ class RolloutEngine:
             rc = self.lib.spi_b200_model_create(self.blob.ctypes.data_as(C.POINTER(C.c_float)), int(self.blob.size),
                                                 C.byref(self._handle))
         _lib.check(rc, "spi_b200_model_create")
+        self.kernel = "auto"
 
     def close(self):
         if getattr(self, "_handle", None) and self._handle.value:
@@ -328,6 +329,7 @@ class RolloutEngine:
         """'auto' | 'lane' (generic leg-per-lane kernel) | 'ws' (warp-specialised Go2-family fast path)."""
         kid = {"auto": 0, "lane": 1, "ws": 2}[kernel]
         _lib.check(self.lib.spi_b200_model_set_kernel(self._handle, kid), "spi_b200_model_set_kernel")
+        self.kernel = kernel
 
     def timing_enable(self, on: bool = True) -> None:
         """Bracket every rollout-kernel launch with CUDA events on its stream (roofline instrumentation)."""
