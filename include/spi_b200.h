@@ -232,6 +232,25 @@ int spi_b200_active_post_step(spi_b200_model* model, float* state, const float* 
                               int M, int P1, float dt, float action_clip, float clip_obs, float grav_x, float grav_y,
                               const float* q_default, void* cuda_stream);
 
+/* The locomotion policy (actor MLP: Linear-ELU x3 + Linear; spigym/agents/modules/modules.py:47-63,
+ * config/algo/ppo.yaml:32-40, evaluated per control step at agents/sysid/active_sysid.py:555-562) on the tensor cores
+ * with fp32-grade accuracy (tcgen05.mma kind::tf32, 3xTF32 split).  Constraints: 3 hidden layers, widths h1, h2
+ * multiples of 128, h3 = 128, <= 16 outputs (the reference's 900-512-256-128-12 actor qualifies).
+ *   dims [5] = in, h1, h2, h3, out; weights[l] [dims[l+1], dims[l]] row-major (torch Linear layout), biases[l]: HOST.
+ * The input is passed PRE-SPLIT (x = x_hi + x_lo, x_hi rounded to tf32) in padded [rows, stride] buffers whose layout
+ * spi_b200_policy_input_layout reports (rows = M rounded up to 128, stride = in rounded up to 32; padding must be
+ * zero-initialised by the owner).  spi_b200_active_post_step writes the observation in that form directly;
+ * spi_b200_policy_split_input converts a plain [M, in] matrix.  out [M, out] fp32.                                 */
+typedef struct spi_b200_policy spi_b200_policy;
+int spi_b200_policy_create(const int* dims, const float* const* weights, const float* const* biases,
+                           spi_b200_policy** out_policy);
+int spi_b200_policy_destroy(spi_b200_policy* policy);
+int spi_b200_policy_input_layout(spi_b200_policy* policy, int M, int* out_rows, int* out_stride);
+int spi_b200_policy_split_input(spi_b200_policy* policy, const float* x, int M, float* x_hi, float* x_lo,
+                                void* cuda_stream);
+int spi_b200_policy_forward(spi_b200_policy* policy, const float* x_hi, const float* x_lo, int M, float* out,
+                            void* cuda_stream);
+
 /* Accumulated Fisher information of whole rollouts on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 split =
  * fp32-accurate): the sum over control steps of the per-step J J^T that active_sysid_openloop.py:402-426 forms and
  * active_sysid.py:567-590 accumulates (terminated groups contribute termination_rew = 0 -> `live`).

@@ -14,6 +14,7 @@
 #include "aba_leg.cuh"
 #include "active_step.cuh"
 #include "fim_tc.cuh"
+#include "mlp_tc.cuh"
 #include "rollout_ws.cuh"
 
 using namespace spi;
@@ -878,6 +879,152 @@ int spi_b200_active_post_step(spi_b200_model* m, float* state, const float* raw_
   if (int rc = check_launch("tick_kernel")) return rc;
   activestep::active_post_step_kernel<<<Mn, 32 * P1, activestep::smem_bytes(P1), st>>>(A);
   return check_launch("active_post_step_kernel");
+}
+
+// ---- tensor-core policy MLP ---------------------------------------------------------------------------------------
+struct spi_b200_policy {
+  int dims[5] = {0, 0, 0, 0, 0};       // in, h1, h2, h3 (= 128), out
+  int Kp = 0;                          // padded input width (multiple of 32)
+  float* w_hi[3] = {nullptr, nullptr, nullptr};
+  float* w_lo[3] = {nullptr, nullptr, nullptr};
+  float* bias[3] = {nullptr, nullptr, nullptr};
+  float* w_out = nullptr; float* b_out = nullptr;
+  float* act[4] = {nullptr, nullptr, nullptr, nullptr};   // h1 hi, h1 lo, h2 hi, h2 lo
+  size_t act_rows = 0;
+};
+
+static void policy_free(spi_b200_policy* p) {
+  for (int l = 0; l < 3; l++) { cudaFree(p->w_hi[l]); cudaFree(p->w_lo[l]); cudaFree(p->bias[l]); }
+  cudaFree(p->w_out); cudaFree(p->b_out);
+  for (int i = 0; i < 4; i++) cudaFree(p->act[i]);
+  delete p;
+}
+
+// tile configuration of the policy GEMMs: SPI_B200_MLP_CFG = 0 (BK 32, 3 stages, 1 CTA / SM) or 1 (BK 16, 3 stages,
+// 96 KB -> 2 CTAs / SM); experiments only
+static int mlp_cfg() {
+  static const int v = [] { const char* e = getenv("SPI_B200_MLP_CFG"); return e ? atoi(e) : 0; }();
+  return v;
+}
+static cudaError_t mlp_set_attributes() {
+  cudaError_t e = cudaFuncSetAttribute(mlptc::mlp_layer_kernel<0, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlptc::Cfg<32, 3>::kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlptc::mlp_layer_kernel<1, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlptc::Cfg<32, 3>::kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlptc::mlp_layer_kernel<0, 16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlptc::Cfg<16, 3>::kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlptc::mlp_layer_kernel<1, 16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlptc::Cfg<16, 3>::kSmemBytes);
+  return e;
+}
+static void mlp_launch(int mode, const mlptc::LayerArgs& L, dim3 grid, cudaStream_t st) {
+  const int cfg = mlp_cfg();
+  if (mode == 0 && cfg == 1) mlptc::mlp_layer_kernel<0, 16, 3><<<grid, mlptc::kThreads, mlptc::Cfg<16, 3>::kSmemBytes, st>>>(L);
+  else if (mode == 0) mlptc::mlp_layer_kernel<0, 32, 3><<<grid, mlptc::kThreads, mlptc::Cfg<32, 3>::kSmemBytes, st>>>(L);
+  else if (cfg == 1) mlptc::mlp_layer_kernel<1, 16, 3><<<grid, mlptc::kThreads, mlptc::Cfg<16, 3>::kSmemBytes, st>>>(L);
+  else mlptc::mlp_layer_kernel<1, 32, 3><<<grid, mlptc::kThreads, mlptc::Cfg<32, 3>::kSmemBytes, st>>>(L);
+}
+
+static float tf32_rna_host(float x) {   // round to nearest, ties away: the value cvt.rna.tf32.f32 produces
+  uint32_t u; std::memcpy(&u, &x, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return x;
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  float r; std::memcpy(&r, &u, 4);
+  return r;
+}
+
+int spi_b200_policy_create(const int* dims, const float* const* weights, const float* const* biases,
+                           spi_b200_policy** out_policy) {
+  if (!out_policy) return fail(-1, "out_policy is NULL");
+  *out_policy = nullptr;
+  if (!dims || !weights || !biases) return fail(-3, "NULL argument");
+  for (int l = 0; l < 4; l++) if (!weights[l] || !biases[l]) return fail(-3, "NULL layer");
+  if (dims[0] <= 0 || dims[1] <= 0 || dims[1] % mlptc::kTile || dims[2] <= 0 || dims[2] % mlptc::kTile ||
+      dims[3] != mlptc::kTile || dims[4] <= 0 || dims[4] > mlptc::kMaxOut)
+    return fail(-3, "tensor-core policy needs 3 hidden layers, widths h1, h2 multiples of 128, h3 = 128, <= 16 outputs");
+  spi_b200_policy* p = new (std::nothrow) spi_b200_policy();
+  if (!p) return fail(-4, "out of host memory");
+  for (int i = 0; i < 5; i++) p->dims[i] = dims[i];
+  p->Kp = (dims[0] + mlptc::kKAlign - 1) / mlptc::kKAlign * mlptc::kKAlign;
+  cudaError_t e = cudaSuccess;
+  for (int l = 0; l < 3 && e == cudaSuccess; l++) {
+    const int N = dims[l + 1], K = dims[l], Kp = (l == 0) ? p->Kp : K;
+    std::vector<float> hi((size_t)N * Kp, 0.f), lo((size_t)N * Kp, 0.f);
+    for (int n = 0; n < N; n++)
+      for (int k = 0; k < K; k++) {
+        const float w = weights[l][(size_t)n * K + k];
+        const float h = tf32_rna_host(w);
+        hi[(size_t)n * Kp + k] = h; lo[(size_t)n * Kp + k] = w - h;
+      }
+    const size_t bytes = hi.size() * sizeof(float);
+    e = cudaMalloc((void**)&p->w_hi[l], bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->w_lo[l], bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->bias[l], (size_t)N * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(p->w_hi[l], hi.data(), bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->w_lo[l], lo.data(), bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->bias[l], biases[l], (size_t)N * sizeof(float), cudaMemcpyHostToDevice);
+  }
+  const size_t wo = (size_t)dims[4] * dims[3] * sizeof(float);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->w_out, wo);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->b_out, (size_t)dims[4] * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(p->w_out, weights[3], wo, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(p->b_out, biases[3], (size_t)dims[4] * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = mlp_set_attributes();
+  if (e != cudaSuccess) {
+    policy_free(p);
+    return fail(-100, std::string("policy upload failed: ") + cudaGetErrorString(e));
+  }
+  *out_policy = p;
+  return 0;
+}
+
+int spi_b200_policy_destroy(spi_b200_policy* p) {
+  if (p) policy_free(p);
+  return 0;
+}
+
+int spi_b200_policy_input_layout(spi_b200_policy* p, int M, int* out_rows, int* out_stride) {
+  if (!p) return fail(-1, "policy handle is NULL");
+  if (M <= 0) return fail(-3, "M must be positive");
+  if (out_rows) *out_rows = (M + mlptc::kTile - 1) / mlptc::kTile * mlptc::kTile;
+  if (out_stride) *out_stride = p->Kp;
+  return 0;
+}
+
+int spi_b200_policy_split_input(spi_b200_policy* p, const float* x, int M, float* x_hi, float* x_lo, void* cuda_stream) {
+  if (!p) return fail(-1, "policy handle is NULL");
+  if (M <= 0 || !x || !x_hi || !x_lo) return fail(-3, "bad arguments");
+  const size_t n = (size_t)M * p->dims[0];
+  mlptc::split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(x, M, p->dims[0], x_hi, x_lo, p->Kp);
+  return check_launch("split_kernel");
+}
+
+int spi_b200_policy_forward(spi_b200_policy* p, const float* x_hi, const float* x_lo, int M, float* out,
+                            void* cuda_stream) {
+  if (!p) return fail(-1, "policy handle is NULL");
+  if (M <= 0 || !x_hi || !x_lo || !out) return fail(-3, "bad arguments");
+  const int Mp = (M + mlptc::kTile - 1) / mlptc::kTile * mlptc::kTile;
+  if (p->act_rows < (size_t)Mp) {
+    for (int i = 0; i < 4; i++) { cudaFree(p->act[i]); p->act[i] = nullptr; }
+    p->act_rows = 0;
+    for (int i = 0; i < 4; i++) CUDA_OK(cudaMalloc((void**)&p->act[i], (size_t)Mp * p->dims[1 + i / 2] * sizeof(float)));
+    p->act_rows = (size_t)Mp;
+  }
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  mlptc::LayerArgs L;
+  std::memset(&L, 0, sizeof(L));
+  // layer 1
+  L.a_hi = x_hi; L.a_lo = x_lo; L.w_hi = p->w_hi[0]; L.w_lo = p->w_lo[0]; L.bias = p->bias[0]; L.Kp = p->Kp; L.N = p->dims[1];
+  L.out_hi = p->act[0]; L.out_lo = p->act[1]; L.out_stride = p->dims[1]; L.M = M;
+  mlp_launch(0, L, dim3(Mp / mlptc::kTile, p->dims[1] / mlptc::kTile), st);
+  if (int rc = check_launch("mlp_layer_kernel<0> (layer 1)")) return rc;
+  // layer 2
+  L.a_hi = p->act[0]; L.a_lo = p->act[1]; L.w_hi = p->w_hi[1]; L.w_lo = p->w_lo[1]; L.bias = p->bias[1]; L.Kp = p->dims[1]; L.N = p->dims[2];
+  L.out_hi = p->act[2]; L.out_lo = p->act[3]; L.out_stride = p->dims[2];
+  mlp_launch(0, L, dim3(Mp / mlptc::kTile, p->dims[2] / mlptc::kTile), st);
+  if (int rc = check_launch("mlp_layer_kernel<0> (layer 2)")) return rc;
+  // layer 3 + output layer
+  L.a_hi = p->act[2]; L.a_lo = p->act[3]; L.w_hi = p->w_hi[2]; L.w_lo = p->w_lo[2]; L.bias = p->bias[2]; L.Kp = p->dims[2]; L.N = p->dims[3];
+  L.out_hi = nullptr; L.out_lo = nullptr; L.out_stride = 0;
+  L.w_out = p->w_out; L.b_out = p->b_out; L.n_out = p->dims[4]; L.out = out;
+  mlp_launch(1, L, dim3(Mp / mlptc::kTile, 1), st);
+  return check_launch("mlp_layer_kernel<1> (layers 3 + 4)");
 }
 
 int spi_b200_fim_contract(spi_b200_model* m, const float* hist, const unsigned char* live, int T, int Mn, int P,

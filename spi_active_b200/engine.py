@@ -39,6 +39,81 @@ def motor_model_id(name_or_id) -> int:
     return int(name_or_id)
 
 
+class TensorCorePolicy:
+    """The actor MLP (Linear-ELU x3 + Linear) on the tensor cores with fp32-grade accuracy (spi_b200_policy_*,
+    3xTF32).  `weights[l]` is the torch Linear weight [out, in]; the reference's 900-512-256-128-12 actor qualifies
+    (h1, h2 multiples of 128, h3 = 128, <= 16 outputs) — anything else raises and the caller keeps its cuBLAS path."""
+
+    def __init__(self, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], device: torch.device):
+        self.lib = _lib.lib()
+        if len(weights) != 4 or len(biases) != 4:
+            raise _lib.SpiB200Error("tensor-core policy needs exactly 4 Linear layers")
+        ws = [np.ascontiguousarray(w.detach().cpu().numpy(), dtype=np.float32) for w in weights]
+        bs = [np.ascontiguousarray(b.detach().cpu().numpy(), dtype=np.float32) for b in biases]
+        dims = np.asarray([ws[0].shape[1]] + [w.shape[0] for w in ws], dtype=np.int32)
+        for l in range(4):
+            if ws[l].shape != (dims[l + 1], dims[l]) or bs[l].shape != (dims[l + 1],):
+                raise _lib.SpiB200Error(f"layer {l}: inconsistent shapes {ws[l].shape} / {bs[l].shape}")
+        self.device = torch.device(device)
+        self.dims = dims.tolist()
+        fp = C.POINTER(C.c_float)
+        wp = (fp * 4)(*[w.ctypes.data_as(fp) for w in ws])
+        bp = (fp * 4)(*[b.ctypes.data_as(fp) for b in bs])
+        self._handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_policy_create(dims.ctypes.data_as(C.POINTER(C.c_int)), wp, bp, C.byref(self._handle))
+        _lib.check(rc, "spi_b200_policy_create")
+
+    def close(self):
+        if getattr(self, "_handle", None) and self._handle.value:
+            self.lib.spi_b200_policy_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def input_layout(self, M: int):
+        """-> (rows, stride) of the padded, pre-split input buffers for M envs."""
+        rows, stride = C.c_int(), C.c_int()
+        _lib.check(self.lib.spi_b200_policy_input_layout(self._handle, int(M), C.byref(rows), C.byref(stride)),
+                   "spi_b200_policy_input_layout")
+        return rows.value, stride.value
+
+    def alloc_input(self, M: int):
+        rows, stride = self.input_layout(M)
+        return (torch.zeros(rows, stride, device=self.device, dtype=torch.float32),
+                torch.zeros(rows, stride, device=self.device, dtype=torch.float32))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def split_input(self, x: torch.Tensor, x_hi: torch.Tensor, x_lo: torch.Tensor):
+        assert x.is_cuda and x.is_contiguous() and x.dtype == torch.float32 and x.shape[1] == self.dims[0]
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_policy_split_input(self._handle, _ptr(x), int(x.shape[0]), _ptr(x_hi), _ptr(x_lo),
+                                                      self._stream())
+        _lib.check(rc, "spi_b200_policy_split_input")
+
+    def forward_split(self, x_hi: torch.Tensor, x_lo: torch.Tensor, M: int, out: Optional[torch.Tensor] = None):
+        rows, stride = self.input_layout(M)
+        assert tuple(x_hi.shape) == (rows, stride) == tuple(x_lo.shape) and x_hi.is_contiguous() and x_lo.is_contiguous()
+        if out is None:
+            out = torch.empty((M, self.dims[4]), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_policy_forward(self._handle, _ptr(x_hi), _ptr(x_lo), int(M), _ptr(out), self._stream())
+        _lib.check(rc, "spi_b200_policy_forward")
+        return out
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        x = x.to(self.device, torch.float32).contiguous()
+        x_hi, x_lo = self.alloc_input(x.shape[0])
+        self.split_input(x, x_hi, x_lo)
+        return self.forward_split(x_hi, x_lo, x.shape[0])
+
+
 class RolloutEngine:
     """Device-resident Go2 model + workspaces; one instance per (process, GPU, stream)."""
 
