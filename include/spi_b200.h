@@ -221,13 +221,15 @@ int spi_b200_fim_reward(spi_b200_model* model, const float* states, int M, int P
  *   state [N,37] in/out; raw_actions [N,12] = policy output the physics of this step used; done [N] bytes in: flags of
  *   the previous step (those envs ran with a zero action), out: new flags; main_commands [M,T,14];
  *   commands [N,14], actions [N,12] out; gait [N], clock [N,4], history [N,14,60] in/out; obs [N,900] out;
+ *   obs_hi / obs_lo [rows, obs_stride] or NULL: the same observation pre-split for spi_b200_policy_forward;
  *   hist_index [840] device ints (short_history gather); fim_hist [K,M,P1,25] + fim_live [K,M] or NULL;
  *   dead_steps [N] or NULL (+= done); schedule [steps,4] device ints (command row, sync flag, FIM slot, unused),
  *   counter [1] / ctrl [4] device ints: ctrl <- schedule[counter++] on the device before the step;
  *   q_default [12] HOST.  1 <= P1 <= 17.                                                                          */
 int spi_b200_active_post_step(spi_b200_model* model, float* state, const float* raw_actions, unsigned char* done,
                               const float* main_commands, int T, float* commands, float* actions, float* gait,
-                              float* clock, float* history, float* obs, const int* hist_index, float* fim_hist,
+                              float* clock, float* history, float* obs, float* obs_hi, float* obs_lo, int obs_stride,
+                              const int* hist_index, float* fim_hist,
                               unsigned char* fim_live, float* dead_steps, const int* schedule, int* counter, int* ctrl,
                               int M, int P1, float dt, float action_clip, float clip_obs, float grav_x, float grav_y,
                               const float* q_default, void* cuda_stream);

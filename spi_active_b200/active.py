@@ -182,6 +182,9 @@ class ActiveConfig:
     # "torch": the post-physics bookkeeping of a step as ~130 torch ops (device-agnostic statement, runs on the CPU
     # oracle in tests); "fused": one CUDA kernel (spi_b200_active_post_step, needs fim_mode tensor); "auto": fused on CUDA
     step_impl: str = "auto"
+    # actor evaluation in the fused step: "tensor" = spi_b200_policy_forward (tcgen05, 3xTF32: fp32-grade accuracy),
+    # "cublas" = torch fp32 GEMMs; "auto" = tensor when the actor has the supported shape (the reference's does)
+    policy_impl: str = "auto"
 
 
 class ActiveExploration:
@@ -258,6 +261,20 @@ class ActiveExploration:
             self.counter = torch.zeros(1, dtype=torch.int32, device=self.device)
             self.ctrl = torch.zeros(4, dtype=torch.int32, device=self.device)
             self.zero_actions = z(N, 12)
+            self.tc_policy = self.obs_hi = self.obs_lo = None
+            if c.policy_impl not in ("auto", "tensor", "cublas"):
+                raise ValueError(f"policy_impl must be 'auto', 'tensor' or 'cublas', not {c.policy_impl!r}")
+            if c.policy_impl != "cublas" and hasattr(backend, "tensor_core_policy"):
+                try:
+                    self.tc_policy = backend.tensor_core_policy(policy.weights, policy.biases)
+                except Exception:
+                    if c.policy_impl == "tensor":
+                        raise
+            elif c.policy_impl == "tensor":
+                raise ValueError("policy_impl='tensor' needs a backend with tensor_core_policy")
+            if self.tc_policy is not None:
+                self.obs_hi, self.obs_lo = self.tc_policy.alloc_input(N)
+                self.raw_actions = z(N, 12)
 
     # ---- physics / reward through the engine -------------------------------------------------------------------------
     def _physics(self):
@@ -330,6 +347,9 @@ class ActiveExploration:
 
     def _policy_step(self):
         if self.step_impl == "fused":
+            if self.tc_policy is not None:
+                return self._fused_step(self.tc_policy.forward_split(self.obs_hi, self.obs_lo, self.num_envs,
+                                                                     out=self.raw_actions))
             return self._fused_step(self.policy(self.obs))
         actions = self.policy(self.obs)
         actions = torch.where(self.done[:, None], torch.zeros_like(actions), actions)   # active_sysid.py:559-562
@@ -344,7 +364,7 @@ class ActiveExploration:
                                       self.actions, self.gait_indices, self.clock, self.history, self.obs,
                                       self.hist_index_i32, self.hist, self.live_hist, self.dead_steps, self.schedule,
                                       self.counter, self.ctrl, self.dt, c.action_clip, CLIP_OBSERVATIONS,
-                                      TERMINATION_GRAVITY, self.model.q_default)
+                                      TERMINATION_GRAVITY, self.model.q_default, obs_hi=self.obs_hi, obs_lo=self.obs_lo)
 
     def _build_schedule(self, n_calls: int, T: int):
         """Row i = the host inputs of the (i + 1)-th env step after a reset: (command row, k-sync flag, FIM ring slot)
@@ -459,6 +479,8 @@ class ActiveExploration:
             live += [self.dead_steps]                 # hist / live_hist slots are rewritten before they are read
         if self.step_impl == "fused":
             live += [self.counter]                    # the warm-up / capture steps must not consume schedule rows
+            if self.tc_policy is not None:
+                live += [self.obs_hi, self.obs_lo]    # what the tensor-core actor actually reads
         saved = [t.clone() for t in live]
         saved_done = self.done.clone()
         s = torch.cuda.Stream(device=self.device)

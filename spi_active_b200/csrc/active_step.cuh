@@ -19,6 +19,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#include <stdint.h>
 
 namespace activestep {
 
@@ -37,6 +38,8 @@ struct Args {
   float* clock;                    // [N,4] in/out
   float* history;                  // [N,14,60] in/out, newest first
   float* obs;                      // [N,900] out
+  float* obs_hi; float* obs_lo;    // [rows, obs_stride] or null: the same observation pre-split for spi_b200_policy_forward
+  int obs_stride;
   const int* hist_index;           // [840] gather index of short_history into the flattened [14*60] ring
   float* fim_hist;                 // [K,M,P1,25] or null
   unsigned char* fim_live;         // [K,M] or null
@@ -155,7 +158,15 @@ __global__ void __launch_bounds__(32 * kMaxGroup) active_post_step_kernel(const 
   float* orow = A.obs + (size_t)env * kObs;
   for (int i = lane; i < kObs; i += 32) {
     const float v = (i < kFrame) ? sm.frame(w)[i] : sm.hist(w)[A.hist_index[i - kFrame]];
-    orow[i] = fminf(fmaxf(v, -A.clip_obs), A.clip_obs);
+    const float o = fminf(fmaxf(v, -A.clip_obs), A.clip_obs);
+    orow[i] = o;
+    if (A.obs_hi) {
+      uint32_t hb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(o));
+      const float h = __uint_as_float(hb);
+      A.obs_hi[(size_t)env * A.obs_stride + i] = h;
+      A.obs_lo[(size_t)env * A.obs_stride + i] = o - h;
+    }
   }
   for (int i = lane; i < kHistLen * kFrame; i += 32) hrow[i] = (i < kFrame) ? sm.frame(w)[i] : sm.hist(w)[i - kFrame];
 

@@ -851,7 +851,8 @@ int spi_b200_fim_reward(spi_b200_model* m, const float* states, int Mn, int P, f
 
 int spi_b200_active_post_step(spi_b200_model* m, float* state, const float* raw_actions, unsigned char* done,
                               const float* main_commands, int T, float* commands, float* actions, float* gait,
-                              float* clock, float* history, float* obs, const int* hist_index, float* fim_hist,
+                              float* clock, float* history, float* obs, float* obs_hi, float* obs_lo, int obs_stride,
+                              const int* hist_index, float* fim_hist,
                               unsigned char* fim_live, float* dead_steps, const int* schedule, int* counter, int* ctrl,
                               int Mn, int P1, float dt, float action_clip, float clip_obs, float grav_x, float grav_y,
                               const float* q_default, void* cuda_stream) {
@@ -861,6 +862,7 @@ int spi_b200_active_post_step(spi_b200_model* m, float* state, const float* raw_
       !obs || !hist_index || !schedule || !counter || !ctrl || !q_default)
     return fail(-3, "NULL buffer");
   if (fim_hist && !fim_live) return fail(-3, "fim_live is NULL");
+  if (obs_hi && (!obs_lo || obs_stride < activestep::kObs)) return fail(-3, "obs_lo is NULL or obs_stride < 900");
   static std::atomic<int> attr_done{0};
   if (!attr_done.load()) {
     CUDA_OK(cudaFuncSetAttribute(activestep::active_post_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -870,6 +872,7 @@ int spi_b200_active_post_step(spi_b200_model* m, float* state, const float* raw_
   activestep::Args A;
   A.state = state; A.raw_actions = raw_actions; A.done = done; A.main_commands = main_commands; A.commands = commands;
   A.actions = actions; A.gait = gait; A.clock = clock; A.history = history; A.obs = obs; A.hist_index = hist_index;
+  A.obs_hi = obs_hi; A.obs_lo = obs_lo; A.obs_stride = obs_stride;
   A.fim_hist = fim_hist; A.fim_live = fim_live; A.dead_steps = dead_steps; A.ctrl = ctrl;
   A.M = Mn; A.P1 = P1; A.T = T; A.dt = dt; A.action_clip = action_clip; A.clip_obs = clip_obs;
   A.grav_x = grav_x; A.grav_y = grav_y;

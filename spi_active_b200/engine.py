@@ -314,7 +314,7 @@ class RolloutEngine:
 
     def active_post_step(self, state, raw_actions, done, main_commands, commands, actions, gait, clock, history, obs,
                          hist_index, fim_hist, fim_live, dead_steps, schedule, counter, ctrl, dt: float,
-                         action_clip: float, clip_obs: float, grav_xy, q_default):
+                         action_clip: float, clip_obs: float, grav_xy, q_default, obs_hi=None, obs_lo=None):
         """The fused post-physics step of the active-exploration rollout (spi_b200_active_post_step); every tensor is
         updated in place.  state[N,37], main_commands[M,T,14], N = M * P1."""
         Mn, T = int(main_commands.shape[0]), int(main_commands.shape[1])
@@ -329,11 +329,16 @@ class RolloutEngine:
         with torch.cuda.device(self.device):
             rc = self.lib.spi_b200_active_post_step(
                 self._handle, _ptr(state), _ptr(raw_actions), _ptr(done), _ptr(main_commands), T, _ptr(commands),
-                _ptr(actions), _ptr(gait), _ptr(clock), _ptr(history), _ptr(obs), _ptr(hist_index), _ptr(fim_hist),
+                _ptr(actions), _ptr(gait), _ptr(clock), _ptr(history), _ptr(obs), _ptr(obs_hi), _ptr(obs_lo),
+                0 if obs_hi is None else int(obs_hi.shape[1]), _ptr(hist_index), _ptr(fim_hist),
                 _ptr(fim_live), _ptr(dead_steps), _ptr(schedule), _ptr(counter), _ptr(ctrl), Mn, P1, float(dt),
                 float(action_clip), float(clip_obs), float(grav_xy[0]), float(grav_xy[1]),
                 qd.ctypes.data_as(C.POINTER(C.c_float)), self._stream())
         _lib.check(rc, "spi_b200_active_post_step")
+
+    def tensor_core_policy(self, weights, biases) -> "TensorCorePolicy":
+        """The actor MLP as a tensor-core operator on this engine's device (raises SpiB200Error for unsupported shapes)."""
+        return TensorCorePolicy(weights, biases, self.device)
 
     def fim_contract(self, hist: torch.Tensor, delta: float, live: Optional[torch.Tensor] = None,
                      out_JtJ: Optional[torch.Tensor] = None, out_trace: Optional[torch.Tensor] = None,
