@@ -520,53 +520,62 @@ WS_HD void base_publish(const BaseState& s, float* bc) {
   bc[kBcPz] = s.p[2];
 }
 
-// 6x6 SPD solve (LDL^T), A given as the articulated inertia blocks, b = -pA
+// 6x6 SPD solve  [[I, H], [H^T, M]] [a_w; a_v] = -[pA.a; pA.l]  by block elimination on the 3x3 blocks:
+//     Minv = adj(M) / det M,   Y = H Minv,   S = I - Y H^T (Schur complement, SPD),   a_w = S^-1 (b_w - Y b_v),
+//     a_v = Minv (b_v - H^T a_w)
+// The base solve is the serial section between the two leg phases (the four leg warps wait for it), so what matters is
+// the length of its dependency chain: two reciprocals and wide 3x3 products instead of the six sequential pivots of an
+// LDL^T factorisation (measured: the LDL^T version ran at 0.6x the legs' IPC — profiles/README.md).  Both 3x3 blocks
+// are well conditioned (M ~ total mass, S ~ the composite rotational inertia), so the adjugate inverses are fp32-safe.
+WS_HD void sym3_adjugate(const float* A, float* C, float* det) {   // A, C symmetric (xx, yy, zz, xy, xz, yz)
+  C[0] = A[1] * A[2] - A[5] * A[5];
+  C[1] = A[0] * A[2] - A[4] * A[4];
+  C[2] = A[0] * A[1] - A[3] * A[3];
+  C[3] = A[4] * A[5] - A[3] * A[2];
+  C[4] = A[3] * A[5] - A[4] * A[1];
+  C[5] = A[3] * A[4] - A[0] * A[5];
+  *det = A[0] * C[0] + A[3] * C[3] + A[4] * C[4];
+}
 WS_HD void solve_base(const ABI& A, const Twist& pA, Twist& a0) {
-  float M[6][6];
+  float Cm[6], detm;
+  sym3_adjugate(A.M, Cm, &detm);
+  const float rm = rcp_fast(detm);
+  // Yc = H adj(M)   (Y = Yc / det M)
+  float Yc[9];
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-      M[i][j] = A.I[sidx(i, j)];
-      M[i][3 + j] = A.H[3 * i + j];
-      M[3 + i][j] = A.H[3 * j + i];
-      M[3 + i][3 + j] = A.M[sidx(i, j)];
+    for (int j = 0; j < 3; j++)
+      Yc[3 * i + j] = A.H[3 * i] * Cm[sidx(0, j)] + A.H[3 * i + 1] * Cm[sidx(1, j)] + A.H[3 * i + 2] * Cm[sidx(2, j)];
+  // S = I - Y H^T, symmetric
+  float S[6];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = i; j < 3; j++) {
+      const float yh = Yc[3 * i] * A.H[3 * j] + Yc[3 * i + 1] * A.H[3 * j + 1] + Yc[3 * i + 2] * A.H[3 * j + 2];
+      S[sidx(i, j)] = fmaf(-rm, yh, A.I[sidx(i, j)]);
     }
-  float L[6][6], D[6], Dinv[6];
+  // t = b_w - Y b_v  with b = -pA:  t = -pA.a + Y pA.l
+  float t[3];
 #pragma unroll
-  for (int j = 0; j < 6; j++) {
-    float d = M[j][j];
-#pragma unroll
-    for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k] * D[k];
-    D[j] = d;
-    Dinv[j] = rcp_fast(d);
-#pragma unroll
-    for (int i = j + 1; i < 6; i++) {
-      float s = M[i][j];
-#pragma unroll
-      for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k] * D[k];
-      L[i][j] = s * Dinv[j];
-    }
+  for (int i = 0; i < 3; i++) {
+    const float yb = Yc[3 * i] * pA.l[0] + Yc[3 * i + 1] * pA.l[1] + Yc[3 * i + 2] * pA.l[2];
+    t[i] = fmaf(rm, yb, -pA.a[i]);
   }
-  float y[6], x[6];
+  float Cs[6], dets;
+  sym3_adjugate(S, Cs, &dets);
+  const float rs = rcp_fast(dets);
 #pragma unroll
-  for (int i = 0; i < 6; i++) {
-    float s = (i < 3) ? -pA.a[i] : -pA.l[i - 3];
+  for (int i = 0; i < 3; i++)
+    a0.a[i] = (Cs[sidx(i, 0)] * t[0] + Cs[sidx(i, 1)] * t[1] + Cs[sidx(i, 2)] * t[2]) * rs;
+  // a_v = Minv (b_v - H^T a_w) = -adj(M) (pA.l + H^T a_w) / det M
+  float u[3];
 #pragma unroll
-    for (int k = 0; k < i; k++) s -= L[i][k] * y[k];
-    y[i] = s;
-  }
+  for (int j = 0; j < 3; j++) u[j] = pA.l[j] + (A.H[j] * a0.a[0] + A.H[3 + j] * a0.a[1] + A.H[6 + j] * a0.a[2]);
 #pragma unroll
-  for (int i = 0; i < 6; i++) y[i] *= Dinv[i];
-#pragma unroll
-  for (int i = 5; i >= 0; i--) {
-    float s = y[i];
-#pragma unroll
-    for (int k = i + 1; k < 6; k++) s -= L[k][i] * x[k];
-    x[i] = s;
-  }
-#pragma unroll
-  for (int i = 0; i < 3; i++) { a0.a[i] = x[i]; a0.l[i] = x[3 + i]; }
+  for (int i = 0; i < 3; i++)
+    a0.l[i] = -((Cm[sidx(i, 0)] * u[0] + Cm[sidx(i, 1)] * u[1] + Cm[sidx(i, 2)] * u[2]) * rm);
 }
 
 // Base role, split in two so that the legs' acceleration pass overlaps the base integration:

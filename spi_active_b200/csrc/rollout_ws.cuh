@@ -174,11 +174,20 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, int la
 #pragma unroll
         for (int i = 0; i < 6; i++) sm.bc[kBcA0 + i][lane] = a0[i];
         ws_barrier();   // [B1] the legs start their acceleration pass
+        // keep the integration BEHIND the barrier: it only needs registers, so ptxas would otherwise schedule it between
+        // the a0 stores and the barrier and delay the legs by ~90 instructions.  Reading a0 back from shared memory is a
+        // dependency the scheduler cannot move across bar.sync (6 LDS, off the critical path).
+#pragma unroll
+        for (int i = 0; i < 6; i++) a0[i] = *(volatile float*)&sm.bc[kBcA0 + i][lane];
         base_advance(S, a0, s, h, bc);
 #pragma unroll
         for (int i = kBcR; i < kBaseOut; i++) sm.bc[i][lane] = bc[i];
-        base_bias(B, bc, pb);   // velocity-product bias of the next sub-step, off the critical path
         ws_barrier();   // [B2]
+        // velocity-product bias of the next sub-step: after the barrier, so that it overlaps the legs' phase 1 instead
+        // of delaying their release (re-read through shared memory for the same reason as a0 above)
+#pragma unroll
+        for (int i = kBcV0; i < kBcV0 + 6; i++) bc[i] = *(volatile float*)&sm.bc[i][lane];
+        base_bias(B, bc, pb);
       }
     }
     if (RECORD) {
