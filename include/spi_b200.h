@@ -62,6 +62,7 @@ enum {
   SPI_BLOB_FOOT_RADIUS = 9,    /* 0.022 */
   SPI_BLOB_NSUB = 10,          /* integrator sub-steps per physics step (float-encoded int) */
   SPI_BLOB_CONTACT_VEPS = 11,  /* slip-speed regulariser m/s */
+  SPI_BLOB_FOOT_SPHERE = 12,   /* 3 floats: foot collision-sphere centre in the FOOT link frame (urdf: -0.002, 0, 0) */
   SPI_BLOB_BASE_INERTIAL = 16, /* 10 floats: URDF base link */
   SPI_BLOB_BASE_LUMPS = 26,    /* 2 x 10 floats: mass, pos[3] in base frame, I[6] about own com */
   SPI_BLOB_LEG_BODIES = 46,    /* 12 x 14 floats: inertial[10], joint origin in parent[3], axis id (0=x,1=y) */
@@ -183,6 +184,13 @@ int spi_b200_sim_step(spi_b200_model* model,
                       const float* params, int P, const int* param_ids, unsigned flags,
                       float* state, const float* torques, int N, int n_steps,
                       float* out_foot_force, void* cuda_stream);
+
+/* Rigid-body state tensor of the 19 Isaac Gym bodies (spigym/simulator/isaacgym/isaacgym.py:541-577
+ * `_rigid_body_pos / _rot / _vel / _ang_vel`; body order of spigym/config/robot/go2/go2.yaml:44: base, FL hip / thigh /
+ * calf / foot, FR ..., Head_upper, Head_lower, RL ..., RR ...) by forward kinematics of the engine state.
+ *   state [N,37] -> out [N,19,13] = link-frame origin pos[3], link-frame quat_xyzw[4], linear velocity OF THE LINK
+ *   ORIGIN [3], angular velocity [3], all in the world frame.                                                       */
+int spi_b200_body_states(spi_b200_model* model, const float* state, int N, float* out, void* cuda_stream);
 
 /* One CONTROL step of N independent envs, each with its own parameter row (the closed-loop / active-exploration path:
  * LeggedRobotBase.step without the observation / reward bookkeeping, legged_robot_base.py:169-209, with the torque law

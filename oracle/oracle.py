@@ -224,3 +224,52 @@ def quat_rotate_inverse(q_xyzw, v):
     b = np.cross(u, v) * w * 2.0
     c = u * (u * v).sum(axis=1, keepdims=True) * 2.0
     return a - b + c
+
+
+# ---- rigid-body state tensor (forward kinematics) -----------------------------------------------------------------
+def _quat_mul(a, b):
+    ax, ay, az, aw = np.moveaxis(a, -1, 0); bx, by, bz, bw = np.moveaxis(b, -1, 0)
+    return np.stack([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz], axis=-1)
+
+
+def _quat_rot(q, v):
+    t = 2.0 * np.cross(q[..., :3], v)
+    return v + q[..., 3:4] * t + np.cross(q[..., :3], t)
+
+
+def body_states(blob, state):
+    """state[N,37] -> [N,19,13] (pos, quat xyzw, linear velocity of the link origin, angular velocity; world frame) of
+    the 19 Isaac Gym bodies in the order of spigym/config/robot/go2/go2.yaml:44 — what
+    spigym/simulator/isaacgym/isaacgym.py:541-577 exposes as `_rigid_body_pos/_rot/_vel/_ang_vel`.  fp64 numpy;
+    joint origins / axes from the model blob (go2.urdf: hip about x, thigh and calf about y, feet and heads fixed)."""
+    b = np.asarray(blob, np.float64)
+    s = np.asarray(state, np.float64)
+    N = s.shape[0]
+    out = np.zeros((N, 19, 13))
+    LEG_BODIES, STRIDE, FOOT_OFFSET, FOOT_SPHERE, LUMPS = 46, 14, 214, 12, 26     # include/spi_b200.h
+
+    def child(pp, pq, pv, pw, r, axis, ang=None, rate=None):
+        rw = _quat_rot(pq, np.broadcast_to(r, pp.shape))
+        cp, cv = pp + rw, pv + np.cross(pw, rw)
+        if axis < 0:
+            return cp, pq, cv, pw
+        jq = np.zeros((N, 4)); jq[:, axis] = np.sin(0.5 * ang); jq[:, 3] = np.cos(0.5 * ang)
+        cq = _quat_mul(pq, jq)
+        ax = np.zeros((N, 3)); ax[:, axis] = rate
+        return cp, cq, cv, pw + _quat_rot(cq, ax)
+
+    base = (s[:, 0:3], s[:, 3:7], s[:, 7:10], s[:, 10:13])
+    out[:, 0] = np.concatenate(base, axis=1)
+    for h in range(2):
+        out[:, 9 + h] = np.concatenate(child(*base, b[LUMPS + 10 * h + 1:LUMPS + 10 * h + 4], -1), axis=1)
+    for leg in range(4):
+        first = 1 + 4 * leg if leg < 2 else 11 + 4 * (leg - 2)
+        cur = base
+        for j in range(3):
+            r = b[LEG_BODIES + STRIDE * (3 * leg + j) + 10:LEG_BODIES + STRIDE * (3 * leg + j) + 13]
+            cur = child(*cur, r, 0 if j == 0 else 1, s[:, 13 + 3 * leg + j], s[:, 25 + 3 * leg + j])
+            out[:, first + j] = np.concatenate(cur, axis=1)
+        foot = b[FOOT_OFFSET + 3 * leg:FOOT_OFFSET + 3 * leg + 3] - b[FOOT_SPHERE:FOOT_SPHERE + 3]
+        out[:, first + 3] = np.concatenate(child(*cur, foot, -1), axis=1)
+    return out

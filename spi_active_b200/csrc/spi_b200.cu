@@ -228,6 +228,81 @@ __global__ void __launch_bounds__(kThreads) sim_step_kernel(const StepArgs A) {
   }
 }
 
+// ---- rigid-body state tensor by forward kinematics: one thread per (env, chain), chain 0..3 = legs, 4 = base + heads ------
+struct FkModel {
+  float r[4][3][3];      // joint origins hip / thigh / calf in the parent frame
+  float foot[4][3];      // foot link origin in the calf frame
+  float head[2][3];      // Head_upper / Head_lower link origins in the base frame
+};
+SPI_DEV void quat_mul(const float* a, const float* b, float* o) {   // xyzw
+  o[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+  o[1] = a[3] * b[1] - a[0] * b[2] + a[1] * b[3] + a[2] * b[0];
+  o[2] = a[3] * b[2] + a[0] * b[1] - a[1] * b[0] + a[2] * b[3];
+  o[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+}
+SPI_DEV void quat_rot(const float* q, const float* v, float* o) {   // R(q) v
+  const float tx = 2.f * (q[1] * v[2] - q[2] * v[1]), ty = 2.f * (q[2] * v[0] - q[0] * v[2]), tz = 2.f * (q[0] * v[1] - q[1] * v[0]);
+  o[0] = v[0] + q[3] * tx + (q[1] * tz - q[2] * ty);
+  o[1] = v[1] + q[3] * ty + (q[2] * tx - q[0] * tz);
+  o[2] = v[2] + q[3] * tz + (q[0] * ty - q[1] * tx);
+}
+SPI_DEV void fk_store(float* o, const float* p, const float* q, const float* v, const float* w) {
+  o[0] = p[0]; o[1] = p[1]; o[2] = p[2]; o[3] = q[0]; o[4] = q[1]; o[5] = q[2]; o[6] = q[3];
+  o[7] = v[0]; o[8] = v[1]; o[9] = v[2]; o[10] = w[0]; o[11] = w[1]; o[12] = w[2];
+}
+// child link across a joint: origin offset r (parent frame), rotation by angle about `axis` (0 = x, 1 = y, -1 = fixed)
+SPI_DEV void fk_child(const float* pp, const float* pq, const float* pv, const float* pw, const float* r, int axis,
+                      float ang, float rate, float* cp, float* cq, float* cv, float* cw) {
+  float rw[3];
+  quat_rot(pq, r, rw);
+  cp[0] = pp[0] + rw[0]; cp[1] = pp[1] + rw[1]; cp[2] = pp[2] + rw[2];
+  cv[0] = pv[0] + (pw[1] * rw[2] - pw[2] * rw[1]);
+  cv[1] = pv[1] + (pw[2] * rw[0] - pw[0] * rw[2]);
+  cv[2] = pv[2] + (pw[0] * rw[1] - pw[1] * rw[0]);
+  if (axis < 0) {
+    cq[0] = pq[0]; cq[1] = pq[1]; cq[2] = pq[2]; cq[3] = pq[3];
+    cw[0] = pw[0]; cw[1] = pw[1]; cw[2] = pw[2];
+    return;
+  }
+  float sh, ch;
+  sincosf(0.5f * ang, &sh, &ch);
+  const float jq[4] = {axis == 0 ? sh : 0.f, axis == 1 ? sh : 0.f, 0.f, ch};
+  quat_mul(pq, jq, cq);
+  const float ax[3] = {axis == 0 ? rate : 0.f, axis == 1 ? rate : 0.f, 0.f};
+  float aw[3];
+  quat_rot(cq, ax, aw);
+  cw[0] = pw[0] + aw[0]; cw[1] = pw[1] + aw[1]; cw[2] = pw[2] + aw[2];
+}
+__global__ void body_states_kernel(const FkModel F, const float* state, int N, float* out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * 5) return;
+  const int e = idx / 5, chain = idx - 5 * e;
+  const float* s = state + (size_t)e * SPI_STATE_DIM;
+  float* o = out + (size_t)e * 19 * 13;
+  const float bp[3] = {s[0], s[1], s[2]}, bq[4] = {s[3], s[4], s[5], s[6]}, bv[3] = {s[7], s[8], s[9]},
+              bw[3] = {s[10], s[11], s[12]};
+  if (chain == 4) {
+    fk_store(o, bp, bq, bv, bw);
+    for (int h = 0; h < 2; h++) {
+      float p[3], q[4], v[3], w[3];
+      fk_child(bp, bq, bv, bw, F.head[h], -1, 0.f, 0.f, p, q, v, w);
+      fk_store(o + (9 + h) * 13, p, q, v, w);
+    }
+    return;
+  }
+  const int first = (chain < 2) ? 1 + 4 * chain : 11 + 4 * (chain - 2);   // FL 1, FR 5, RL 11, RR 15
+  float pp[3] = {bp[0], bp[1], bp[2]}, pq[4] = {bq[0], bq[1], bq[2], bq[3]}, pv[3] = {bv[0], bv[1], bv[2]},
+        pw[3] = {bw[0], bw[1], bw[2]};
+  for (int j = 0; j < 4; j++) {
+    float p[3], q[4], v[3], w[3];
+    if (j < 3) fk_child(pp, pq, pv, pw, F.r[chain][j], j == 0 ? 0 : 1, s[13 + 3 * chain + j], s[25 + 3 * chain + j], p, q, v, w);
+    else fk_child(pp, pq, pv, pw, F.foot[chain], -1, 0.f, 0.f, p, q, v, w);
+    fk_store(o + (first + j) * 13, p, q, v, w);
+    for (int k = 0; k < 3; k++) { pp[k] = p[k]; pv[k] = v[k]; pw[k] = w[k]; }
+    for (int k = 0; k < 4; k++) pq[k] = q[k];
+  }
+}
+
 // torque law on its own, one thread per (row, joint)
 __global__ void torque_kernel(const DeviceModel* Mp, const float* actions, const float* q, const float* qd,
                               const float* gains, const float* motor_params, int N, int motor_model, unsigned flags,
@@ -406,6 +481,7 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(int iters, float seed, f
 // host side: model handle, error handling, C-ABI
 // ================================================================================================
 struct spi_b200_model {
+  FkModel fk;
   DeviceModel host_model;
   DeviceModel* d_model = nullptr;
   ws::ModelK ws_model;      // constants of the warp-specialised fast path (passed as a kernel parameter)
@@ -669,6 +745,13 @@ int spi_b200_model_create(const float* model_blob, int n_floats, spi_b200_model*
   if (int rc = blob_to_model(model_blob, n_floats, &m->host_model)) { delete m; return rc; }
   std::memset(&m->ws_model, 0, sizeof(m->ws_model));
   m->ws_ok = ws::model_from_blob(model_blob, &m->ws_model) == 0;
+  for (int leg = 0; leg < 4; leg++) {
+    for (int j = 0; j < 3; j++)
+      for (int k = 0; k < 3; k++) m->fk.r[leg][j][k] = model_blob[SPI_BLOB_LEG_BODIES + SPI_LEG_BODY_STRIDE * (3 * leg + j) + 10 + k];
+    for (int k = 0; k < 3; k++) m->fk.foot[leg][k] = model_blob[SPI_BLOB_FOOT_OFFSET + 3 * leg + k] - model_blob[SPI_BLOB_FOOT_SPHERE + k];
+  }
+  for (int h = 0; h < 2; h++)   // the head links' inertial frames coincide with their link frames in the URDF
+    for (int k = 0; k < 3; k++) m->fk.head[h][k] = model_blob[SPI_BLOB_BASE_LUMPS + 10 * h + 1 + k];
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -822,6 +905,14 @@ int spi_b200_sim_step(spi_b200_model* m, const float* params, int P, const int* 
   const int n_cta = (N + kRolloutsPerCta - 1) / kRolloutsPerCta;
   sim_step_kernel<<<n_cta, kThreads, 0, (cudaStream_t)cuda_stream>>>(A);
   return check_launch("sim_step_kernel");
+}
+
+int spi_b200_body_states(spi_b200_model* m, const float* state, int N, float* out, void* cuda_stream) {
+  if (!m) return fail(-1, "model handle is NULL");
+  if (N <= 0 || !state || !out) return fail(-3, "bad arguments");
+  const int n = N * 5;
+  body_states_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(m->fk, state, N, out);
+  return check_launch("body_states_kernel");
 }
 
 int spi_b200_compute_torques(spi_b200_model* m, const float* actions, const float* q, const float* qd,

@@ -253,6 +253,18 @@ class RolloutEngine:
         _lib.check(rc, "spi_b200_sim_step")
         return state
 
+    def body_states(self, state: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """state[N,37] -> [N,19,13] rigid-body states of the 19 Isaac Gym bodies (forward kinematics, world frame)."""
+        assert state.is_cuda and state.dtype == torch.float32 and state.is_contiguous()
+        N = state.shape[0]
+        if out is None:
+            out = torch.empty((N, 19, 13), device=self.device, dtype=torch.float32)
+        assert out.is_contiguous() and tuple(out.shape) == (N, 19, 13)
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_body_states(self._handle, _ptr(state), N, _ptr(out), self._stream())
+        _lib.check(rc, "spi_b200_body_states")
+        return out
+
     def env_step(self, state: torch.Tensor, actions: torch.Tensor, params=None, param_names=(), gains=None,
                  decimation: Optional[int] = None, motor_model="none", flags: int = 0,
                  zero_action_mask: Optional[torch.Tensor] = None) -> torch.Tensor:

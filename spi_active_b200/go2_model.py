@@ -26,7 +26,7 @@ import numpy as np
 # ---- blob offsets (mirror of include/spi_b200.h; tests parse the header and compare) -----------------
 BLOB = dict(
     MAGIC=0, DT=1, GRAVITY_Z=2, ACTION_SCALE=3, ACTION_CLIP=4, CONTACT_KN=5, CONTACT_CN=6,
-    CONTACT_MU=7, CONTACT_DT=8, FOOT_RADIUS=9, NSUB=10, CONTACT_VEPS=11, BASE_INERTIAL=16,
+    CONTACT_MU=7, CONTACT_DT=8, FOOT_RADIUS=9, NSUB=10, CONTACT_VEPS=11, FOOT_SPHERE=12, BASE_INERTIAL=16,
     BASE_LUMPS=26, LEG_BODIES=46, FOOT_OFFSET=214, Q_DEFAULT=226, TORQUE_LIMIT=238, KP=250, KD=262,
     Q_LOWER=274, Q_UPPER=286, QD_LIMIT=298, SIZE=312,
 )
@@ -296,6 +296,7 @@ def build_model_blob(model: Go2Model | None = None) -> np.ndarray:
     b[BLOB["FOOT_RADIUS"]] = m.foot_radius
     b[BLOB["NSUB"]] = float(int(m.contact.nsub))
     b[BLOB["CONTACT_VEPS"]] = m.contact.veps
+    b[BLOB["FOOT_SPHERE"]:BLOB["FOOT_SPHERE"] + 3] = m.foot_sphere_offset     # foot link frame = FOOT_OFFSET - this
     b[BLOB["BASE_INERTIAL"]:BLOB["BASE_INERTIAL"] + 10] = m.base.as_row()
     for k, (child, pos) in enumerate(m.base_lumps):
         o = BLOB["BASE_LUMPS"] + 10 * k

@@ -264,7 +264,10 @@ class B200Sim(BaseSimulator):
         self._refresh_dof()
         self.contact_forces.zero_()
         self.contact_forces[:, self._feet_idx, :] = self._foot_force
-        self._rigid_body_state[:, 0, :] = self._state[:, 0:13]     # base link; other links: see DESIGN.md §7
+        if hasattr(self._backend, "body_states"):                  # all 19 links by forward kinematics (CUDA)
+            self._backend.body_states(self._state, out=self._rigid_body_state)
+        else:
+            self._rigid_body_state[:, 0, :] = self._state[:, 0:13]
 
     def _refresh_dof(self):
         self.dof_pos.copy_(self._state[:, 13:25])

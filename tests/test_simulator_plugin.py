@@ -31,6 +31,14 @@ class OracleBackend:
             foot_force.copy_(torch.from_numpy(ff.astype(np.float32)))
         return state
 
+    def body_states(self, state, out=None):
+        from oracle import oracle as orc
+        bs = torch.from_numpy(orc.body_states(self.blob, state.numpy()).astype(np.float32))
+        if out is None:
+            return bs
+        out.copy_(bs)
+        return out
+
     def close(self):
         pass
 
@@ -151,3 +159,71 @@ def test_stepwise_replay_on_gpu_matches_fused_operator(engine, nominal_model):
     _, fused = engine.evaluate_candidates(torch.tensor([[8.5]]), ["mass"], segs, return_per_seg=True)
     np.testing.assert_allclose(per, fused[0].cpu().numpy(), atol=2e-5)
     assert float(sim.contact_forces[:, [4, 8, 14, 18], 2].abs().sum()) > 0
+
+
+# ---- rigid-body state tensor (forward kinematics) ------------------------------------------------
+def _random_states(n, seed, model):
+    rng = np.random.default_rng(seed)
+    s = np.zeros((n, 37))
+    s[:, 0:3] = rng.uniform(-1, 1, (n, 3)); s[:, 2] = rng.uniform(0.2, 0.5, n)
+    q = rng.standard_normal((n, 4)); s[:, 3:7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    s[:, 7:13] = rng.uniform(-1, 1, (n, 6))
+    s[:, 13:25] = np.asarray(model.q_default) + rng.uniform(-0.4, 0.4, (n, 12))
+    s[:, 25:37] = rng.uniform(-3, 3, (n, 12))
+    return s
+
+
+def test_body_states_oracle_kinematics(oracle_lib, blob, nominal_model):
+    """The FK restatement against independent facts: URDF geometry at the zero pose, the foot height the contact model
+    uses, and velocities as the time derivative of positions / orientations along a free-flight trajectory."""
+    from scipy.spatial.transform import Rotation
+    m = nominal_model
+    z = np.zeros((1, 37)); z[0, 2] = 0.4; z[0, 6] = 1.0
+    bs = oracle_lib.body_states(blob, z)[0]
+    names = gm.BODY_NAMES
+    np.testing.assert_allclose(bs[names.index("FL_hip"), :3], [0.1934, 0.0465, 0.4], atol=1e-7)
+    np.testing.assert_allclose(bs[names.index("RR_thigh"), :3], [-0.1934, -0.0465 - 0.0955, 0.4], atol=1e-7)
+    np.testing.assert_allclose(bs[names.index("FR_foot"), :3], [0.1934, -0.0465 - 0.0955, 0.4 - 0.426], atol=1e-7)
+    np.testing.assert_allclose(bs[names.index("Head_lower"), :3], [0.293, 0.0, 0.34], atol=1e-7)
+    assert np.allclose(bs[:, 3:7], [0, 0, 0, 1]) and np.allclose(bs[:, 7:13], 0)
+    # velocities = d/dt of the kinematics: integrate the state itself (constant twist / joint rates) over a small dt
+    s0 = _random_states(6, 1, m)
+    dt = 1e-6
+    s1 = s0.copy()
+    s1[:, 0:3] += dt * s0[:, 7:10]
+    rot = Rotation.from_rotvec(dt * s0[:, 10:13]) * Rotation.from_quat(s0[:, 3:7])     # world-frame angular velocity
+    s1[:, 3:7] = rot.as_quat()
+    s1[:, 13:25] += dt * s0[:, 25:37]
+    b0, b1 = oracle_lib.body_states(blob, s0), oracle_lib.body_states(blob, s1)
+    np.testing.assert_allclose((b1[..., 0:3] - b0[..., 0:3]) / dt, b0[..., 7:10], atol=2e-5)
+    dR = Rotation.from_quat(b1[..., 3:7].reshape(-1, 4)) * Rotation.from_quat(b0[..., 3:7].reshape(-1, 4)).inv()
+    np.testing.assert_allclose(dR.as_rotvec().reshape(6, 19, 3) / dt, b0[..., 10:13], atol=2e-5)
+    # the foot sphere the contact model uses sits at foot origin + R (-0.002, 0, 0)
+    f = names.index("RL_foot")
+    c = b0[:, f, :3] + Rotation.from_quat(b0[:, f, 3:7]).apply(np.asarray(m.foot_sphere_offset))
+    calf = names.index("RL_calf")
+    c2 = b0[:, calf, :3] + Rotation.from_quat(b0[:, calf, 3:7]).apply(blob[214 + 6:214 + 9].astype(np.float64))
+    np.testing.assert_allclose(c, c2, atol=1e-7)
+
+
+def test_plugin_exposes_all_rigid_bodies(blob, nominal_model):
+    sim, _ = _make_sim(3, "cpu", backend=OracleBackend(blob))
+    sim.refresh_sim_tensors()
+    assert sim._rigid_body_pos.shape == (3, 19, 3) and sim._rigid_body_rot.shape == (3, 19, 4)
+    feet = [sim.find_rigid_body_indice(f"{leg}_foot") for leg in gm.LEGS]
+    assert feet == [4, 8, 14, 18]
+    z = sim._rigid_body_pos[:, feet, 2]
+    assert float(z.min()) > 0.0 and float(z.max()) < 0.34          # feet hang below the base at the default pose
+    assert torch.allclose(sim._rigid_body_pos[:, 0], sim.robot_root_states[:, 0:3])
+
+
+@pytest.mark.gpu
+def test_body_states_kernel_matches_oracle(engine, oracle_lib, blob, nominal_model):
+    s = _random_states(257, 2, nominal_model)
+    out = engine.body_states(torch.from_numpy(s.astype(np.float32)).to(engine.device)).cpu().numpy()
+    ref = oracle_lib.body_states(blob, s.astype(np.float32))
+    np.testing.assert_allclose(out[..., 0:3], ref[..., 0:3], atol=2e-6)
+    sign = np.sign((out[..., 3:7] * ref[..., 3:7]).sum(-1, keepdims=True))
+    assert (sign > 0).all()                                         # same hemisphere: composed, not re-extracted
+    np.testing.assert_allclose(out[..., 3:7], ref[..., 3:7], atol=2e-6)
+    np.testing.assert_allclose(out[..., 7:13], ref[..., 7:13], atol=2e-5)
