@@ -247,10 +247,12 @@ int spi_b200_active_post_step(spi_b200_model* model, float* state, const float* 
  * with fp32-grade accuracy (tcgen05.mma kind::tf32, 3xTF32 split).  Constraints: 3 hidden layers, widths h1, h2
  * multiples of 128, h3 = 128, <= 16 outputs (the reference's 900-512-256-128-12 actor qualifies).
  *   dims [5] = in, h1, h2, h3, out; weights[l] [dims[l+1], dims[l]] row-major (torch Linear layout), biases[l]: HOST.
- * The input is passed PRE-SPLIT (x = x_hi + x_lo, x_hi rounded to tf32) in padded [rows, stride] buffers whose layout
- * spi_b200_policy_input_layout reports (rows = M rounded up to 128, stride = in rounded up to 32; padding must be
- * zero-initialised by the owner).  spi_b200_active_post_step writes the observation in that form directly;
- * spi_b200_policy_split_input converts a plain [M, in] matrix.  out [M, out] fp32.                                 */
+ * The input is passed PRE-SPLIT (x = x_hi + x_lo, x_hi rounded to tf32) in two buffers of rows * stride floats
+ * (spi_b200_policy_input_layout: rows = M rounded up to 128, stride = in rounded up to 32; zero-initialised by the owner)
+ * whose element order is OPAQUE: 128 x 32 tiles stored as the swizzled shared-memory image the tensor core reads, so that a
+ * pipeline stage is four contiguous 16 KB TMA bulk copies (csrc/tiled_layout.cuh).  spi_b200_active_post_step writes the
+ * observation in that form directly; spi_b200_policy_split_input / _unsplit_input convert from / to a plain row-major
+ * [M, in] matrix.  out [M, out] fp32.                                                                              */
 typedef struct spi_b200_policy spi_b200_policy;
 int spi_b200_policy_create(const int* dims, const float* const* weights, const float* const* biases,
                            spi_b200_policy** out_policy);
@@ -258,6 +260,8 @@ int spi_b200_policy_destroy(spi_b200_policy* policy);
 int spi_b200_policy_input_layout(spi_b200_policy* policy, int M, int* out_rows, int* out_stride);
 int spi_b200_policy_split_input(spi_b200_policy* policy, const float* x, int M, float* x_hi, float* x_lo,
                                 void* cuda_stream);
+int spi_b200_policy_unsplit_input(spi_b200_policy* policy, const float* x_hi, const float* x_lo, int M, float* x,
+                                  void* cuda_stream);
 int spi_b200_policy_forward(spi_b200_policy* policy, const float* x_hi, const float* x_lo, int M, float* out,
                             void* cuda_stream);
 

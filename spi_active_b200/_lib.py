@@ -15,7 +15,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("SPI_B200_LIB", _PKG / "libspi_b200.so"))  # override: kernel experiments only
 SOURCES = [_PKG / "csrc" / "spi_b200.cu"]
 HEADERS = [_PKG / "csrc" / "aba_leg.cuh", _PKG / "csrc" / "go2_ws.cuh", _PKG / "csrc" / "rollout_ws.cuh",
-           _PKG / "csrc" / "fim_tc.cuh", _PKG / "csrc" / "active_step.cuh", _PKG / "csrc" / "mlp_tc.cuh",
+           _PKG / "csrc" / "fim_tc.cuh", _PKG / "csrc" / "active_step.cuh", _PKG / "csrc" / "mlp_tc.cuh", _PKG / "csrc" / "tiled_layout.cuh",
            _PKG.parent / "include" / "spi_b200.h"]
 # SPI_WS_FAST_SINCOS: joint sin/cos through MUFU after a 2-constant reduction to [-pi, pi]; measured deviation from
 # the fp64 oracle stays at the fp32 noise floor of the oracle itself (profiles/README.md, tools/dev_accuracy.py)
@@ -85,6 +85,7 @@ SIGNATURES = {
     "spi_b200_policy_destroy": (C.c_int, [_V]),
     "spi_b200_policy_input_layout": (C.c_int, [_V, C.c_int, _I, _I]),
     "spi_b200_policy_split_input": (C.c_int, [_V, _V, C.c_int, _V, _V, _V]),
+    "spi_b200_policy_unsplit_input": (C.c_int, [_V, _V, _V, C.c_int, _V, _V]),
     "spi_b200_policy_forward": (C.c_int, [_V, _V, _V, C.c_int, _V, _V]),
     "spi_b200_fim_contract": (C.c_int, [_V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _V, _V, _V]),
     "spi_b200_cem_refit": (C.c_int, [_V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_float, _V, _V, _V, _V, _V]),

@@ -21,6 +21,8 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include "tiled_layout.cuh"
+
 namespace activestep {
 
 constexpr int kFrame = 60, kHistLen = 14, kObs = kFrame * (1 + kHistLen);   // 900
@@ -38,7 +40,7 @@ struct Args {
   float* clock;                    // [N,4] in/out
   float* history;                  // [N,14,60] in/out, newest first
   float* obs;                      // [N,900] out
-  float* obs_hi; float* obs_lo;    // [rows, obs_stride] or null: the same observation pre-split for spi_b200_policy_forward
+  float* obs_hi; float* obs_lo;    // [rows, obs_stride] (tiled_layout.cuh) or null: pre-split input of spi_b200_policy_forward
   int obs_stride;
   const int* hist_index;           // [840] gather index of short_history into the flattened [14*60] ring
   float* fim_hist;                 // [K,M,P1,25] or null
@@ -164,8 +166,9 @@ __global__ void __launch_bounds__(32 * kMaxGroup) active_post_step_kernel(const 
       uint32_t hb;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(o));
       const float h = __uint_as_float(hb);
-      A.obs_hi[(size_t)env * A.obs_stride + i] = h;
-      A.obs_lo[(size_t)env * A.obs_stride + i] = o - h;
+      const size_t at = tiled::offset(env, i, A.obs_stride);
+      A.obs_hi[at] = h;
+      A.obs_lo[at] = o - h;
     }
   }
   for (int i = lane; i < kHistLen * kFrame; i += 32) hrow[i] = (i < kFrame) ? sm.frame(w)[i] : sm.hist(w)[i - kFrame];

@@ -994,25 +994,14 @@ static void policy_free(spi_b200_policy* p) {
   delete p;
 }
 
-// tile configuration of the policy GEMMs: SPI_B200_MLP_CFG = 0 (BK 32, 3 stages, 1 CTA / SM) or 1 (BK 16, 3 stages,
-// 96 KB -> 2 CTAs / SM); experiments only
-static int mlp_cfg() {
-  static const int v = [] { const char* e = getenv("SPI_B200_MLP_CFG"); return e ? atoi(e) : 0; }();
-  return v;
-}
 static cudaError_t mlp_set_attributes() {
-  cudaError_t e = cudaFuncSetAttribute(mlptc::mlp_layer_kernel<0, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlptc::Cfg<32, 3>::kSmemBytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlptc::mlp_layer_kernel<1, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlptc::Cfg<32, 3>::kSmemBytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlptc::mlp_layer_kernel<0, 16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlptc::Cfg<16, 3>::kSmemBytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlptc::mlp_layer_kernel<1, 16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlptc::Cfg<16, 3>::kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(mlptc::mlp_layer_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlptc::kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlptc::mlp_layer_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlptc::kSmemBytes);
   return e;
 }
 static void mlp_launch(int mode, const mlptc::LayerArgs& L, dim3 grid, cudaStream_t st) {
-  const int cfg = mlp_cfg();
-  if (mode == 0 && cfg == 1) mlptc::mlp_layer_kernel<0, 16, 3><<<grid, mlptc::kThreads, mlptc::Cfg<16, 3>::kSmemBytes, st>>>(L);
-  else if (mode == 0) mlptc::mlp_layer_kernel<0, 32, 3><<<grid, mlptc::kThreads, mlptc::Cfg<32, 3>::kSmemBytes, st>>>(L);
-  else if (cfg == 1) mlptc::mlp_layer_kernel<1, 16, 3><<<grid, mlptc::kThreads, mlptc::Cfg<16, 3>::kSmemBytes, st>>>(L);
-  else mlptc::mlp_layer_kernel<1, 32, 3><<<grid, mlptc::kThreads, mlptc::Cfg<32, 3>::kSmemBytes, st>>>(L);
+  if (mode == 0) mlptc::mlp_layer_kernel<0><<<grid, mlptc::kThreads, mlptc::kSmemBytes, st>>>(L);
+  else mlptc::mlp_layer_kernel<1><<<grid, mlptc::kThreads, mlptc::kSmemBytes, st>>>(L);
 }
 
 static float tf32_rna_host(float x) {   // round to nearest, ties away: the value cvt.rna.tf32.f32 produces
@@ -1044,7 +1033,8 @@ int spi_b200_policy_create(const int* dims, const float* const* weights, const f
       for (int k = 0; k < K; k++) {
         const float w = weights[l][(size_t)n * K + k];
         const float h = tf32_rna_host(w);
-        hi[(size_t)n * Kp + k] = h; lo[(size_t)n * Kp + k] = w - h;
+        const size_t o = tiled::offset(n, k, Kp);
+        hi[o] = h; lo[o] = w - h;
       }
     const size_t bytes = hi.size() * sizeof(float);
     e = cudaMalloc((void**)&p->w_hi[l], bytes);
@@ -1087,6 +1077,14 @@ int spi_b200_policy_split_input(spi_b200_policy* p, const float* x, int M, float
   const size_t n = (size_t)M * p->dims[0];
   mlptc::split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(x, M, p->dims[0], x_hi, x_lo, p->Kp);
   return check_launch("split_kernel");
+}
+
+int spi_b200_policy_unsplit_input(spi_b200_policy* p, const float* x_hi, const float* x_lo, int M, float* x, void* cuda_stream) {
+  if (!p) return fail(-1, "policy handle is NULL");
+  if (M <= 0 || !x || !x_hi || !x_lo) return fail(-3, "bad arguments");
+  const size_t n = (size_t)M * p->dims[0];
+  mlptc::unsplit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(x_hi, x_lo, M, p->dims[0], p->Kp, x);
+  return check_launch("unsplit_kernel");
 }
 
 int spi_b200_policy_forward(spi_b200_policy* p, const float* x_hi, const float* x_lo, int M, float* out,

@@ -76,7 +76,8 @@ class TensorCorePolicy:
             pass
 
     def input_layout(self, M: int):
-        """-> (rows, stride) of the padded, pre-split input buffers for M envs."""
+        """-> (rows, stride): the pre-split input buffers for M envs hold rows * stride floats each, in an opaque tiled
+        order (csrc/tiled_layout.cuh) — write them with split_input or spi_b200_active_post_step only."""
         rows, stride = C.c_int(), C.c_int()
         _lib.check(self.lib.spi_b200_policy_input_layout(self._handle, int(M), C.byref(rows), C.byref(stride)),
                    "spi_b200_policy_input_layout")
@@ -96,6 +97,14 @@ class TensorCorePolicy:
             rc = self.lib.spi_b200_policy_split_input(self._handle, _ptr(x), int(x.shape[0]), _ptr(x_hi), _ptr(x_lo),
                                                       self._stream())
         _lib.check(rc, "spi_b200_policy_split_input")
+
+    def unsplit_input(self, x_hi: torch.Tensor, x_lo: torch.Tensor, M: int) -> torch.Tensor:
+        """The plain [M, in] matrix a pair of split buffers holds (x_hi + x_lo, exact)."""
+        x = torch.empty((M, self.dims[0]), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_policy_unsplit_input(self._handle, _ptr(x_hi), _ptr(x_lo), int(M), _ptr(x), self._stream())
+        _lib.check(rc, "spi_b200_policy_unsplit_input")
+        return x
 
     def forward_split(self, x_hi: torch.Tensor, x_lo: torch.Tensor, M: int, out: Optional[torch.Tensor] = None):
         rows, stride = self.input_layout(M)

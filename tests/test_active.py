@@ -324,8 +324,10 @@ def test_fused_post_step_kernel_matches_torch_statement(engine, policy_impl):
         b.step_idx += 1; b._policy_step()
         compare(f"step {k}")
         if b.tc_policy is not None:     # hi + lo is the observation, exactly; the padding stays zero
-            np.testing.assert_array_equal((b.obs_hi + b.obs_lo)[:b.num_envs, :900].cpu().numpy(), b.obs.cpu().numpy())
-            assert float(b.obs_hi[:, 900:].abs().max()) == 0.0 and float(b.obs_hi[b.num_envs:].abs().max()) == 0.0
+            np.testing.assert_array_equal(b.tc_policy.unsplit_input(b.obs_hi, b.obs_lo, b.num_envs).cpu().numpy(),
+                                          b.obs.cpu().numpy())
+            n_written = b.num_envs * 900                                          # the padding stays zero
+            assert int((b.obs_hi != 0).sum()) <= n_written and int((b.obs_lo != 0).sum()) <= n_written
         # one-step check: restart the fused copy from the torch path's exact state (the closed loop amplifies the
         # ~1e-7 rounding differences of the observation arithmetic by an order of magnitude per few steps)
         for name in ("state", "obs", "history", "done", "dead_steps"):
