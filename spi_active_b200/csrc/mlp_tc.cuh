@@ -27,17 +27,22 @@
 namespace mlptc {
 
 constexpr int kTile = 128;                   // UMMA M = N
-constexpr int kEpilogue = 128;               // warps 0-3: accumulator promotion + epilogue (thread = row)
-constexpr int kThreads = kEpilogue + 64;     // warp 4: MMA issuer, warp 5: bulk-copy producer (one elected lane each)
+constexpr int kEpilogue = 256;               // warps 0-7: accumulator promotion + epilogue; warp w owns rows 32 (w & 3) .. + 31 (its
+                                             // TMEM lane quadrant) and columns 64 (w >> 2) .. + 63
+constexpr int kHalfCols = 64;
+constexpr int kThreads = kEpilogue + 64;     // warp 8: MMA issuer, warp 9: bulk-copy producer (one elected lane each)
 constexpr int kAccCols = 128;                // one fp32 accumulator tile
 constexpr int kTmemCols = 2 * kAccCols;      // two accumulators, used alternately by groups of k-blocks
-constexpr int kMaxOut = 16;
 constexpr int kKAlign = 32;                  // the padded K of every operand is a multiple of this
 constexpr int kBK = 32;                      // fp32 elements of K per stage = one 128-byte swizzle atom per row
 constexpr int kStages = 3;
 constexpr int kOperandBytes = kTile * kBK * 4;               // 16 KB = one tile of tiled_layout.cuh
 constexpr int kStageBytes = 4 * kOperandBytes;               // A_hi, A_lo, W_hi, W_lo
-constexpr int kSmemBytes = kStages * kStageBytes + 256;
+constexpr int kMaxOut = 16;
+// shared-memory tail behind the stages: barriers + TMEM slot (256 B) | bias of this n-tile (512 B) | output layer: weights
+// [kMaxOut][128] (8 KB) + bias (64 B)
+constexpr int kTailBias = 256, kTailWout = kTailBias + 512, kTailBout = kTailWout + kMaxOut * kTile * 4;
+constexpr int kSmemBytes = kStages * kStageBytes + kTailBout + 64;
 // k-blocks per accumulator group: the tensor core's accumulation truncates (a ~3e-8 relative bias per MMA), so an
 // accumulator only ever holds 48 MMAs before it is added to the fp32 running sums in registers
 constexpr int kGroup = 4;
@@ -70,7 +75,53 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
-__device__ __forceinline__ float elu(float x) { return x > 0.f ? x : expm1f(x); }
+// the same copy delivered to the same CTA-relative offset (data and mbarrier) of every CTA in cta_mask
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+      : "memory");
+}
+// tcgen05.commit whose mbarrier arrive is delivered to the same barrier of every CTA in cta_mask
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctaid_x() { uint32_t v; asm volatile("mov.u32 %0, %%cluster_ctaid.x;" : "=r"(v)); return v; }
+__device__ __forceinline__ uint32_t cluster_ctaid_y() { uint32_t v; asm volatile("mov.u32 %0, %%cluster_ctaid.y;" : "=r"(v)); return v; }
+
+// TMA 1-D bulk copy shared -> global (bulk-group completion)
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpilogue) : "memory"); }
+
+// ELU without branches (the library expm1f compiles to divergent regions that serialise the 64 independent elements of an
+// epilogue thread: measured 6.7 us of a 9 us epilogue).  x <= 0:  expm1(x) = Taylor degree 8 on (-0.35, 0] (truncation
+// 2e-10), 2^(x log2 e) - 1 below (MUFU.EX2: 2 ulp of a value <= 0.7, i.e. <= 1.2e-7 absolute on a result of magnitude >= 0.3)
+__device__ __forceinline__ float elu(float x) {
+  float p = 2.4801587e-5f;                 // 1/8!
+  p = fmaf(p, x, 1.9841270e-4f);           // 1/7!
+  p = fmaf(p, x, 1.3888889e-3f);
+  p = fmaf(p, x, 8.3333333e-3f);
+  p = fmaf(p, x, 4.1666667e-2f);
+  p = fmaf(p, x, 1.6666667e-1f);
+  p = fmaf(p, x, 0.5f);
+  p = fmaf(p * x, x, x);                   // x + x^2 (1/2 + x (1/6 + ...))
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+  const float neg = (x > -0.35f) ? p : e - 1.0f;
+  return (x > 0.f) ? x : neg;
+}
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -85,6 +136,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 
+// development only: in-kernel timestamps of CTA (0, 0) (globaltimer ns): 0 start, 1 set-up done, 2 accumulators promoted
+// (= main loop done), 3 epilogue done, 4 exit; printed by spi_b200_policy_forward when SPI_B200_MLP_STAMPS is set
+__device__ unsigned long long g_stamps[3][8];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define MLP_STAMP(i) do { if (L.stamp >= 0 && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) g_stamps[L.stamp][i] = gtimer(); } while (0)
+
 struct LayerArgs {
   const float* a_hi; const float* a_lo;    // [Mp, Kp] activations, split, tiled_layout.cuh
   const float* w_hi; const float* w_lo;    // [N, Kp] weights (torch Linear layout [out, in]), split, tiled_layout.cuh
@@ -92,6 +149,9 @@ struct LayerArgs {
   int Kp, N;
   float* out_hi; float* out_lo; int out_stride;   // MODE 0: ELU(a w^T + b) split, tiled [Mp, out_stride]
   const float* w_out; const float* b_out; int n_out; float* out; int M;   // MODE 1: + output layer -> out [M, n_out]
+  int stamp;    // development only: row of g_stamps, or -1
+  int dbg;      // development only (SPI_B200_MLP_DBG): 1 = issue no MMAs, 2 = copy no operands — timing experiments, results are garbage
+  int cx, cy;   // thread-block cluster shape (x: CTAs that share an n-tile = the W operand, y: CTAs that share an m-tile = A)
 };
 
 // One 128 x 128 tile of  A W^T  per CTA;  grid = (Mp / 128, N / 128).  Warp-specialised, no CTA-wide barrier in the loop:
@@ -110,20 +170,35 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * kTile, n0 = blockIdx.y * kTile;
+  MLP_STAMP(0);
 
+  float* bias_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + kTailBias);     // [128] bias of this n-tile
+  float* wout_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + kTailWout);     // [n_out][128]
+  float* bout_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + kTailBout);     // [n_out]
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // Cluster (cx, cy): the cy CTAs of a cluster column share the m-tile, the cx CTAs of a cluster row share the n-tile.  Each CTA
+  // fetches 1 / cy of the A tiles and 1 / cx of the W tiles and multicasts the slice to the CTAs that need it, so every operand
+  // byte leaves L2 once per cluster instead of once per CTA.  A stage may be refilled once every CTA this one writes into has
+  // consumed it: the MMA issuers multicast their tcgen05.commit to the empty barriers of exactly those CTAs.
+  const bool clustered = L.cx * L.cy > 1;
+  const uint32_t ccx = clustered ? cluster_ctaid_x() : 0u, ccy = clustered ? cluster_ctaid_y() : 0u;
+  uint16_t mask_a = 0, mask_w = 0;      // CTA ranks (x fastest) that share this CTA's A / W tile
+  for (int j = 0; j < L.cy; j++) mask_a |= (uint16_t)(1u << (ccx + (uint32_t)j * L.cx));
+  for (int i = 0; i < L.cx; i++) mask_w |= (uint16_t)(1u << ((uint32_t)i + ccy * L.cx));
   if (tid == 32) {
-    for (int s = 0; s < kStages; s++) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
+    for (int s = 0; s < kStages; s++) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), (uint32_t)(L.cx + L.cy - 1)); }
     for (int a = 0; a < 2; a++) { mbar_init(smem_u32(accfull + a), 1); mbar_init(smem_u32(accempty + a), kEpilogue); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (clustered) cluster_sync();        // every peer's barriers exist before anything is multicast to them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *tmem_slot;
+  MLP_STAMP(1);
   const int n_blocks = L.Kp / kBK;
   const int n_groups = (n_blocks + kGroup - 1) / kGroup;
   const uint32_t smem_base = smem_u32(smem);
@@ -137,10 +212,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
         const int s = kb % kStages;
         if (kb >= kStages) mbar_wait(smem_u32(empty + s), (uint32_t)((kb / kStages - 1) & 1));
         const uint32_t bar = smem_u32(full + s), stage = smem_base + (uint32_t)s * kStageBytes;
+        if (L.dbg & 2) { mbar_arrive(bar); continue; }
         mbar_expect_tx(bar, kStageBytes);
+        if (!clustered) {
 #pragma unroll
-        for (int op = 0; op < 4; op++)
-          bulk_g2s(stage + (uint32_t)op * kOperandBytes, src[op] + (size_t)kb * tiled::kTileFloats, kOperandBytes, bar);
+          for (int op = 0; op < 4; op++)
+            bulk_g2s(stage + (uint32_t)op * kOperandBytes, src[op] + (size_t)kb * tiled::kTileFloats, kOperandBytes, bar);
+        } else {
+          const uint32_t a_bytes = kOperandBytes / (uint32_t)L.cy, w_bytes = kOperandBytes / (uint32_t)L.cx;
+          const uint32_t a_off = ccy * a_bytes, w_off = ccx * w_bytes;
+#pragma unroll
+          for (int op = 0; op < 2; op++)
+            bulk_g2s_mc(stage + (uint32_t)op * kOperandBytes + a_off, src[op] + (size_t)kb * tiled::kTileFloats + a_off / 4, a_bytes,
+                        bar, mask_a);
+#pragma unroll
+          for (int op = 2; op < 4; op++)
+            bulk_g2s_mc(stage + (uint32_t)op * kOperandBytes + w_off, src[op] + (size_t)kb * tiled::kTileFloats + w_off / 4, w_bytes,
+                        bar, mask_w);
+        }
       }
     }
   } else if (warp == kEpilogue / 32) {
@@ -158,67 +247,119 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
         const uint32_t tacc = tmem_d + (uint32_t)((g & 1) * kAccCols);
 #pragma unroll
         for (int k = 0; k < kBK / 8; k++) {
+          if (L.dbg & 1) break;
           const uint64_t off = (uint64_t)(k * 2);     // 32 bytes >> 4, inside the 14-bit start-address field
           mma_tf32(tacc, al + off, wh + off, (!group_start || k > 0) ? 1u : 0u);
           mma_tf32(tacc, ah + off, wl + off, 1u);
           mma_tf32(tacc, ah + off, wh + off, 1u);
         }
-        umma_commit(smem_u32(empty + s));
+        if (clustered) umma_commit_mc(smem_u32(empty + s), (uint16_t)(mask_a | mask_w));
+        else umma_commit(smem_u32(empty + s));
         if (group_end) umma_commit(smem_u32(accfull + (g & 1)));
       }
     }
   } else {
-    // ===== promotion + epilogue (thread = row) =====
-    float acc[kAccCols];
+    // ===== promotion + epilogue: thread = (row, column half) =====
+    const int q = warp & 3, hf = warp >> 2;
+    const int r = q * 32 + lane;                     // row of the tile = TMEM lane
+    const int c0 = hf * kHalfCols;                   // first column of this thread
+    // epilogue constants, fetched while the pipeline fills (ordered before their use by the epilogue barrier below)
+    for (int i = tid; i < kTile; i += kEpilogue) bias_s[i] = __ldg(L.bias + n0 + i);
+    if (MODE == 1) {
+      for (int i = tid; i < L.n_out * kTile; i += kEpilogue) wout_s[i] = __ldg(L.w_out + i);
+      for (int i = tid; i < L.n_out; i += kEpilogue) bout_s[i] = __ldg(L.b_out + i);
+    }
+    epi_barrier();
+    float acc[kHalfCols];
 #pragma unroll
-    for (int i = 0; i < kAccCols; i++) acc[i] = 0.f;
+    for (int i = 0; i < kHalfCols; i++) acc[i] = 0.f;
     for (int g = 0; g < n_groups; g++) {   // acc += accumulator of group g, then hand the accumulator back to the MMA warp
       mbar_wait(smem_u32(accfull + (g & 1)), (uint32_t)((g >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-      for (int cb = 0; cb < kAccCols / 32; cb++) {
-        uint32_t r[32];
-        tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)((g & 1) * kAccCols + cb * 32), r);
+      for (int cb = 0; cb < kHalfCols / 32; cb++) {
+        if (L.dbg & 4) break;
+        uint32_t v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((g & 1) * kAccCols + c0 + cb * 32), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < 32; i++) acc[cb * 32 + i] += __uint_as_float(r[i]);
+        for (int i = 0; i < 32; i++) acc[cb * 32 + i] += __uint_as_float(v[i]);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(smem_u32(accempty + (g & 1)));
     }
-    const int row = m0 + tid;
+    MLP_STAMP(2);
+    // every MMA has retired (the last accfull arrived) and every copy has landed: the stages are free
     if (MODE == 0) {
+      // ELU(acc + b) -> tf32 hi / lo, written as the next layer's operand tiles (tiled_layout.cuh): the 128 x 128 output is
+      // 4 k-blocks x {hi, lo} = 8 tiles of 16 KB, assembled in shared memory and stored with 8 contiguous bulk copies
 #pragma unroll
-      for (int i = 0; i < kAccCols; i += 4) {
-        float h[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) h[j] = elu(acc[i + j] + __ldg(L.bias + n0 + i + j));
+      for (int i = 0; i < kHalfCols; i += 4) {
+        const int col = c0 + i;
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col);
+        const float h0 = elu(acc[i] + b4.x), h1 = elu(acc[i + 1] + b4.y), h2 = elu(acc[i + 2] + b4.z), h3 = elu(acc[i + 3] + b4.w);
         float4 vh, vl;
-        vh.x = tf32_round(h[0]); vl.x = h[0] - vh.x;
-        vh.y = tf32_round(h[1]); vl.y = h[1] - vh.y;
-        vh.z = tf32_round(h[2]); vl.z = h[2] - vh.z;
-        vh.w = tf32_round(h[3]); vl.w = h[3] - vh.w;
-        const size_t o = tiled::offset(row, n0 + i, L.out_stride);      // 4 consecutive k = one 16-byte chunk
-        *reinterpret_cast<float4*>(L.out_hi + o) = vh;
-        *reinterpret_cast<float4*>(L.out_lo + o) = vl;
+        vh.x = tf32_round(h0); vl.x = h0 - vh.x;
+        vh.y = tf32_round(h1); vl.y = h1 - vh.y;
+        vh.z = tf32_round(h2); vl.z = h2 - vh.z;
+        vh.w = tf32_round(h3); vl.w = h3 - vh.w;
+        const int ob = col >> 5, ch = (col & 31) >> 2;
+        unsigned char* dst = smem + ob * kOperandBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4);
+        *reinterpret_cast<float4*>(dst) = vh;
+        *reinterpret_cast<float4*>(dst + 4 * kOperandBytes) = vl;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the bulk-copy engine
+      epi_barrier();
+      MLP_STAMP(5);
+      if (tid == 0) {
+        const size_t t0 = ((size_t)blockIdx.x * (size_t)(L.out_stride >> 5) + (size_t)(n0 >> 5)) * tiled::kTileFloats;
+#pragma unroll
+        for (int ob = 0; ob < 4; ob++) {
+          bulk_s2g(L.out_hi + t0 + (size_t)ob * tiled::kTileFloats, smem_base + (uint32_t)ob * kOperandBytes, kOperandBytes);
+          bulk_s2g(L.out_lo + t0 + (size_t)ob * tiled::kTileFloats, smem_base + (uint32_t)(4 + ob) * kOperandBytes, kOperandBytes);
+        }
+        bulk_commit_wait_read();
       }
     } else {
-      // all MMAs have retired (the last accfull arrived), so the stages are free: stage the output layer's weights there
-      float* w_s = reinterpret_cast<float*>(smem);      // [n_out][128]
-      for (int i = tid; i < L.n_out * kTile; i += kEpilogue) w_s[i] = L.w_out[i];
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpilogue) : "memory");
+      // last hidden layer (one n-tile) + the output layer: y[j] = b_out[j] + sum_i w_out[j][i] ELU(acc[i] + b[i]); each thread
+      // contracts its 64 columns (4 independent partial sums), the two halves of a row meet in shared memory in a fixed order
+      float* part = reinterpret_cast<float*>(smem);      // [128][kMaxOut]
 #pragma unroll
-      for (int i = 0; i < kAccCols; i++) acc[i] = elu(acc[i] + __ldg(L.bias + n0 + i));
-      for (int j = 0; j < L.n_out; j++) {
-        float y = L.b_out[j];
+      for (int i = 0; i < kHalfCols; i += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + i);
+        acc[i] = elu(acc[i] + b4.x); acc[i + 1] = elu(acc[i + 1] + b4.y);
+        acc[i + 2] = elu(acc[i + 2] + b4.z); acc[i + 3] = elu(acc[i + 3] + b4.w);
+      }
+      const int row = m0 + r;
+      float yv[kMaxOut];
 #pragma unroll
-        for (int i = 0; i < kAccCols; i++) y = fmaf(w_s[j * kTile + i], acc[i], y);
-        if (row < L.M) L.out[(size_t)row * L.n_out + j] = y;
+      for (int j = 0; j < kMaxOut; j++) {
+        if (j >= L.n_out) break;
+        float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+        const float4* w4 = reinterpret_cast<const float4*>(wout_s + j * kTile + c0);
+#pragma unroll
+        for (int i = 0; i < kHalfCols / 4; i++) {
+          const float4 w = w4[i];
+          y0 = fmaf(w.x, acc[4 * i], y0); y1 = fmaf(w.y, acc[4 * i + 1], y1);
+          y2 = fmaf(w.z, acc[4 * i + 2], y2); y3 = fmaf(w.w, acc[4 * i + 3], y3);
+        }
+        const float y = (y0 + y1) + (y2 + y3);
+        yv[j] = y;
+        if (hf == 1) part[r * kMaxOut + j] = y;
+      }
+      epi_barrier();
+      if (hf == 0 && row < L.M) {
+#pragma unroll
+        for (int j = 0; j < kMaxOut; j++)
+          if (j < L.n_out) L.out[(size_t)row * L.n_out + j] = bout_s[j] + (yv[j] + part[r * kMaxOut + j]);
       }
     }
   }
+  MLP_STAMP(3);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  MLP_STAMP(4);
+  if (clustered) cluster_sync();        // no peer still signals this CTA's barriers when it exits
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
 }
 

@@ -999,9 +999,46 @@ static cudaError_t mlp_set_attributes() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mlptc::mlp_layer_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlptc::kSmemBytes);
   return e;
 }
-static void mlp_launch(int mode, const mlptc::LayerArgs& L, dim3 grid, cudaStream_t st) {
-  if (mode == 0) mlptc::mlp_layer_kernel<0><<<grid, mlptc::kThreads, mlptc::kSmemBytes, st>>>(L);
-  else mlptc::mlp_layer_kernel<1><<<grid, mlptc::kThreads, mlptc::kSmemBytes, st>>>(L);
+// Thread-block cluster shape of a layer launch: the largest (cx, cy) <= the preferred shape that divides the grid.
+// SPI_B200_MLP_CLUSTER="cx,cy" overrides the preference (development knob for the measurements in profiles/README.md).
+static void mlp_cluster_shape(dim3 grid, int* cx, int* cy) {
+  static int pref_x = 0, pref_y = 0;
+  if (!pref_x) {
+    int x = 1, y = 1;   // measured on B200: multicast clusters (2,1) .. (2,4) change nothing (the main loop is shared-memory bound)
+    if (const char* e = std::getenv("SPI_B200_MLP_CLUSTER")) {
+      int a = 0, b = 0;
+      if (std::sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && b >= 1 && a * b <= 8) { x = a; y = b; }
+    }
+    pref_y = y; pref_x = x;
+  }
+  int x = pref_x, y = pref_y;
+  while (x > 1 && (grid.x % x || mlptc::kOperandBytes % x)) x >>= 1;
+  while (y > 1 && (grid.y % y || mlptc::kOperandBytes % y)) y >>= 1;
+  *cx = x < 1 ? 1 : x; *cy = y < 1 ? 1 : y;
+}
+
+static cudaError_t mlp_launch(int mode, mlptc::LayerArgs L, dim3 grid, cudaStream_t st) {
+  mlp_cluster_shape(grid, &L.cx, &L.cy);
+  static int dbg = -1, layers = 7, layer_no = 0;
+  if (dbg < 0) {
+    const char* e = std::getenv("SPI_B200_MLP_DBG"); dbg = e ? std::atoi(e) : 0;
+    const char* l = std::getenv("SPI_B200_MLP_LAYERS"); layers = l ? std::atoi(l) : 7;
+  }
+  L.dbg = dbg;
+  static int stamps = -1;
+  if (stamps < 0) stamps = std::getenv("SPI_B200_MLP_STAMPS") ? 1 : 0;
+  const int this_layer = (mode == 1) ? 2 : (layer_no++ & 1);
+  if (!((layers >> this_layer) & 1)) return cudaSuccess;
+  L.stamp = stamps ? this_layer : -1;
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = dim3(mlptc::kThreads); cfg.dynamicSmemBytes = mlptc::kSmemBytes; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)L.cx; attr[0].val.clusterDim.y = (unsigned)L.cy; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (mode == 0) return cudaLaunchKernelEx(&cfg, mlptc::mlp_layer_kernel<0>, L);
+  return cudaLaunchKernelEx(&cfg, mlptc::mlp_layer_kernel<1>, L);
 }
 
 static float tf32_rna_host(float x) {   // round to nearest, ties away: the value cvt.rna.tf32.f32 produces
@@ -1104,18 +1141,26 @@ int spi_b200_policy_forward(spi_b200_policy* p, const float* x_hi, const float* 
   // layer 1
   L.a_hi = x_hi; L.a_lo = x_lo; L.w_hi = p->w_hi[0]; L.w_lo = p->w_lo[0]; L.bias = p->bias[0]; L.Kp = p->Kp; L.N = p->dims[1];
   L.out_hi = p->act[0]; L.out_lo = p->act[1]; L.out_stride = p->dims[1]; L.M = M;
-  mlp_launch(0, L, dim3(Mp / mlptc::kTile, p->dims[1] / mlptc::kTile), st);
+  CUDA_OK(mlp_launch(0, L, dim3(Mp / mlptc::kTile, p->dims[1] / mlptc::kTile), st));
   if (int rc = check_launch("mlp_layer_kernel<0> (layer 1)")) return rc;
   // layer 2
   L.a_hi = p->act[0]; L.a_lo = p->act[1]; L.w_hi = p->w_hi[1]; L.w_lo = p->w_lo[1]; L.bias = p->bias[1]; L.Kp = p->dims[1]; L.N = p->dims[2];
   L.out_hi = p->act[2]; L.out_lo = p->act[3]; L.out_stride = p->dims[2];
-  mlp_launch(0, L, dim3(Mp / mlptc::kTile, p->dims[2] / mlptc::kTile), st);
+  CUDA_OK(mlp_launch(0, L, dim3(Mp / mlptc::kTile, p->dims[2] / mlptc::kTile), st));
   if (int rc = check_launch("mlp_layer_kernel<0> (layer 2)")) return rc;
   // layer 3 + output layer
   L.a_hi = p->act[2]; L.a_lo = p->act[3]; L.w_hi = p->w_hi[2]; L.w_lo = p->w_lo[2]; L.bias = p->bias[2]; L.Kp = p->dims[2]; L.N = p->dims[3];
   L.out_hi = nullptr; L.out_lo = nullptr; L.out_stride = 0;
   L.w_out = p->w_out; L.b_out = p->b_out; L.n_out = p->dims[4]; L.out = out;
-  mlp_launch(1, L, dim3(Mp / mlptc::kTile, 1), st);
+  CUDA_OK(mlp_launch(1, L, dim3(Mp / mlptc::kTile, 1), st));
+  if (std::getenv("SPI_B200_MLP_STAMPS")) {   // development only
+    unsigned long long h[3][8];
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(h, mlptc::g_stamps, sizeof(h));
+    for (int l = 0; l < 3; l++)
+      std::fprintf(stderr, "[mlp stamps] layer %d: setup %llu  mainloop %llu  epilogue %llu (compute %llu)  exit %llu  | start-to-next-start %lld ns\n", l + 1,
+                   h[l][1] - h[l][0], h[l][2] - h[l][1], h[l][3] - h[l][2], h[l][5] - h[l][2], h[l][4] - h[l][3], l < 2 ? (long long)(h[l + 1][0] - h[l][0]) : 0ll);
+  }
   return check_launch("mlp_layer_kernel<1> (layers 3 + 4)");
 }
 
