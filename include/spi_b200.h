@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SPI_B200_VERSION 101 /* major*100 + minor */
+#define SPI_B200_VERSION 102 /* major*100 + minor */
 
 /* ------------------------------------------------------------------------------------------
  * Model blob layout (fp32[SPI_BLOB_SIZE]).  Built on the host from the URDF
@@ -230,14 +230,17 @@ int spi_b200_fim_reward(spi_b200_model* model, const float* states, int M, int P
  *   the previous step (those envs ran with a zero action), out: new flags; main_commands [M,T,14];
  *   commands [N,14], actions [N,12] out; gait [N], clock [N,4], history [N,14,60] in/out; obs [N,900] out;
  *   obs_hi / obs_lo [rows, obs_stride] or NULL: the same observation pre-split for spi_b200_policy_forward;
+ *   ring_slots: 0, or 15 = RING MODE: obs_hi / obs_lo are the observation state itself, a ring of 15 clipped frames per env
+ *   (element slot * 60 + term); the step writes its frame into slot ctrl[3] and touches nothing else — history, obs and
+ *   hist_index may be NULL — and the actor runs through spi_b200_policy_forward_ring with the matching head position;
  *   hist_index [840] device ints (short_history gather); fim_hist [K,M,P1,25] + fim_live [K,M] or NULL;
- *   dead_steps [N] or NULL (+= done); schedule [steps,4] device ints (command row, sync flag, FIM slot, unused),
+ *   dead_steps [N] or NULL (+= done); schedule [steps,4] device ints (command row, sync flag, FIM slot, ring head),
  *   counter [1] / ctrl [4] device ints: ctrl <- schedule[counter++] on the device before the step;
  *   q_default [12] HOST.  1 <= P1 <= 17.                                                                          */
 int spi_b200_active_post_step(spi_b200_model* model, float* state, const float* raw_actions, unsigned char* done,
                               const float* main_commands, int T, float* commands, float* actions, float* gait,
                               float* clock, float* history, float* obs, float* obs_hi, float* obs_lo, int obs_stride,
-                              const int* hist_index, float* fim_hist,
+                              int ring_slots, const int* hist_index, float* fim_hist,
                               unsigned char* fim_live, float* dead_steps, const int* schedule, int* counter, int* ctrl,
                               int M, int P1, float dt, float action_clip, float clip_obs, float grav_x, float grav_y,
                               const float* q_default, void* cuda_stream);
@@ -264,6 +267,17 @@ int spi_b200_policy_unsplit_input(spi_b200_policy* policy, const float* x_hi, co
                                   void* cuda_stream);
 int spi_b200_policy_forward(spi_b200_policy* policy, const float* x_hi, const float* x_lo, int M, float* out,
                             void* cuda_stream);
+
+/* Ring-ordered input (active exploration): the actor's input [frame | per-key blocks of the 14 previous frames] is a
+ * fixed permutation of a ring of the last 15 frames, so instead of rebuilding the 900-dim observation every control step
+ * (legged_robot_base.py:511-527, 819-829: ~17 KB of memory traffic per env and step) the caller keeps the ring as the
+ * pre-split operand, writes one frame per step, and the first layer's weight columns are permuted instead — one copy per
+ * head position.  col_map [n_rot][dims[0]] HOST: col_map[r][k] = the original input column whose weight multiplies ring
+ * element k when the head is at position r (-1 = unused element).  rot_dev: DEVICE int holding the head position of
+ * this forward (read by the kernel, so a captured step needs no host work), or NULL for position 0.                  */
+int spi_b200_policy_enable_ring(spi_b200_policy* policy, const int* col_map, int n_rot);
+int spi_b200_policy_forward_ring(spi_b200_policy* policy, const float* x_hi, const float* x_lo, int M,
+                                 const int* rot_dev, float* out, void* cuda_stream);
 
 /* Accumulated Fisher information of whole rollouts on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 split =
  * fp32-accurate): the sum over control steps of the per-step J J^T that active_sysid_openloop.py:402-426 forms and

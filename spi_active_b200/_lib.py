@@ -78,7 +78,7 @@ SIGNATURES = {
     "spi_b200_body_states": (C.c_int, [_V, _V, C.c_int, _V, _V]),
     "spi_b200_compute_torques": (C.c_int, [_V, _V, _V, _V, _V, _V, C.c_int, C.c_int, C.c_uint, _V, _V]),
     "spi_b200_fim_reward": (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_float, C.c_int, _V, _V, _V]),
-    "spi_b200_active_post_step": (C.c_int, [_V, _V, _V, _V, _V, C.c_int, _V, _V, _V, _V, _V, _V, _V, _V, C.c_int, _V, _V,
+    "spi_b200_active_post_step": (C.c_int, [_V, _V, _V, _V, _V, C.c_int, _V, _V, _V, _V, _V, _V, _V, _V, C.c_int, C.c_int, _V, _V,
                                             _V, _V, _V, _V, _V, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                             C.c_float, C.c_float, _F, _V]),
     "spi_b200_policy_create": (C.c_int, [_I, C.POINTER(_F), C.POINTER(_F), C.POINTER(_V)]),
@@ -87,6 +87,8 @@ SIGNATURES = {
     "spi_b200_policy_split_input": (C.c_int, [_V, _V, C.c_int, _V, _V, _V]),
     "spi_b200_policy_unsplit_input": (C.c_int, [_V, _V, _V, C.c_int, _V, _V]),
     "spi_b200_policy_forward": (C.c_int, [_V, _V, _V, C.c_int, _V, _V]),
+    "spi_b200_policy_enable_ring": (C.c_int, [_V, _I, C.c_int]),
+    "spi_b200_policy_forward_ring": (C.c_int, [_V, _V, _V, C.c_int, _V, _V, _V]),
     "spi_b200_fim_contract": (C.c_int, [_V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _V, _V, _V]),
     "spi_b200_cem_refit": (C.c_int, [_V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_float, _V, _V, _V, _V, _V]),
     "spi_b200_cem_sample": (C.c_int, [_V, _V, _V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_int,

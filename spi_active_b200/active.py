@@ -82,6 +82,27 @@ def _history_gather_index() -> torch.Tensor:
     return torch.tensor(idx, dtype=torch.long)
 
 
+RING_SLOTS = HISTORY_LEN + 1      # the current frame + the 14 history frames
+
+
+def ring_col_map() -> np.ndarray:
+    """col_map[h, slot * 60 + term] = the actor-input column that a ring of the last 15 frames feeds when its newest
+    frame sits in slot h (the head moves DOWN by one slot per step, so slot (h + a) % 15 holds the frame of age a):
+    age 0 is the frame block obs[:60], age a >= 1 is row a - 1 of the history, which _history_gather_index scatters over
+    the per-key blocks of obs[60:].  Used to permute the first layer's weight columns once per head position instead of
+    rebuilding the observation every step (spi_b200_policy_enable_ring)."""
+    gather = _history_gather_index().numpy()                 # obs[60 + j] = hist_flat[gather[j]]
+    where = np.empty(HISTORY_LEN * FRAME_DIM, dtype=np.int64)
+    where[gather] = np.arange(HISTORY_LEN * FRAME_DIM)       # hist_flat[f] feeds obs[60 + where[f]]
+    cm = np.full((RING_SLOTS, ACTOR_OBS_DIM), -1, dtype=np.int32)
+    for h in range(RING_SLOTS):
+        for s in range(RING_SLOTS):
+            a = (s - h) % RING_SLOTS
+            for i in range(FRAME_DIM):
+                cm[h, s * FRAME_DIM + i] = i if a == 0 else FRAME_DIM + where[(a - 1) * FRAME_DIM + i]
+    return cm
+
+
 def quat_rotate_inverse(q: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
     """spigym/utils/torch_utils.py:83-92 (q = xyzw)."""
     q_w = q[:, 3:4]
@@ -185,6 +206,10 @@ class ActiveConfig:
     # actor evaluation in the fused step: "tensor" = spi_b200_policy_forward (tcgen05, 3xTF32: fp32-grade accuracy),
     # "cublas" = torch fp32 GEMMs; "auto" = tensor when the actor has the supported shape (the reference's does)
     policy_impl: str = "auto"
+    # with the tensor-core actor: keep the observation as a ring of 15 pre-split frames and permute the first layer's weight
+    # columns per head position instead of rebuilding the 900-dim observation every step (spi_b200_policy_forward_ring);
+    # False = the post-step kernel materialises obs / history like the reference does
+    obs_ring: bool = True
 
 
 class ActiveExploration:
@@ -272,9 +297,13 @@ class ActiveExploration:
                         raise
             elif c.policy_impl == "tensor":
                 raise ValueError("policy_impl='tensor' needs a backend with tensor_core_policy")
+            self.ring = False
             if self.tc_policy is not None:
                 self.obs_hi, self.obs_lo = self.tc_policy.alloc_input(N)
                 self.raw_actions = z(N, 12)
+                if c.obs_ring and self.tc_policy.dims[0] == ACTOR_OBS_DIM:
+                    self.tc_policy.enable_ring(ring_col_map())
+                    self.ring = True
 
     # ---- physics / reward through the engine -------------------------------------------------------------------------
     def _physics(self):
@@ -347,6 +376,9 @@ class ActiveExploration:
 
     def _policy_step(self):
         if self.step_impl == "fused":
+            if self.tc_policy is not None and self.ring:
+                return self._fused_step(self.tc_policy.forward_ring(self.obs_hi, self.obs_lo, self.num_envs,
+                                                                    self.ctrl[3:4], out=self.raw_actions))
             if self.tc_policy is not None:
                 return self._fused_step(self.tc_policy.forward_split(self.obs_hi, self.obs_lo, self.num_envs,
                                                                      out=self.raw_actions))
@@ -360,11 +392,48 @@ class ActiveExploration:
         c = self.cfg
         self.backend.env_step(self.state, raw_actions, params=self.params, param_names=self.param_names,
                               motor_model=c.motor_model, flags=gm.FLAG_HIP_HALF, zero_action_mask=self.done)
+        ring = getattr(self, "ring", False)
         self.backend.active_post_step(self.state, raw_actions, self.done, self.main_commands, self.commands,
-                                      self.actions, self.gait_indices, self.clock, self.history, self.obs,
-                                      self.hist_index_i32, self.hist, self.live_hist, self.dead_steps, self.schedule,
+                                      self.actions, self.gait_indices, self.clock, None if ring else self.history,
+                                      None if ring else self.obs, None if ring else self.hist_index_i32, self.hist,
+                                      self.live_hist, self.dead_steps, self.schedule,
                                       self.counter, self.ctrl, self.dt, c.action_clip, CLIP_OBSERVATIONS,
-                                      TERMINATION_GRAVITY, self.model.q_default, obs_hi=self.obs_hi, obs_lo=self.obs_lo)
+                                      TERMINATION_GRAVITY, self.model.q_default, obs_hi=self.obs_hi, obs_lo=self.obs_lo,
+                                      ring_slots=RING_SLOTS if ring else 0)
+
+    # ---- ring mode: the plain observation / history exist only on request ------------------------------------------------
+    def materialize_observation(self):
+        """Ring mode: self.obs [N,900] and self.history [N,14,60] <- what the ring holds (clipped frames; the reference
+        clips when it builds the observation, so obs is identical and history differs only beyond +-clip)."""
+        if not getattr(self, "ring", False):
+            return self.obs
+        N = self.num_envs
+        R = self.tc_policy.unsplit_input(self.obs_hi, self.obs_lo, N).view(N, -1)[:, :RING_SLOTS * FRAME_DIM]
+        R = R.reshape(N, RING_SLOTS, FRAME_DIM)
+        h = int(self.ctrl[3].item())
+        order = [(h + a) % RING_SLOTS for a in range(RING_SLOTS)]
+        frames = R[:, order, :]                                      # age 0 .. 14
+        # the observation reads the history BEFORE this step's frame was pushed (ages 1 .. 14); the stored history
+        # already holds it (ages 0 .. 13)
+        self.history.copy_(frames[:, :HISTORY_LEN, :])
+        before = frames[:, 1:, :].reshape(N, HISTORY_LEN * FRAME_DIM)
+        self.obs.copy_(torch.cat([frames[:, 0, :], before[:, self.hist_index]], dim=1))
+        return self.obs
+
+    def load_observation(self, obs: torch.Tensor, history: torch.Tensor):
+        """Ring mode: ring <- the 15 frames behind (obs [N,900], history [N,14,60] AFTER the push of obs' frame) at the
+        current head position: ages 0 .. 13 are the history rows, age 14 is the oldest row of the pre-push history,
+        which only the observation still carries."""
+        assert getattr(self, "ring", False)
+        N = self.num_envs
+        h = int(self.ctrl[3].item())
+        before = torch.zeros(N, HISTORY_LEN * FRAME_DIM, device=self.device)
+        before[:, self.hist_index] = obs[:, FRAME_DIM:]
+        oldest = before.view(N, HISTORY_LEN, FRAME_DIM)[:, HISTORY_LEN - 1:, :]
+        frames = torch.cat([history, oldest], dim=1).clamp(-CLIP_OBSERVATIONS, CLIP_OBSERVATIONS)
+        R = torch.zeros(N, RING_SLOTS, FRAME_DIM, device=self.device)
+        R[:, [(h + a) % RING_SLOTS for a in range(RING_SLOTS)], :] = frames
+        self.tc_policy.split_input(R.reshape(N, RING_SLOTS * FRAME_DIM).contiguous(), self.obs_hi, self.obs_lo)
 
     def _build_schedule(self, n_calls: int, T: int):
         """Row i = the host inputs of the (i + 1)-th env step after a reset: (command row, k-sync flag, FIM ring slot)
@@ -377,6 +446,7 @@ class ActiveExploration:
             rows[i, 0] = min(idx, T - 1)
             rows[i, 1] = int((k == 1) or (k > 1 and idx % k == 1))
             rows[i, 2] = 0 if i == 0 else (i - 1) % K                    # call 0 is the reset step (dropped)
+            rows[i, 3] = (-i) % RING_SLOTS                               # observation ring: the head moves down one slot per step
         if getattr(self, "schedule", None) is None or self.schedule.shape[0] < n_rows:
             self.schedule = torch.zeros((n_rows, 4), dtype=torch.int32, device=self.device)
             self._graph = None            # a captured step holds the old buffer's address
@@ -409,6 +479,9 @@ class ActiveExploration:
         for t in (self.actions, self.history, self.gait_indices, self.clock, self.total_reward, self.jtj, self.step_reward):
             t.zero_()
         self.done.zero_()
+        if fused and self.tc_policy is not None:
+            self.obs_hi.zero_(); self.obs_lo.zero_()
+            self.ctrl.zero_()
         if fused:
             self._build_schedule(int(total_steps or self.total_steps), self.main_commands.shape[1])
             # the gait clock of the first step (go2_omni.step); afterwards the post-step kernel advances it
@@ -416,7 +489,7 @@ class ActiveExploration:
             self.gait_indices.copy_(g); self.clock.copy_(clk)
             self.step_idx += 1
             self._fused_step(self.zero_actions)
-            return self.obs
+            return self.materialize_observation()
         self._advance_inputs()
         self._env_step(torch.zeros(N, 12, device=self.device))
         return self.obs
@@ -478,7 +551,7 @@ class ActiveExploration:
         if self.fim_mode == "tensor":
             live += [self.dead_steps]                 # hist / live_hist slots are rewritten before they are read
         if self.step_impl == "fused":
-            live += [self.counter]                    # the warm-up / capture steps must not consume schedule rows
+            live += [self.counter, self.ctrl]         # the warm-up / capture steps must not consume schedule rows
             if self.tc_policy is not None:
                 live += [self.obs_hi, self.obs_lo]    # what the tensor-core actor actually reads
         saved = [t.clone() for t in live]

@@ -42,11 +42,17 @@ struct Args {
   float* obs;                      // [N,900] out
   float* obs_hi; float* obs_lo;    // [rows, obs_stride] (tiled_layout.cuh) or null: pre-split input of spi_b200_policy_forward
   int obs_stride;
+  // ring_slots > 0 (= 15): obs_hi / obs_lo ARE the observation state — a ring of 15 frames per env, K position
+  // slot * 60 + term; this step's frame goes to slot ctrl[3] and nothing else is touched (history / obs / hist_index
+  // are not used).  The actor's first layer then runs with the weight columns permuted for that head position
+  // (spi_b200_policy_enable_ring): the 900-dim observation [frame | per-key history blocks] is never materialised.
+  int ring_slots;
   const int* hist_index;           // [840] gather index of short_history into the flattened [14*60] ring
   float* fim_hist;                 // [K,M,P1,25] or null
   unsigned char* fim_live;         // [K,M] or null
   float* dead_steps;               // [N] or null
-  const int* ctrl;                 // device: [0] command row t, [1] k-sync flag, [2] FIM ring slot (written by tick_kernel)
+  const int* ctrl;                 // device: [0] command row t, [1] k-sync flag, [2] FIM ring slot, [3] observation ring head
+                                   // (written by tick_kernel)
   int M, P1, T;
   float dt, action_clip, clip_obs, grav_x, grav_y;
   float q_default[12];
@@ -69,29 +75,33 @@ __device__ __forceinline__ void quat_rotate_inverse(const float* q, const float*
   o[2] = (v[2] * s - cz * w * 2.0f) + q[2] * dot * 2.0f;
 }
 
-// per-env shared-memory slice: state row (40) | frame (64) | history ring (840), + one flag per env at the end
-constexpr int kEnvSmemFloats = 40 + 64 + kHistLen * kFrame;
-inline size_t smem_bytes(int P1) { return (size_t)P1 * (kEnvSmemFloats * sizeof(float) + sizeof(int)); }
+// per-env shared-memory slice: state row (40) | frame (64) | history (840; not in ring mode), + one flag per env at the end
+constexpr int kEnvSmemFloats = 40 + 64 + kHistLen * kFrame, kEnvSmemFloatsRing = 40 + 64;
+inline size_t smem_bytes(int P1, bool ring = false) {
+  return (size_t)P1 * ((ring ? kEnvSmemFloatsRing : kEnvSmemFloats) * sizeof(float) + sizeof(int));
+}
 
 // The per-step host inputs (command row, k-sync flag, FIM ring slot) come from a schedule uploaded once per rollout:
 // ctrl <- schedule[counter], counter += 1.  One thread; runs right before the post-step kernel of the same step, so a
 // captured step needs no host work between replays.
 __global__ void tick_kernel(const int* schedule, int* counter, int* ctrl) {
   const int c = counter[0];
-  ctrl[0] = schedule[4 * c]; ctrl[1] = schedule[4 * c + 1]; ctrl[2] = schedule[4 * c + 2];
+  ctrl[0] = schedule[4 * c]; ctrl[1] = schedule[4 * c + 1]; ctrl[2] = schedule[4 * c + 2]; ctrl[3] = schedule[4 * c + 3];
   counter[0] = c + 1;
 }
 
 __global__ void __launch_bounds__(32 * kMaxGroup) active_post_step_kernel(const Args A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const bool ring = A.ring_slots > 0;
   struct View {
-    float* base; int* flag;
-    __device__ float* st(int w) const { return base + (size_t)w * kEnvSmemFloats; }
+    float* base; int* flag; int stride;
+    __device__ float* st(int w) const { return base + (size_t)w * stride; }
     __device__ float* frame(int w) const { return st(w) + 40; }
     __device__ float* hist(int w) const { return st(w) + 104; }
   } sm;
   sm.base = reinterpret_cast<float*>(smem_raw);
-  sm.flag = reinterpret_cast<int*>(sm.base + (size_t)A.P1 * kEnvSmemFloats);
+  sm.stride = ring ? kEnvSmemFloatsRing : kEnvSmemFloats;
+  sm.flag = reinterpret_cast<int*>(sm.base + (size_t)A.P1 * sm.stride);
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = blockIdx.x;
   const int env = m * A.P1 + w;
@@ -153,6 +163,20 @@ __global__ void __launch_bounds__(32 * kMaxGroup) active_post_step_kernel(const 
   }
   if (lane < 14) A.commands[(size_t)env * 14 + lane] = cmd[lane];
 
+  if (ring) {
+    // ---- ring mode: the clipped frame, split, into slot ctrl[3] of the actor's input operand -------------------------------
+    __syncwarp();
+    const int k0 = A.ctrl[3] * kFrame;
+    for (int i = lane; i < kFrame; i += 32) {
+      const float o = fminf(fmaxf(sm.frame(w)[i], -A.clip_obs), A.clip_obs);
+      uint32_t hb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(o));
+      const float h = __uint_as_float(hb);
+      const size_t at = tiled::offset(env, k0 + i, A.obs_stride);
+      A.obs_hi[at] = h;
+      A.obs_lo[at] = o - h;
+    }
+  } else {
   // ---- observation = [frame | gathered history], clip; then push the frame -----------------------------------------------
   float* hrow = A.history + (size_t)env * (kHistLen * kFrame);
   for (int i = lane; i < kHistLen * kFrame; i += 32) sm.hist(w)[i] = hrow[i];
@@ -172,6 +196,7 @@ __global__ void __launch_bounds__(32 * kMaxGroup) active_post_step_kernel(const 
     }
   }
   for (int i = lane; i < kHistLen * kFrame; i += 32) hrow[i] = (i < kFrame) ? sm.frame(w)[i] : sm.hist(w)[i - kFrame];
+  }
 
   // ---- termination flag, k-step sync, gait clock of the next step --------------------------------------------------------
   if (lane == 0) A.done[env] = group_done ? 1 : 0;

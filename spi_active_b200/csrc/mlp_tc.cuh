@@ -149,6 +149,7 @@ struct LayerArgs {
   int Kp, N;
   float* out_hi; float* out_lo; int out_stride;   // MODE 0: ELU(a w^T + b) split, tiled [Mp, out_stride]
   const float* w_out; const float* b_out; int n_out; float* out; int M;   // MODE 1: + output layer -> out [M, n_out]
+  const int* rot; size_t rot_stride; int n_rot;   // device int selecting one of n_rot weight copies rot_stride floats apart, or null
   int stamp;    // development only: row of g_stamps, or -1
   int dbg;      // development only (SPI_B200_MLP_DBG): 1 = issue no MMAs, 2 = copy no operands — timing experiments, results are garbage
   int cx, cy;   // thread-block cluster shape (x: CTAs that share an n-tile = the W operand, y: CTAs that share an m-tile = A)
@@ -206,7 +207,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
   if (warp == kEpilogue / 32 + 1) {
     // ===== bulk-copy producer =====
     if (lane == 0) {
-      const size_t a_tile = (size_t)blockIdx.x * n_blocks * tiled::kTileFloats, w_tile = (size_t)blockIdx.y * n_blocks * tiled::kTileFloats;
+      size_t w_copy = 0;
+      if (L.rot) { const int r = *L.rot; w_copy = (size_t)(r < 0 ? 0 : (r >= L.n_rot ? L.n_rot - 1 : r)) * L.rot_stride; }
+      const size_t a_tile = (size_t)blockIdx.x * n_blocks * tiled::kTileFloats,
+                   w_tile = w_copy + (size_t)blockIdx.y * n_blocks * tiled::kTileFloats;
       const float* src[4] = {L.a_hi + a_tile, L.a_lo + a_tile, L.w_hi + w_tile, L.w_lo + w_tile};
       for (int kb = 0; kb < n_blocks; kb++) {
         const int s = kb % kStages;

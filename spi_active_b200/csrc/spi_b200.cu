@@ -943,15 +943,20 @@ int spi_b200_fim_reward(spi_b200_model* m, const float* states, int Mn, int P, f
 int spi_b200_active_post_step(spi_b200_model* m, float* state, const float* raw_actions, unsigned char* done,
                               const float* main_commands, int T, float* commands, float* actions, float* gait,
                               float* clock, float* history, float* obs, float* obs_hi, float* obs_lo, int obs_stride,
-                              const int* hist_index, float* fim_hist,
+                              int ring_slots, const int* hist_index, float* fim_hist,
                               unsigned char* fim_live, float* dead_steps, const int* schedule, int* counter, int* ctrl,
                               int Mn, int P1, float dt, float action_clip, float clip_obs, float grav_x, float grav_y,
                               const float* q_default, void* cuda_stream) {
   if (!m) return fail(-1, "model handle is NULL");
   if (Mn <= 0 || P1 < 1 || P1 > activestep::kMaxGroup || T <= 0) return fail(-3, "bad M / group size / T");
-  if (!state || !raw_actions || !done || !main_commands || !commands || !actions || !gait || !clock || !history ||
-      !obs || !hist_index || !schedule || !counter || !ctrl || !q_default)
+  if (!state || !raw_actions || !done || !main_commands || !commands || !actions || !gait || !clock || !schedule ||
+      !counter || !ctrl || !q_default)
     return fail(-3, "NULL buffer");
+  if (ring_slots < 0 || (ring_slots > 0 && ring_slots != activestep::kHistLen + 1))
+    return fail(-3, "ring_slots must be 0 or 15 (the frame + 14 history frames)");
+  if (ring_slots > 0 && (!obs_hi || !obs_lo || obs_stride < ring_slots * activestep::kFrame))
+    return fail(-3, "ring mode needs obs_hi / obs_lo with obs_stride >= 900");
+  if (ring_slots == 0 && (!history || !obs || !hist_index)) return fail(-3, "NULL buffer");
   if (fim_hist && !fim_live) return fail(-3, "fim_live is NULL");
   if (obs_hi && (!obs_lo || obs_stride < activestep::kObs)) return fail(-3, "obs_lo is NULL or obs_stride < 900");
   static std::atomic<int> attr_done{0};
@@ -963,7 +968,7 @@ int spi_b200_active_post_step(spi_b200_model* m, float* state, const float* raw_
   activestep::Args A;
   A.state = state; A.raw_actions = raw_actions; A.done = done; A.main_commands = main_commands; A.commands = commands;
   A.actions = actions; A.gait = gait; A.clock = clock; A.history = history; A.obs = obs; A.hist_index = hist_index;
-  A.obs_hi = obs_hi; A.obs_lo = obs_lo; A.obs_stride = obs_stride;
+  A.obs_hi = obs_hi; A.obs_lo = obs_lo; A.obs_stride = obs_stride; A.ring_slots = ring_slots;
   A.fim_hist = fim_hist; A.fim_live = fim_live; A.dead_steps = dead_steps; A.ctrl = ctrl;
   A.M = Mn; A.P1 = P1; A.T = T; A.dt = dt; A.action_clip = action_clip; A.clip_obs = clip_obs;
   A.grav_x = grav_x; A.grav_y = grav_y;
@@ -971,7 +976,7 @@ int spi_b200_active_post_step(spi_b200_model* m, float* state, const float* raw_
   cudaStream_t st = (cudaStream_t)cuda_stream;
   activestep::tick_kernel<<<1, 1, 0, st>>>(schedule, counter, ctrl);
   if (int rc = check_launch("tick_kernel")) return rc;
-  activestep::active_post_step_kernel<<<Mn, 32 * P1, activestep::smem_bytes(P1), st>>>(A);
+  activestep::active_post_step_kernel<<<Mn, 32 * P1, activestep::smem_bytes(P1, ring_slots > 0), st>>>(A);
   return check_launch("active_post_step_kernel");
 }
 
@@ -985,11 +990,16 @@ struct spi_b200_policy {
   float* w_out = nullptr; float* b_out = nullptr;
   float* act[4] = {nullptr, nullptr, nullptr, nullptr};   // h1 hi, h1 lo, h2 hi, h2 lo
   size_t act_rows = 0;
+  std::vector<float> w1_host;          // layer-1 weights [h1, in] (ring copies are built from it)
+  float* ring_hi = nullptr; float* ring_lo = nullptr;   // [n_rot] tiled copies of layer 1 with permuted columns
+  int n_rot = 0;
+  size_t rot_stride = 0;               // floats between two copies
 };
 
 static void policy_free(spi_b200_policy* p) {
   for (int l = 0; l < 3; l++) { cudaFree(p->w_hi[l]); cudaFree(p->w_lo[l]); cudaFree(p->bias[l]); }
   cudaFree(p->w_out); cudaFree(p->b_out);
+  cudaFree(p->ring_hi); cudaFree(p->ring_lo);
   for (int i = 0; i < 4; i++) cudaFree(p->act[i]);
   delete p;
 }
@@ -1062,6 +1072,7 @@ int spi_b200_policy_create(const int* dims, const float* const* weights, const f
   if (!p) return fail(-4, "out of host memory");
   for (int i = 0; i < 5; i++) p->dims[i] = dims[i];
   p->Kp = (dims[0] + mlptc::kKAlign - 1) / mlptc::kKAlign * mlptc::kKAlign;
+  p->w1_host.assign(weights[0], weights[0] + (size_t)dims[1] * dims[0]);
   cudaError_t e = cudaSuccess;
   for (int l = 0; l < 3 && e == cudaSuccess; l++) {
     const int N = dims[l + 1], K = dims[l], Kp = (l == 0) ? p->Kp : K;
@@ -1124,8 +1135,50 @@ int spi_b200_policy_unsplit_input(spi_b200_policy* p, const float* x_hi, const f
   return check_launch("unsplit_kernel");
 }
 
+int spi_b200_policy_enable_ring(spi_b200_policy* p, const int* col_map, int n_rot) {
+  if (!p) return fail(-1, "policy handle is NULL");
+  if (!col_map || n_rot < 1 || n_rot > 64) return fail(-3, "col_map is NULL or n_rot outside 1..64");
+  const int N = p->dims[1], K = p->dims[0], Kp = p->Kp;
+  for (size_t i = 0; i < (size_t)n_rot * K; i++)
+    if (col_map[i] < -1 || col_map[i] >= K) return fail(-3, "col_map entry outside [-1, in)");
+  const size_t stride = (size_t)N * Kp;
+  std::vector<float> hi(stride * n_rot, 0.f), lo(stride * n_rot, 0.f);
+  for (int r = 0; r < n_rot; r++)
+    for (int n = 0; n < N; n++)
+      for (int k = 0; k < K; k++) {
+        const int c = col_map[(size_t)r * K + k];
+        if (c < 0) continue;
+        const float w = p->w1_host[(size_t)n * K + c];
+        const float h = tf32_rna_host(w);
+        const size_t o = (size_t)r * stride + tiled::offset(n, k, Kp);
+        hi[o] = h; lo[o] = w - h;
+      }
+  cudaFree(p->ring_hi); cudaFree(p->ring_lo);
+  p->ring_hi = p->ring_lo = nullptr; p->n_rot = 0;
+  CUDA_OK(cudaMalloc((void**)&p->ring_hi, hi.size() * sizeof(float)));
+  CUDA_OK(cudaMalloc((void**)&p->ring_lo, lo.size() * sizeof(float)));
+  CUDA_OK(cudaMemcpy(p->ring_hi, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(p->ring_lo, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice));
+  p->n_rot = n_rot; p->rot_stride = stride;
+  return 0;
+}
+
+static int policy_forward_impl(spi_b200_policy* p, const float* x_hi, const float* x_lo, int M, bool ring,
+                               const int* rot_dev, float* out, void* cuda_stream);
+
 int spi_b200_policy_forward(spi_b200_policy* p, const float* x_hi, const float* x_lo, int M, float* out,
                             void* cuda_stream) {
+  return policy_forward_impl(p, x_hi, x_lo, M, false, nullptr, out, cuda_stream);
+}
+
+int spi_b200_policy_forward_ring(spi_b200_policy* p, const float* x_hi, const float* x_lo, int M, const int* rot_dev,
+                                 float* out, void* cuda_stream) {
+  if (p && !p->n_rot) return fail(-3, "spi_b200_policy_enable_ring has not been called");
+  return policy_forward_impl(p, x_hi, x_lo, M, true, rot_dev, out, cuda_stream);
+}
+
+static int policy_forward_impl(spi_b200_policy* p, const float* x_hi, const float* x_lo, int M, bool ring,
+                               const int* rot_dev, float* out, void* cuda_stream) {
   if (!p) return fail(-1, "policy handle is NULL");
   if (M <= 0 || !x_hi || !x_lo || !out) return fail(-3, "bad arguments");
   const int Mp = (M + mlptc::kTile - 1) / mlptc::kTile * mlptc::kTile;
@@ -1141,9 +1194,11 @@ int spi_b200_policy_forward(spi_b200_policy* p, const float* x_hi, const float* 
   // layer 1
   L.a_hi = x_hi; L.a_lo = x_lo; L.w_hi = p->w_hi[0]; L.w_lo = p->w_lo[0]; L.bias = p->bias[0]; L.Kp = p->Kp; L.N = p->dims[1];
   L.out_hi = p->act[0]; L.out_lo = p->act[1]; L.out_stride = p->dims[1]; L.M = M;
+  if (ring) { L.w_hi = p->ring_hi; L.w_lo = p->ring_lo; L.rot = rot_dev; L.rot_stride = p->rot_stride; L.n_rot = p->n_rot; }
   CUDA_OK(mlp_launch(0, L, dim3(Mp / mlptc::kTile, p->dims[1] / mlptc::kTile), st));
   if (int rc = check_launch("mlp_layer_kernel<0> (layer 1)")) return rc;
   // layer 2
+  L.rot = nullptr; L.rot_stride = 0; L.n_rot = 0;
   L.a_hi = p->act[0]; L.a_lo = p->act[1]; L.w_hi = p->w_hi[1]; L.w_lo = p->w_lo[1]; L.bias = p->bias[1]; L.Kp = p->dims[1]; L.N = p->dims[2];
   L.out_hi = p->act[2]; L.out_lo = p->act[3]; L.out_stride = p->dims[2];
   CUDA_OK(mlp_launch(0, L, dim3(Mp / mlptc::kTile, p->dims[2] / mlptc::kTile), st));

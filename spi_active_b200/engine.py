@@ -116,6 +116,29 @@ class TensorCorePolicy:
         _lib.check(rc, "spi_b200_policy_forward")
         return out
 
+    def enable_ring(self, col_map: np.ndarray):
+        """col_map[n_rot, in] (int): ring element k multiplies the weight of original input column col_map[r, k] when the
+        head is at position r (-1 = unused) — spi_b200_policy_enable_ring."""
+        cm = np.ascontiguousarray(col_map, dtype=np.int32)
+        assert cm.ndim == 2 and cm.shape[1] == self.dims[0]
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_policy_enable_ring(self._handle, cm.ctypes.data_as(C.POINTER(C.c_int)), int(cm.shape[0]))
+        _lib.check(rc, "spi_b200_policy_enable_ring")
+        self.n_rot = int(cm.shape[0])
+
+    def forward_ring(self, x_hi: torch.Tensor, x_lo: torch.Tensor, M: int, rot: torch.Tensor, out: Optional[torch.Tensor] = None):
+        """forward_split on a ring-ordered input; rot = DEVICE int32 tensor whose element 0 is the head position."""
+        rows, stride = self.input_layout(M)
+        assert tuple(x_hi.shape) == (rows, stride) == tuple(x_lo.shape) and x_hi.is_contiguous() and x_lo.is_contiguous()
+        assert rot.is_cuda and rot.dtype == torch.int32
+        if out is None:
+            out = torch.empty((M, self.dims[4]), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            rc = self.lib.spi_b200_policy_forward_ring(self._handle, _ptr(x_hi), _ptr(x_lo), int(M), _ptr(rot), _ptr(out),
+                                                       self._stream())
+        _lib.check(rc, "spi_b200_policy_forward_ring")
+        return out
+
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         x = x.to(self.device, torch.float32).contiguous()
         x_hi, x_lo = self.alloc_input(x.shape[0])
@@ -335,23 +358,25 @@ class RolloutEngine:
 
     def active_post_step(self, state, raw_actions, done, main_commands, commands, actions, gait, clock, history, obs,
                          hist_index, fim_hist, fim_live, dead_steps, schedule, counter, ctrl, dt: float,
-                         action_clip: float, clip_obs: float, grav_xy, q_default, obs_hi=None, obs_lo=None):
+                         action_clip: float, clip_obs: float, grav_xy, q_default, obs_hi=None, obs_lo=None,
+                         ring_slots: int = 0):
         """The fused post-physics step of the active-exploration rollout (spi_b200_active_post_step); every tensor is
-        updated in place.  state[N,37], main_commands[M,T,14], N = M * P1."""
+        updated in place.  state[N,37], main_commands[M,T,14], N = M * P1.  ring_slots = 15: obs_hi / obs_lo are the ring
+        of frames the actor reads (history / obs / hist_index unused, may be None)."""
         Mn, T = int(main_commands.shape[0]), int(main_commands.shape[1])
         N = int(state.shape[0])
         P1 = N // Mn
         assert N == Mn * P1 and main_commands.shape[2] == 14 and done.element_size() == 1
         for t in (state, raw_actions, done, main_commands, commands, actions, gait, clock, history, obs, hist_index,
                   schedule, counter, ctrl):
-            assert t.is_cuda and t.is_contiguous()
-        assert hist_index.dtype == torch.int32 and schedule.dtype == torch.int32 and counter.dtype == torch.int32
+            assert t is None or (t.is_cuda and t.is_contiguous())
+        assert (hist_index is None or hist_index.dtype == torch.int32) and schedule.dtype == torch.int32 and counter.dtype == torch.int32
         qd = np.ascontiguousarray(q_default, dtype=np.float32)
         with torch.cuda.device(self.device):
             rc = self.lib.spi_b200_active_post_step(
                 self._handle, _ptr(state), _ptr(raw_actions), _ptr(done), _ptr(main_commands), T, _ptr(commands),
                 _ptr(actions), _ptr(gait), _ptr(clock), _ptr(history), _ptr(obs), _ptr(obs_hi), _ptr(obs_lo),
-                0 if obs_hi is None else int(obs_hi.shape[1]), _ptr(hist_index), _ptr(fim_hist),
+                0 if obs_hi is None else int(obs_hi.shape[1]), int(ring_slots), _ptr(hist_index), _ptr(fim_hist),
                 _ptr(fim_live), _ptr(dead_steps), _ptr(schedule), _ptr(counter), _ptr(ctrl), Mn, P1, float(dt),
                 float(action_clip), float(clip_obs), float(grav_xy[0]), float(grav_xy[1]),
                 qd.ctypes.data_as(C.POINTER(C.c_float)), self._stream())

@@ -77,6 +77,27 @@ def test_observation_layout_matches_reference():
     assert np.abs(g["actor_obs"][5]).max() == 100.0        # the clip was exercised
 
 
+def test_ring_col_map_reproduces_the_observation():
+    """The ring formulation of the actor input (spi_b200_policy_forward_ring): pushing one frame per step into slot
+    (-step) % 15 and reading through ring_col_map gives exactly the observation the reference builds from its history
+    buffers (frame | per-key history blocks), for every head position."""
+    rng = np.random.default_rng(0)
+    gather = act._history_gather_index().numpy()
+    cm = act.ring_col_map()
+    assert cm.shape == (act.RING_SLOTS, 900)
+    history = np.zeros((14, 60))
+    ring = np.zeros((act.RING_SLOTS, 60))
+    for step in range(40):
+        frame = rng.standard_normal(60)
+        obs = np.concatenate([frame, history.reshape(-1)[gather]])           # legged_robot_base.py:511-527, 819-829
+        h = (-step) % act.RING_SLOTS
+        ring[h] = frame
+        flat = ring.reshape(-1)
+        np.testing.assert_array_equal(obs[cm[h]], flat)                      # ring element k carries obs[cm[h, k]]
+        assert sorted(cm[h].tolist()) == list(range(900))
+        history = np.concatenate([frame[None], history[:-1]])                # history_handler.add
+
+
 def test_param_table_and_group_layout(blob, nominal_model):
     cfg = act.ActiveConfig(exploration_params=["mass", "comx", "motor_model_calf_a"])
     ex = act.ActiveExploration(OracleActiveBackend(blob, nominal_model), act.PolicyMLP.random("cpu"), 3, cfg)
@@ -272,7 +293,7 @@ def test_evaluate_policy_gpu_matches_oracle_loop(engine, blob, nominal_model):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("policy_impl", ["cublas", "tensor"])
+@pytest.mark.parametrize("policy_impl", ["cublas", "tensor", "tensor-ring"])
 def test_fused_post_step_kernel_matches_torch_statement(engine, policy_impl):
     """spi_b200_active_post_step (one kernel per step) against the torch statement of the same step (which the golden
     vectors pin to the reference's code): every piece of state after each of 12 closed-loop steps, with a k-sync in the
@@ -282,6 +303,9 @@ def test_fused_post_step_kernel_matches_torch_statement(engine, policy_impl):
                             fim_mode="tensor", fim_chunk=4)
     cmds = _commands(5, 40, seed=2)
     cmds[:, 20:, 0] *= -1.0                      # the command rows change inside the window
+    ring = policy_impl == "tensor-ring"          # the observation lives as a ring of pre-split frames (obs_ring)
+    policy_impl = policy_impl.split("-")[0]
+    base = dataclasses.replace(base, obs_ring=ring)
     exs = {}
     for impl in ("torch", "fused"):
         ex = exs[impl] = act.ActiveExploration(engine, act.PolicyMLP.random(engine.device, seed=1), 5,
@@ -289,7 +313,7 @@ def test_fused_post_step_kernel_matches_torch_statement(engine, policy_impl):
         assert ex.step_impl == impl
         ex.reset_all(cmds, total_steps=30)
     a, b = exs["torch"], exs["fused"]
-    assert (b.tc_policy is not None) == (policy_impl == "tensor")
+    assert (b.tc_policy is not None) == (policy_impl == "tensor") and b.ring == ring
     # same actor arithmetic (cuBLAS on both sides): the post-step kernel must agree to fp32 rounding; with the 3xTF32
     # actor the actions differ by ~2e-6, which a stiff foot contact turns into ~1e-4 on a velocity within one step
     vel_tol = 2e-5 if policy_impl == "cublas" else 2e-3
@@ -297,6 +321,7 @@ def test_fused_post_step_kernel_matches_torch_statement(engine, policy_impl):
     frame_vel = np.zeros(60, bool); frame_vel[12:15] = True; frame_vel[45:57] = True      # base_ang_vel, dof_vel terms
 
     def compare(tag):
+        b.materialize_observation()              # ring mode: obs / history <- the ring (a no-op otherwise)
         for name in ("state", "actions", "obs", "history", "commands", "done", "dead_steps"):
             x, y = getattr(a, name).float().cpu().numpy(), getattr(b, name).float().cpu().numpy()
             if name == "state":
@@ -323,7 +348,7 @@ def test_fused_post_step_kernel_matches_torch_statement(engine, policy_impl):
         a._advance_inputs(); a._policy_step(); a._hist_count = (a._hist_count + 1) % 4
         b.step_idx += 1; b._policy_step()
         compare(f"step {k}")
-        if b.tc_policy is not None:     # hi + lo is the observation, exactly; the padding stays zero
+        if b.tc_policy is not None and not ring:     # hi + lo is the observation, exactly; the padding stays zero
             np.testing.assert_array_equal(b.tc_policy.unsplit_input(b.obs_hi, b.obs_lo, b.num_envs).cpu().numpy(),
                                           b.obs.cpu().numpy())
             n_written = b.num_envs * 900                                          # the padding stays zero
@@ -334,7 +359,9 @@ def test_fused_post_step_kernel_matches_torch_statement(engine, policy_impl):
             getattr(b, name).copy_(getattr(a, name))
         g, clk = act.step_contact_targets(a.gait_indices, a.commands, a.dt)
         b.gait_indices.copy_(g); b.clock.copy_(clk)
-        if b.tc_policy is not None:     # the tensor-core actor reads the pre-split observation
+        if ring:
+            b.load_observation(a.obs, a.history)
+        elif b.tc_policy is not None:     # the tensor-core actor reads the pre-split observation
             b.tc_policy.split_input(b.obs, b.obs_hi, b.obs_lo)
         np.testing.assert_allclose(b.hist.cpu().numpy(), a.hist.cpu().numpy(), rtol=2e-5, atol=2e-5)
         np.testing.assert_array_equal(b.live_hist.cpu().numpy(), a.live_hist.cpu().numpy())

@@ -64,3 +64,36 @@ def test_policy_rejects_unsupported_shapes():
     ws, bs = _make((900, 512, 256, 64, 12), 0)
     with pytest.raises(SpiB200Error):
         TensorCorePolicy(ws, bs, torch.device("cuda:0"))
+
+
+def test_policy_forward_ring_permutes_the_first_layer():
+    """spi_b200_policy_forward_ring: with col_map[r] a permutation of the input columns (and a few unused elements), the
+    forward on the ring-ordered input at head position r equals the plain forward on the un-permuted input."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from spi_active_b200.engine import TensorCorePolicy
+    dev = torch.device("cuda:0")
+    dims, M, n_rot = (900, 512, 256, 128, 12), 300, 4
+    ws, bs = _make(dims, seed=11)
+    pol = TensorCorePolicy(ws, bs, dev)
+    rng = np.random.default_rng(5)
+    col_map = np.stack([rng.permutation(900) for _ in range(n_rot)]).astype(np.int32)
+    col_map[2, :7] = -1                                    # rotation 2 ignores 7 ring elements (their columns get no input)
+    pol.enable_ring(col_map)
+    x = torch.randn(M, 900, generator=torch.Generator().manual_seed(3)) * 1.5
+    rot = torch.zeros(1, dtype=torch.int32, device=dev)
+    for r in range(n_rot):
+        ring = torch.zeros(M, 900)
+        valid = col_map[r] >= 0
+        ring[:, valid] = x[:, col_map[r][valid]]           # ring element k carries input column col_map[r, k]
+        ring[:, ~valid] = 123.0                            # must be ignored
+        x_eff = torch.zeros(M, 900)
+        x_eff[:, col_map[r][valid]] = x[:, col_map[r][valid]]
+        hi, lo = pol.alloc_input(M)
+        pol.split_input(ring.to(dev).contiguous(), hi, lo)
+        rot.fill_(r)
+        y = pol.forward_ring(hi, lo, M, rot)
+        torch.cuda.synchronize()
+        ref = _mlp64(x_eff.numpy(), [w.numpy() for w in ws], [b.numpy() for b in bs])
+        err = np.abs(y.cpu().numpy() - ref).max() / np.abs(ref).max()
+        assert err < 5e-6, (r, err)
