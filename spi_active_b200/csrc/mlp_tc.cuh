@@ -12,7 +12,8 @@
 //     the global arrays are stored tile by tile as the SWIZZLE_128B K-major shared-memory image (tiled_layout.cuh) and a
 //     stage is four contiguous 16 KB TMA bulk copies (cp.async.bulk + mbarrier complete_tx), 3-stage ring with
 //     full / empty mbarriers (tcgen05.commit releases a stage);
-//   * a dedicated warp issues 12 MMAs (4 k-steps x 3 products) of 128 x 128 x 8 per stage into a 128-column fp32 TMEM tile;
+//   * a dedicated warp issues 8 MMAs per stage (4 k-steps x {a_hi [w_hi; w_lo] at N = 256, a_lo w_hi at N = 128}) into a 256-column
+//     fp32 TMEM tile whose two halves are added during the promotion;
 //   * the tensor core's accumulation truncates (measured: a 1e-5 bias over K = 928), so two TMEM accumulators alternate
 //     between groups of 4 k-blocks and are promoted into fp32 registers (tcgen05.ld + round-to-nearest add);
 //   * epilogue (thread = row): + bias -> ELU -> split -> hi / lo of the next layer's input; the last hidden layer (128
@@ -31,8 +32,8 @@ constexpr int kEpilogue = 256;               // warps 0-7: accumulator promotion
                                              // TMEM lane quadrant) and columns 64 (w >> 2) .. + 63
 constexpr int kHalfCols = 64;
 constexpr int kThreads = kEpilogue + 64;     // warp 8: MMA issuer, warp 9: bulk-copy producer (one elected lane each)
-constexpr int kAccCols = 128;                // one fp32 accumulator tile
-constexpr int kTmemCols = 2 * kAccCols;      // two accumulators, used alternately by groups of k-blocks
+constexpr int kAccCols = 256;                // one accumulator: columns [0,128) = a_hi w_hi + a_lo w_hi, [128,256) = a_hi w_lo
+constexpr int kTmemCols = 2 * kAccCols;      // two accumulators, used alternately by groups of k-blocks (all of TMEM)
 constexpr int kKAlign = 32;                  // the padded K of every operand is a multiple of this
 constexpr int kBK = 32;                      // fp32 elements of K per stage = one 128-byte swizzle atom per row
 constexpr int kStages = 3;
@@ -60,6 +61,18 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr) {
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
+}
+
+// instruction descriptors (cute::UMMA::InstrDescriptor, see fim_tc.cuh): tf32 x tf32 -> f32, K-major operands, M = 128
+__host__ __device__ constexpr uint32_t idesc_tf32(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24); }
+__device__ __forceinline__ void mma_tf32_n(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -246,16 +259,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
         mbar_wait(smem_u32(full + s), (uint32_t)((kb / kStages) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t stage = smem_base + (uint32_t)s * kStageBytes;
+        // the W_hi and W_lo tiles of a stage are adjacent, i.e. ONE 256-row K-major operand [W_hi; W_lo]: a_hi meets both in a
+        // single N = 256 MMA (columns [0,128) += a_hi w_hi, [128,256) += a_hi w_lo), a_lo w_hi goes into the first half with an
+        // N = 128 MMA.  Same tensor-pipe time as three N = 128 MMAs, but a_hi is read from shared memory once instead of
+        // twice — and shared-memory bandwidth (MMA operand reads + the copy engine's writes) is what bounds this loop
         const uint64_t ah = make_desc_sw128(stage), al = make_desc_sw128(stage + kOperandBytes),
-                       wh = make_desc_sw128(stage + 2 * kOperandBytes), wl = make_desc_sw128(stage + 3 * kOperandBytes);
+                       wh = make_desc_sw128(stage + 2 * kOperandBytes);
         const uint32_t tacc = tmem_d + (uint32_t)((g & 1) * kAccCols);
 #pragma unroll
         for (int k = 0; k < kBK / 8; k++) {
           if (L.dbg & 1) break;
           const uint64_t off = (uint64_t)(k * 2);     // 32 bytes >> 4, inside the 14-bit start-address field
-          mma_tf32(tacc, al + off, wh + off, (!group_start || k > 0) ? 1u : 0u);
-          mma_tf32(tacc, ah + off, wl + off, 1u);
-          mma_tf32(tacc, ah + off, wh + off, 1u);
+          mma_tf32_n(tacc, ah + off, wh + off, idesc_tf32(2 * kTile), (!group_start || k > 0) ? 1u : 0u);
+          mma_tf32_n(tacc, al + off, wh + off, idesc_tf32(kTile), 1u);
         }
         if (clustered) umma_commit_mc(smem_u32(empty + s), (uint16_t)(mask_a | mask_w));
         else umma_commit(smem_u32(empty + s));
@@ -281,13 +297,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
       mbar_wait(smem_u32(accfull + (g & 1)), (uint32_t)((g >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-      for (int cb = 0; cb < kHalfCols / 32; cb++) {
+      for (int cb = 0; cb < 2 * (kHalfCols / 32); cb++) {     // both halves of the accumulator (hi.hi + lo.hi, then hi.lo)
         if (L.dbg & 4) break;
         uint32_t v[32];
-        tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((g & 1) * kAccCols + c0 + cb * 32), v);
+        const int half = cb / (kHalfCols / 32), sub = cb % (kHalfCols / 32);
+        tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((g & 1) * kAccCols + half * kTile + c0 + sub * 32), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < 32; i++) acc[cb * 32 + i] += __uint_as_float(v[i]);
+        for (int i = 0; i < 32; i++) acc[sub * 32 + i] += __uint_as_float(v[i]);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(smem_u32(accempty + (g & 1)));

@@ -994,6 +994,11 @@ struct spi_b200_policy {
   float* ring_hi = nullptr; float* ring_lo = nullptr;   // [n_rot] tiled copies of layer 1 with permuted columns
   int n_rot = 0;
   size_t rot_stride = 0;               // floats between two copies
+  // row chunks of a forward run as independent layer chains on side streams (policy_forward_impl)
+  static constexpr int kMaxChunks = 8;
+  cudaStream_t side[kMaxChunks - 1] = {};
+  cudaEvent_t fork = nullptr, join[kMaxChunks - 1] = {};
+  bool streams_ready = false;
 };
 
 static void policy_free(spi_b200_policy* p) {
@@ -1001,6 +1006,10 @@ static void policy_free(spi_b200_policy* p) {
   cudaFree(p->w_out); cudaFree(p->b_out);
   cudaFree(p->ring_hi); cudaFree(p->ring_lo);
   for (int i = 0; i < 4; i++) cudaFree(p->act[i]);
+  if (p->streams_ready) {
+    for (int i = 0; i < spi_b200_policy::kMaxChunks - 1; i++) { cudaStreamDestroy(p->side[i]); cudaEventDestroy(p->join[i]); }
+    cudaEventDestroy(p->fork);
+  }
   delete p;
 }
 
@@ -1027,9 +1036,9 @@ static void mlp_cluster_shape(dim3 grid, int* cx, int* cy) {
   *cx = x < 1 ? 1 : x; *cy = y < 1 ? 1 : y;
 }
 
-static cudaError_t mlp_launch(int mode, mlptc::LayerArgs L, dim3 grid, cudaStream_t st) {
+static cudaError_t mlp_launch(int mode, int layer, mlptc::LayerArgs L, dim3 grid, cudaStream_t st) {
   mlp_cluster_shape(grid, &L.cx, &L.cy);
-  static int dbg = -1, layers = 7, layer_no = 0;
+  static int dbg = -1, layers = 7;
   if (dbg < 0) {
     const char* e = std::getenv("SPI_B200_MLP_DBG"); dbg = e ? std::atoi(e) : 0;
     const char* l = std::getenv("SPI_B200_MLP_LAYERS"); layers = l ? std::atoi(l) : 7;
@@ -1037,7 +1046,7 @@ static cudaError_t mlp_launch(int mode, mlptc::LayerArgs L, dim3 grid, cudaStrea
   L.dbg = dbg;
   static int stamps = -1;
   if (stamps < 0) stamps = std::getenv("SPI_B200_MLP_STAMPS") ? 1 : 0;
-  const int this_layer = (mode == 1) ? 2 : (layer_no++ & 1);
+  const int this_layer = layer;
   if (!((layers >> this_layer) & 1)) return cudaSuccess;
   L.stamp = stamps ? this_layer : -1;
   cudaLaunchConfig_t cfg;
@@ -1189,25 +1198,66 @@ static int policy_forward_impl(spi_b200_policy* p, const float* x_hi, const floa
     p->act_rows = (size_t)Mp;
   }
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  mlptc::LayerArgs L;
-  std::memset(&L, 0, sizeof(L));
-  // layer 1
-  L.a_hi = x_hi; L.a_lo = x_lo; L.w_hi = p->w_hi[0]; L.w_lo = p->w_lo[0]; L.bias = p->bias[0]; L.Kp = p->Kp; L.N = p->dims[1];
-  L.out_hi = p->act[0]; L.out_lo = p->act[1]; L.out_stride = p->dims[1]; L.M = M;
-  if (ring) { L.w_hi = p->ring_hi; L.w_lo = p->ring_lo; L.rot = rot_dev; L.rot_stride = p->rot_stride; L.n_rot = p->n_rot; }
-  CUDA_OK(mlp_launch(0, L, dim3(Mp / mlptc::kTile, p->dims[1] / mlptc::kTile), st));
-  if (int rc = check_launch("mlp_layer_kernel<0> (layer 1)")) return rc;
-  // layer 2
-  L.rot = nullptr; L.rot_stride = 0; L.n_rot = 0;
-  L.a_hi = p->act[0]; L.a_lo = p->act[1]; L.w_hi = p->w_hi[1]; L.w_lo = p->w_lo[1]; L.bias = p->bias[1]; L.Kp = p->dims[1]; L.N = p->dims[2];
-  L.out_hi = p->act[2]; L.out_lo = p->act[3]; L.out_stride = p->dims[2];
-  CUDA_OK(mlp_launch(0, L, dim3(Mp / mlptc::kTile, p->dims[2] / mlptc::kTile), st));
-  if (int rc = check_launch("mlp_layer_kernel<0> (layer 2)")) return rc;
-  // layer 3 + output layer
-  L.a_hi = p->act[2]; L.a_lo = p->act[3]; L.w_hi = p->w_hi[2]; L.w_lo = p->w_lo[2]; L.bias = p->bias[2]; L.Kp = p->dims[2]; L.N = p->dims[3];
-  L.out_hi = nullptr; L.out_lo = nullptr; L.out_stride = 0;
-  L.w_out = p->w_out; L.b_out = p->b_out; L.n_out = p->dims[4]; L.out = out;
-  CUDA_OK(mlp_launch(1, L, dim3(Mp / mlptc::kTile, 1), st));
+  // The rows are cut into chunks of whole 128-row tiles and every chunk runs its own layer 1 -> 2 -> 3 chain on its own
+  // stream: a layer's grid is 2.4 / 1.2 / 0.6 waves of one-CTA-per-SM tiles at the config-5 batch, and with a single chain
+  // every partial wave idles most of the GPU; independent chains let the block scheduler fill those SMs with the next
+  // layer of a chunk that is already done (measured: profiles/README.md).  Fork / join through events, so the whole
+  // forward is still one dependency of `cuda_stream` and can be captured in a CUDA graph.
+  const int m_tiles = Mp / mlptc::kTile;
+  static int pref_chunks = 0;
+  if (!pref_chunks) {
+    const char* e = std::getenv("SPI_B200_MLP_CHUNKS");
+    pref_chunks = e ? std::atoi(e) : 2;
+    if (pref_chunks < 1) pref_chunks = 1;
+    if (pref_chunks > spi_b200_policy::kMaxChunks) pref_chunks = spi_b200_policy::kMaxChunks;
+  }
+  const int n_chunks = (m_tiles >= 8 * pref_chunks) ? pref_chunks : 1;     // small batches: one chain
+  if (n_chunks > 1 && !p->streams_ready) {
+    for (int i = 0; i < spi_b200_policy::kMaxChunks - 1; i++) {
+      CUDA_OK(cudaStreamCreateWithFlags(&p->side[i], cudaStreamNonBlocking));
+      CUDA_OK(cudaEventCreateWithFlags(&p->join[i], cudaEventDisableTiming));
+    }
+    CUDA_OK(cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming));
+    p->streams_ready = true;
+  }
+  if (n_chunks > 1) CUDA_OK(cudaEventRecord(p->fork, st));
+  for (int c = 0; c < n_chunks; c++) {
+    const int t0 = (int)((long long)m_tiles * c / n_chunks), t1 = (int)((long long)m_tiles * (c + 1) / n_chunks);
+    const int tiles = t1 - t0, row0 = t0 * mlptc::kTile;
+    if (tiles <= 0 || row0 >= M) continue;
+    cudaStream_t cs = (c == 0) ? st : p->side[c - 1];
+    if (c > 0) CUDA_OK(cudaStreamWaitEvent(cs, p->fork, 0));
+    const size_t in_off = (size_t)t0 * (size_t)(p->Kp / 32) * tiled::kTileFloats;
+    const size_t h1_off = (size_t)t0 * (size_t)(p->dims[1] / 32) * tiled::kTileFloats;
+    const size_t h2_off = (size_t)t0 * (size_t)(p->dims[2] / 32) * tiled::kTileFloats;
+    mlptc::LayerArgs L;
+    std::memset(&L, 0, sizeof(L));
+    // layer 1
+    L.a_hi = x_hi + in_off; L.a_lo = x_lo + in_off; L.w_hi = p->w_hi[0]; L.w_lo = p->w_lo[0]; L.bias = p->bias[0];
+    L.Kp = p->Kp; L.N = p->dims[1];
+    L.out_hi = p->act[0] + h1_off; L.out_lo = p->act[1] + h1_off; L.out_stride = p->dims[1]; L.M = M - row0;
+    if (ring) { L.w_hi = p->ring_hi; L.w_lo = p->ring_lo; L.rot = rot_dev; L.rot_stride = p->rot_stride; L.n_rot = p->n_rot; }
+    CUDA_OK(mlp_launch(0, 0, L, dim3(tiles, p->dims[1] / mlptc::kTile), cs));
+    if (int rc = check_launch("mlp_layer_kernel<0> (layer 1)")) return rc;
+    // layer 2
+    L.rot = nullptr; L.rot_stride = 0; L.n_rot = 0;
+    L.a_hi = p->act[0] + h1_off; L.a_lo = p->act[1] + h1_off; L.w_hi = p->w_hi[1]; L.w_lo = p->w_lo[1]; L.bias = p->bias[1];
+    L.Kp = p->dims[1]; L.N = p->dims[2];
+    L.out_hi = p->act[2] + h2_off; L.out_lo = p->act[3] + h2_off; L.out_stride = p->dims[2];
+    CUDA_OK(mlp_launch(0, 1, L, dim3(tiles, p->dims[2] / mlptc::kTile), cs));
+    if (int rc = check_launch("mlp_layer_kernel<0> (layer 2)")) return rc;
+    // layer 3 + output layer
+    L.a_hi = p->act[2] + h2_off; L.a_lo = p->act[3] + h2_off; L.w_hi = p->w_hi[2]; L.w_lo = p->w_lo[2]; L.bias = p->bias[2];
+    L.Kp = p->dims[2]; L.N = p->dims[3];
+    L.out_hi = nullptr; L.out_lo = nullptr; L.out_stride = 0;
+    L.w_out = p->w_out; L.b_out = p->b_out; L.n_out = p->dims[4]; L.out = out + (size_t)row0 * p->dims[4];
+    CUDA_OK(mlp_launch(1, 2, L, dim3(tiles, 1), cs));
+    if (int rc = check_launch("mlp_layer_kernel<1> (layers 3 + 4)")) return rc;
+    if (c > 0) {
+      CUDA_OK(cudaEventRecord(p->join[c - 1], cs));
+      CUDA_OK(cudaStreamWaitEvent(st, p->join[c - 1], 0));
+    }
+  }
   if (std::getenv("SPI_B200_MLP_STAMPS")) {   // development only
     unsigned long long h[3][8];
     cudaStreamSynchronize(st);
