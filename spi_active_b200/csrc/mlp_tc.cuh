@@ -40,9 +40,9 @@ constexpr int kStages = 3;
 constexpr int kOperandBytes = kTile * kBK * 4;               // 16 KB = one tile of tiled_layout.cuh
 constexpr int kStageBytes = 4 * kOperandBytes;               // A_hi, A_lo, W_hi, W_lo
 constexpr int kMaxOut = 16;
-// shared-memory tail behind the stages: barriers + TMEM slot (256 B) | bias of this n-tile (512 B) | output layer: weights
-// [kMaxOut][128] (8 KB) + bias (64 B)
-constexpr int kTailBias = 256, kTailWout = kTailBias + 512, kTailBout = kTailWout + kMaxOut * kTile * 4;
+// shared-memory tail behind the stages: barriers + TMEM slot (256 B) | bias of this n-tile (<= 256 floats) | output layer:
+// weights [kMaxOut][128] (8 KB) + bias (64 B)
+constexpr int kTailBias = 256, kTailWout = kTailBias + 1024, kTailBout = kTailWout + kMaxOut * kTile * 4;
 constexpr int kSmemBytes = kStages * kStageBytes + kTailBout + 64;
 // k-blocks per accumulator group: the tensor core's accumulation truncates (a ~3e-8 relative bias per MMA), so an
 // accumulator only ever holds 48 MMAs before it is added to the fp32 running sums in registers
@@ -165,51 +165,59 @@ struct LayerArgs {
   const int* rot; size_t rot_stride; int n_rot;   // device int selecting one of n_rot weight copies rot_stride floats apart, or null
   int stamp;    // development only: row of g_stamps, or -1
   int dbg;      // development only (SPI_B200_MLP_DBG): 1 = issue no MMAs, 2 = copy no operands — timing experiments, results are garbage
-  int cx, cy;   // thread-block cluster shape (x: CTAs that share an n-tile = the W operand, y: CTAs that share an m-tile = A)
 };
 
-// One 128 x 128 tile of  A W^T  per CTA;  grid = (Mp / 128, N / 128).  Warp-specialised, no CTA-wide barrier in the loop:
-//   producer (1 lane)     wait empty[s] -> expect_tx(64 KB) -> 4 x cp.async.bulk of one contiguous 16 KB tile each -> full[s]
-//   MMA issuer (1 lane)   wait full[s] -> 12 x tcgen05.mma (4 k-steps x {lo.hi, hi.lo, hi.hi}) -> tcgen05.commit -> empty[s]
-//                         (+ accfull at the end of a group of 4 blocks; waits accempty before it reuses an accumulator)
-//   promotion (128 thr)   wait accfull -> tcgen05.ld -> fp32 add into registers -> arrive accempty;  then the epilogue
-template <int MODE>
+// One 128 x BN tile of  A W^T  per CTA (BN = 256 for the wide layers, 128 otherwise);  grid = (Mp / 128, N / BN).
+// Warp-specialised, no CTA-wide barrier in the loop:
+//   producer (1 lane)     wait empty[s] -> expect_tx -> cp.async.bulk of contiguous 16 KB tiles (a_hi, a_lo, BN / 128 x w_hi,
+//                         BN / 128 x w_lo) -> full[s]
+//   MMA issuer (1 lane)   wait full[s] -> per k-step of 8:  BN = 256: a_hi w_hi, a_hi w_lo, a_lo w_hi as three N = 256 MMAs;
+//                         BN = 128: a_hi [w_hi; w_lo] as ONE N = 256 MMA + a_lo w_hi at N = 128 (the halves are added in
+//                         the promotion) -> tcgen05.commit -> empty[s]  (+ accfull at the end of a group of k-blocks;
+//                         waits accempty before it reuses an accumulator)
+//   promotion (256 thr)   wait accfull -> tcgen05.ld -> fp32 add into registers -> arrive accempty;  then the epilogue
+// What bounds the loop (measured, profiles/README.md): L2 -> SM operand bytes at the chip-wide L2 throughput when every SM
+// streams, then the shared-memory reads of the SS-mode MMAs; BN = 256 moves 25 % fewer bytes per flop than BN = 128.
+template <int BN> struct Cfg {
+  static constexpr int kWTiles = BN / kTile;                                  // 16 KB tiles per W operand and k-block
+  static constexpr int kStageBytes = (2 + 2 * kWTiles) * kOperandBytes;       // a_hi, a_lo, w_hi[..], w_lo[..]
+  static constexpr int kStages = (BN == 256) ? 2 : 3;                         // 192 KB of stages either way
+  static constexpr int kCols = BN / 2;                                        // output columns per epilogue thread
+};
+static_assert(Cfg<128>::kStages * Cfg<128>::kStageBytes == kStages * kStageBytes, "stage budget");
+static_assert(Cfg<256>::kStages * Cfg<256>::kStageBytes == kStages * kStageBytes, "stage budget");
+
+template <int MODE, int BN>
 __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs L) {
   using namespace fimtc;
+  using C = Cfg<BN>;
+  static_assert(MODE == 0 || BN == kTile, "the fused output layer needs the whole hidden layer in one 128-wide tile");
+  constexpr int kS = C::kStages, kSB = C::kStageBytes, kWT = C::kWTiles, kNC = C::kCols;
   extern __shared__ __align__(1024) unsigned char smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);   // [kStages] producer -> MMA
-  uint64_t* empty = full + kStages;                                             // [kStages] MMA -> producer
-  uint64_t* accfull = empty + kStages;                                          // [2] MMA -> promotion
-  uint64_t* accempty = accfull + 2;                                             // [2] promotion -> MMA
+  unsigned char* tail = smem + kStages * kStageBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);      // [kS] producer -> MMA
+  uint64_t* empty = full + 3;                              // [kS] MMA -> producer
+  uint64_t* accfull = empty + 3;                           // [2] MMA -> promotion
+  uint64_t* accempty = accfull + 2;                        // [2] promotion -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * kTile, n0 = blockIdx.y * kTile;
+  const int m0 = blockIdx.x * kTile, n0 = blockIdx.y * BN;
   MLP_STAMP(0);
 
-  float* bias_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + kTailBias);     // [128] bias of this n-tile
-  float* wout_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + kTailWout);     // [n_out][128]
-  float* bout_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + kTailBout);     // [n_out]
+  float* bias_s = reinterpret_cast<float*>(tail + kTailBias);     // [BN] bias of this n-tile
+  float* wout_s = reinterpret_cast<float*>(tail + kTailWout);     // [n_out][128]
+  float* bout_s = reinterpret_cast<float*>(tail + kTailBout);     // [n_out]
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // Cluster (cx, cy): the cy CTAs of a cluster column share the m-tile, the cx CTAs of a cluster row share the n-tile.  Each CTA
-  // fetches 1 / cy of the A tiles and 1 / cx of the W tiles and multicasts the slice to the CTAs that need it, so every operand
-  // byte leaves L2 once per cluster instead of once per CTA.  A stage may be refilled once every CTA this one writes into has
-  // consumed it: the MMA issuers multicast their tcgen05.commit to the empty barriers of exactly those CTAs.
-  const bool clustered = L.cx * L.cy > 1;
-  const uint32_t ccx = clustered ? cluster_ctaid_x() : 0u, ccy = clustered ? cluster_ctaid_y() : 0u;
-  uint16_t mask_a = 0, mask_w = 0;      // CTA ranks (x fastest) that share this CTA's A / W tile
-  for (int j = 0; j < L.cy; j++) mask_a |= (uint16_t)(1u << (ccx + (uint32_t)j * L.cx));
-  for (int i = 0; i < L.cx; i++) mask_w |= (uint16_t)(1u << ((uint32_t)i + ccy * L.cx));
   if (tid == 32) {
-    for (int s = 0; s < kStages; s++) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), (uint32_t)(L.cx + L.cy - 1)); }
+    for (int s = 0; s < kS; s++) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
     for (int a = 0; a < 2; a++) { mbar_init(smem_u32(accfull + a), 1); mbar_init(smem_u32(accempty + a), kEpilogue); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (clustered) cluster_sync();        // every peer's barriers exist before anything is multicast to them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *tmem_slot;
   MLP_STAMP(1);
@@ -222,30 +230,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
     if (lane == 0) {
       size_t w_copy = 0;
       if (L.rot) { const int r = *L.rot; w_copy = (size_t)(r < 0 ? 0 : (r >= L.n_rot ? L.n_rot - 1 : r)) * L.rot_stride; }
-      const size_t a_tile = (size_t)blockIdx.x * n_blocks * tiled::kTileFloats,
-                   w_tile = w_copy + (size_t)blockIdx.y * n_blocks * tiled::kTileFloats;
-      const float* src[4] = {L.a_hi + a_tile, L.a_lo + a_tile, L.w_hi + w_tile, L.w_lo + w_tile};
+      const size_t a_tile = (size_t)blockIdx.x * n_blocks * tiled::kTileFloats;
+      const size_t w_tile = w_copy + (size_t)blockIdx.y * kWT * n_blocks * tiled::kTileFloats;   // first of kWT 128-row tiles
       for (int kb = 0; kb < n_blocks; kb++) {
-        const int s = kb % kStages;
-        if (kb >= kStages) mbar_wait(smem_u32(empty + s), (uint32_t)((kb / kStages - 1) & 1));
-        const uint32_t bar = smem_u32(full + s), stage = smem_base + (uint32_t)s * kStageBytes;
+        const int s = kb % kS;
+        if (kb >= kS) mbar_wait(smem_u32(empty + s), (uint32_t)((kb / kS - 1) & 1));
+        const uint32_t bar = smem_u32(full + s), stage = smem_base + (uint32_t)s * kSB;
         if (L.dbg & 2) { mbar_arrive(bar); continue; }
-        mbar_expect_tx(bar, kStageBytes);
-        if (!clustered) {
+        mbar_expect_tx(bar, kSB);
+        const size_t ko = (size_t)kb * tiled::kTileFloats;
+        bulk_g2s(stage, L.a_hi + a_tile + ko, kOperandBytes, bar);
+        bulk_g2s(stage + kOperandBytes, L.a_lo + a_tile + ko, kOperandBytes, bar);
 #pragma unroll
-          for (int op = 0; op < 4; op++)
-            bulk_g2s(stage + (uint32_t)op * kOperandBytes, src[op] + (size_t)kb * tiled::kTileFloats, kOperandBytes, bar);
-        } else {
-          const uint32_t a_bytes = kOperandBytes / (uint32_t)L.cy, w_bytes = kOperandBytes / (uint32_t)L.cx;
-          const uint32_t a_off = ccy * a_bytes, w_off = ccx * w_bytes;
-#pragma unroll
-          for (int op = 0; op < 2; op++)
-            bulk_g2s_mc(stage + (uint32_t)op * kOperandBytes + a_off, src[op] + (size_t)kb * tiled::kTileFloats + a_off / 4, a_bytes,
-                        bar, mask_a);
-#pragma unroll
-          for (int op = 2; op < 4; op++)
-            bulk_g2s_mc(stage + (uint32_t)op * kOperandBytes + w_off, src[op] + (size_t)kb * tiled::kTileFloats + w_off / 4, w_bytes,
-                        bar, mask_w);
+        for (int t = 0; t < kWT; t++) {
+          const size_t wo = w_tile + (size_t)t * n_blocks * tiled::kTileFloats + ko;
+          bulk_g2s(stage + (uint32_t)(2 + t) * kOperandBytes, L.w_hi + wo, kOperandBytes, bar);
+          bulk_g2s(stage + (uint32_t)(2 + kWT + t) * kOperandBytes, L.w_lo + wo, kOperandBytes, bar);
         }
       }
     }
@@ -253,58 +253,65 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
     // ===== MMA issuer =====
     if (lane == 0) {
       for (int kb = 0; kb < n_blocks; kb++) {
-        const int s = kb % kStages, g = kb / kGroup;
+        const int s = kb % kS, g = kb / kGroup;
         const bool group_start = (kb % kGroup) == 0, group_end = ((kb + 1) % kGroup) == 0 || kb == n_blocks - 1;
         if (group_start && g >= 2) mbar_wait(smem_u32(accempty + (g & 1)), (uint32_t)(((g - 2) >> 1) & 1));
-        mbar_wait(smem_u32(full + s), (uint32_t)((kb / kStages) & 1));
+        mbar_wait(smem_u32(full + s), (uint32_t)((kb / kS) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t stage = smem_base + (uint32_t)s * kStageBytes;
-        // the W_hi and W_lo tiles of a stage are adjacent, i.e. ONE 256-row K-major operand [W_hi; W_lo]: a_hi meets both in a
-        // single N = 256 MMA (columns [0,128) += a_hi w_hi, [128,256) += a_hi w_lo), a_lo w_hi goes into the first half with an
-        // N = 128 MMA.  Same tensor-pipe time as three N = 128 MMAs, but a_hi is read from shared memory once instead of
-        // twice — and shared-memory bandwidth (MMA operand reads + the copy engine's writes) is what bounds this loop
+        const uint32_t stage = smem_base + (uint32_t)s * kSB;
+        // a W operand of BN rows = BN / 128 adjacent 16 KB tiles (8-row groups 1024 bytes apart throughout); for BN = 128 the
+        // w_hi and w_lo tiles are adjacent too, i.e. ONE 256-row operand [w_hi; w_lo]
         const uint64_t ah = make_desc_sw128(stage), al = make_desc_sw128(stage + kOperandBytes),
-                       wh = make_desc_sw128(stage + 2 * kOperandBytes);
+                       wh = make_desc_sw128(stage + 2 * kOperandBytes), wl = make_desc_sw128(stage + (2 + kWT) * kOperandBytes);
         const uint32_t tacc = tmem_d + (uint32_t)((g & 1) * kAccCols);
 #pragma unroll
         for (int k = 0; k < kBK / 8; k++) {
           if (L.dbg & 1) break;
           const uint64_t off = (uint64_t)(k * 2);     // 32 bytes >> 4, inside the 14-bit start-address field
-          mma_tf32_n(tacc, ah + off, wh + off, idesc_tf32(2 * kTile), (!group_start || k > 0) ? 1u : 0u);
-          mma_tf32_n(tacc, al + off, wh + off, idesc_tf32(kTile), 1u);
+          const uint32_t first = (!group_start || k > 0) ? 1u : 0u;
+          if (BN == 256) {
+            mma_tf32_n(tacc, al + off, wh + off, idesc_tf32(256), first);
+            mma_tf32_n(tacc, ah + off, wl + off, idesc_tf32(256), 1u);
+            mma_tf32_n(tacc, ah + off, wh + off, idesc_tf32(256), 1u);
+          } else {
+            mma_tf32_n(tacc, ah + off, wh + off, idesc_tf32(256), first);   // [0,128) += a_hi w_hi, [128,256) += a_hi w_lo
+            mma_tf32_n(tacc, al + off, wh + off, idesc_tf32(128), 1u);      // [0,128) += a_lo w_hi
+          }
         }
-        if (clustered) umma_commit_mc(smem_u32(empty + s), (uint16_t)(mask_a | mask_w));
-        else umma_commit(smem_u32(empty + s));
+        umma_commit(smem_u32(empty + s));
         if (group_end) umma_commit(smem_u32(accfull + (g & 1)));
       }
     }
   } else {
-    // ===== promotion + epilogue: thread = (row, column half) =====
+    // ===== promotion + epilogue: thread = (row, column set) =====
+    // BN = 128: thread (q, hf) owns output columns 64 hf + [0, 64) and adds the two accumulator halves;
+    // BN = 256: it owns columns 64 hf + [0, 64) of BOTH 128-column halves of the tile (so that each half of the output can
+    //           be staged in shared memory by all 256 threads), held as acc[half * 64 + i]
     const int q = warp & 3, hf = warp >> 2;
     const int r = q * 32 + lane;                     // row of the tile = TMEM lane
-    const int c0 = hf * kHalfCols;                   // first column of this thread
+    const int c0 = hf * kHalfCols;
     // epilogue constants, fetched while the pipeline fills (ordered before their use by the epilogue barrier below)
-    for (int i = tid; i < kTile; i += kEpilogue) bias_s[i] = __ldg(L.bias + n0 + i);
+    for (int i = tid; i < BN; i += kEpilogue) bias_s[i] = __ldg(L.bias + n0 + i);
     if (MODE == 1) {
       for (int i = tid; i < L.n_out * kTile; i += kEpilogue) wout_s[i] = __ldg(L.w_out + i);
       for (int i = tid; i < L.n_out; i += kEpilogue) bout_s[i] = __ldg(L.b_out + i);
     }
     epi_barrier();
-    float acc[kHalfCols];
+    float acc[kNC];
 #pragma unroll
-    for (int i = 0; i < kHalfCols; i++) acc[i] = 0.f;
+    for (int i = 0; i < kNC; i++) acc[i] = 0.f;
     for (int g = 0; g < n_groups; g++) {   // acc += accumulator of group g, then hand the accumulator back to the MMA warp
       mbar_wait(smem_u32(accfull + (g & 1)), (uint32_t)((g >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-      for (int cb = 0; cb < 2 * (kHalfCols / 32); cb++) {     // both halves of the accumulator (hi.hi + lo.hi, then hi.lo)
+      for (int cb = 0; cb < 4; cb++) {     // 2 halves x 2 x 32 columns
         if (L.dbg & 4) break;
         uint32_t v[32];
-        const int half = cb / (kHalfCols / 32), sub = cb % (kHalfCols / 32);
+        const int half = cb >> 1, sub = cb & 1;
         tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((g & 1) * kAccCols + half * kTile + c0 + sub * 32), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < 32; i++) acc[sub * 32 + i] += __uint_as_float(v[i]);
+        for (int i = 0; i < 32; i++) acc[(BN == 256 ? half * kHalfCols : 0) + sub * 32 + i] += __uint_as_float(v[i]);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(smem_u32(accempty + (g & 1)));
@@ -312,34 +319,39 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
     MLP_STAMP(2);
     // every MMA has retired (the last accfull arrived) and every copy has landed: the stages are free
     if (MODE == 0) {
-      // ELU(acc + b) -> tf32 hi / lo, written as the next layer's operand tiles (tiled_layout.cuh): the 128 x 128 output is
+      // ELU(acc + b) -> tf32 hi / lo, written as the next layer's operand tiles (tiled_layout.cuh): 128 output columns are
       // 4 k-blocks x {hi, lo} = 8 tiles of 16 KB, assembled in shared memory and stored with 8 contiguous bulk copies
 #pragma unroll
-      for (int i = 0; i < kHalfCols; i += 4) {
-        const int col = c0 + i;
-        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col);
-        const float h0 = elu(acc[i] + b4.x), h1 = elu(acc[i + 1] + b4.y), h2 = elu(acc[i + 2] + b4.z), h3 = elu(acc[i + 3] + b4.w);
-        float4 vh, vl;
-        vh.x = tf32_round(h0); vl.x = h0 - vh.x;
-        vh.y = tf32_round(h1); vl.y = h1 - vh.y;
-        vh.z = tf32_round(h2); vl.z = h2 - vh.z;
-        vh.w = tf32_round(h3); vl.w = h3 - vh.w;
-        const int ob = col >> 5, ch = (col & 31) >> 2;
-        unsigned char* dst = smem + ob * kOperandBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4);
-        *reinterpret_cast<float4*>(dst) = vh;
-        *reinterpret_cast<float4*>(dst + 4 * kOperandBytes) = vl;
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the bulk-copy engine
-      epi_barrier();
-      MLP_STAMP(5);
-      if (tid == 0) {
-        const size_t t0 = ((size_t)blockIdx.x * (size_t)(L.out_stride >> 5) + (size_t)(n0 >> 5)) * tiled::kTileFloats;
+      for (int half = 0; half < BN / kTile; half++) {
+        if (half > 0) epi_barrier();                 // the previous half has left shared memory (tid 0 waited for the reads)
 #pragma unroll
-        for (int ob = 0; ob < 4; ob++) {
-          bulk_s2g(L.out_hi + t0 + (size_t)ob * tiled::kTileFloats, smem_base + (uint32_t)ob * kOperandBytes, kOperandBytes);
-          bulk_s2g(L.out_lo + t0 + (size_t)ob * tiled::kTileFloats, smem_base + (uint32_t)(4 + ob) * kOperandBytes, kOperandBytes);
+        for (int i = 0; i < kHalfCols; i += 4) {
+          const int col = c0 + i;                    // within this 128-column half
+          const float* a = acc + half * kHalfCols + i;
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + half * kTile + col);
+          const float h0 = elu(a[0] + b4.x), h1 = elu(a[1] + b4.y), h2 = elu(a[2] + b4.z), h3 = elu(a[3] + b4.w);
+          float4 vh, vl;
+          vh.x = tf32_round(h0); vl.x = h0 - vh.x;
+          vh.y = tf32_round(h1); vl.y = h1 - vh.y;
+          vh.z = tf32_round(h2); vl.z = h2 - vh.z;
+          vh.w = tf32_round(h3); vl.w = h3 - vh.w;
+          const int ob = col >> 5, ch = (col & 31) >> 2;
+          unsigned char* dst = smem + ob * kOperandBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4);
+          *reinterpret_cast<float4*>(dst) = vh;
+          *reinterpret_cast<float4*>(dst + 4 * kOperandBytes) = vl;
         }
-        bulk_commit_wait_read();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the bulk-copy engine
+        epi_barrier();
+        if (half == 0) MLP_STAMP(5);
+        if (tid == 0) {
+          const size_t t0 = ((size_t)blockIdx.x * (size_t)(L.out_stride >> 5) + (size_t)((n0 + half * kTile) >> 5)) * tiled::kTileFloats;
+#pragma unroll
+          for (int ob = 0; ob < 4; ob++) {
+            bulk_s2g(L.out_hi + t0 + (size_t)ob * tiled::kTileFloats, smem_base + (uint32_t)ob * kOperandBytes, kOperandBytes);
+            bulk_s2g(L.out_lo + t0 + (size_t)ob * tiled::kTileFloats, smem_base + (uint32_t)(4 + ob) * kOperandBytes, kOperandBytes);
+          }
+          bulk_commit_wait_read();
+        }
       }
     } else {
       // last hidden layer (one n-tile) + the output layer: y[j] = b_out[j] + sum_i w_out[j][i] ELU(acc[i] + b[i]); each thread
@@ -380,7 +392,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   MLP_STAMP(4);
-  if (clustered) cluster_sync();        // no peer still signals this CTA's barriers when it exits
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
 }
 

@@ -1014,50 +1014,34 @@ static void policy_free(spi_b200_policy* p) {
 }
 
 static cudaError_t mlp_set_attributes() {
-  cudaError_t e = cudaFuncSetAttribute(mlptc::mlp_layer_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlptc::kSmemBytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlptc::mlp_layer_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlptc::kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(mlptc::mlp_layer_kernel<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlptc::kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlptc::mlp_layer_kernel<0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlptc::kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlptc::mlp_layer_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlptc::kSmemBytes);
   return e;
 }
-// Thread-block cluster shape of a layer launch: the largest (cx, cy) <= the preferred shape that divides the grid.
-// SPI_B200_MLP_CLUSTER="cx,cy" overrides the preference (development knob for the measurements in profiles/README.md).
-static void mlp_cluster_shape(dim3 grid, int* cx, int* cy) {
-  static int pref_x = 0, pref_y = 0;
-  if (!pref_x) {
-    int x = 1, y = 1;   // measured on B200: multicast clusters (2,1) .. (2,4) change nothing (the main loop is shared-memory bound)
-    if (const char* e = std::getenv("SPI_B200_MLP_CLUSTER")) {
-      int a = 0, b = 0;
-      if (std::sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && b >= 1 && a * b <= 8) { x = a; y = b; }
-    }
-    pref_y = y; pref_x = x;
-  }
-  int x = pref_x, y = pref_y;
-  while (x > 1 && (grid.x % x || mlptc::kOperandBytes % x)) x >>= 1;
-  while (y > 1 && (grid.y % y || mlptc::kOperandBytes % y)) y >>= 1;
-  *cx = x < 1 ? 1 : x; *cy = y < 1 ? 1 : y;
-}
 
-static cudaError_t mlp_launch(int mode, int layer, mlptc::LayerArgs L, dim3 grid, cudaStream_t st) {
-  mlp_cluster_shape(grid, &L.cx, &L.cy);
-  static int dbg = -1, layers = 7;
-  if (dbg < 0) {
+// mode 0: hidden layer -> split activations (128 x 256 tiles when the width allows, else 128 x 128); mode 1: last hidden
+// layer + output layer.  `layer` only labels the development timestamps.
+static cudaError_t mlp_launch(int mode, int layer, mlptc::LayerArgs L, int m_tiles, cudaStream_t st) {
+  static int dbg = -1, layers = 7, stamps = 0, wide = 0;
+  if (dbg < 0) {   // development knobs (profiles/README.md)
     const char* e = std::getenv("SPI_B200_MLP_DBG"); dbg = e ? std::atoi(e) : 0;
     const char* l = std::getenv("SPI_B200_MLP_LAYERS"); layers = l ? std::atoi(l) : 7;
+    // 128 x 256 tiles: 25 % fewer operand bytes per flop but only 2 pipeline stages fit -> measured SLOWER (0.138 vs 0.112 ms)
+    const char* w = std::getenv("SPI_B200_MLP_WIDE"); wide = w ? std::atoi(w) : 0;
+    stamps = std::getenv("SPI_B200_MLP_STAMPS") ? 1 : 0;
   }
   L.dbg = dbg;
-  static int stamps = -1;
-  if (stamps < 0) stamps = std::getenv("SPI_B200_MLP_STAMPS") ? 1 : 0;
-  const int this_layer = layer;
-  if (!((layers >> this_layer) & 1)) return cudaSuccess;
-  L.stamp = stamps ? this_layer : -1;
-  cudaLaunchConfig_t cfg;
-  std::memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = grid; cfg.blockDim = dim3(mlptc::kThreads); cfg.dynamicSmemBytes = mlptc::kSmemBytes; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)L.cx; attr[0].val.clusterDim.y = (unsigned)L.cy; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  if (mode == 0) return cudaLaunchKernelEx(&cfg, mlptc::mlp_layer_kernel<0>, L);
-  return cudaLaunchKernelEx(&cfg, mlptc::mlp_layer_kernel<1>, L);
+  if (!((layers >> layer) & 1)) return cudaSuccess;
+  L.stamp = stamps ? layer : -1;
+  if (mode == 1) {
+    mlptc::mlp_layer_kernel<1, 128><<<dim3(m_tiles, 1), mlptc::kThreads, mlptc::kSmemBytes, st>>>(L);
+  } else if (wide && L.N % 256 == 0) {
+    mlptc::mlp_layer_kernel<0, 256><<<dim3(m_tiles, L.N / 256), mlptc::kThreads, mlptc::kSmemBytes, st>>>(L);
+  } else {
+    mlptc::mlp_layer_kernel<0, 128><<<dim3(m_tiles, L.N / 128), mlptc::kThreads, mlptc::kSmemBytes, st>>>(L);
+  }
+  return cudaGetLastError();
 }
 
 static float tf32_rna_host(float x) {   // round to nearest, ties away: the value cvt.rna.tf32.f32 produces
@@ -1237,21 +1221,21 @@ static int policy_forward_impl(spi_b200_policy* p, const float* x_hi, const floa
     L.Kp = p->Kp; L.N = p->dims[1];
     L.out_hi = p->act[0] + h1_off; L.out_lo = p->act[1] + h1_off; L.out_stride = p->dims[1]; L.M = M - row0;
     if (ring) { L.w_hi = p->ring_hi; L.w_lo = p->ring_lo; L.rot = rot_dev; L.rot_stride = p->rot_stride; L.n_rot = p->n_rot; }
-    CUDA_OK(mlp_launch(0, 0, L, dim3(tiles, p->dims[1] / mlptc::kTile), cs));
+    CUDA_OK(mlp_launch(0, 0, L, tiles, cs));
     if (int rc = check_launch("mlp_layer_kernel<0> (layer 1)")) return rc;
     // layer 2
     L.rot = nullptr; L.rot_stride = 0; L.n_rot = 0;
     L.a_hi = p->act[0] + h1_off; L.a_lo = p->act[1] + h1_off; L.w_hi = p->w_hi[1]; L.w_lo = p->w_lo[1]; L.bias = p->bias[1];
     L.Kp = p->dims[1]; L.N = p->dims[2];
     L.out_hi = p->act[2] + h2_off; L.out_lo = p->act[3] + h2_off; L.out_stride = p->dims[2];
-    CUDA_OK(mlp_launch(0, 1, L, dim3(tiles, p->dims[2] / mlptc::kTile), cs));
+    CUDA_OK(mlp_launch(0, 1, L, tiles, cs));
     if (int rc = check_launch("mlp_layer_kernel<0> (layer 2)")) return rc;
     // layer 3 + output layer
     L.a_hi = p->act[2] + h2_off; L.a_lo = p->act[3] + h2_off; L.w_hi = p->w_hi[2]; L.w_lo = p->w_lo[2]; L.bias = p->bias[2];
     L.Kp = p->dims[2]; L.N = p->dims[3];
     L.out_hi = nullptr; L.out_lo = nullptr; L.out_stride = 0;
     L.w_out = p->w_out; L.b_out = p->b_out; L.n_out = p->dims[4]; L.out = out + (size_t)row0 * p->dims[4];
-    CUDA_OK(mlp_launch(1, 2, L, dim3(tiles, 1), cs));
+    CUDA_OK(mlp_launch(1, 2, L, tiles, cs));
     if (int rc = check_launch("mlp_layer_kernel<1> (layers 3 + 4)")) return rc;
     if (c > 0) {
       CUDA_OK(cudaEventRecord(p->join[c - 1], cs));
