@@ -32,12 +32,47 @@ struct WsArgs {
   const unsigned char* zero_mask;   // paired mode: [S] 1 = this env's action is replaced by 0 (terminated group), or null
 };
 
+// The roles exchange their per-sub-step data as float4 (LDS.128 / STS.128, lane stride 16 bytes: conflict-free): 7 + 6
+// shared-memory instructions per leg and 28 + 6 + 4 for the base instead of 27 + 22 and 108 + 22 + 12 scalar ones — the
+// exchange was 7 % of all issued instructions of a kernel that is bound by issue slots (profiles/README.md).
+constexpr int kLegVec = (kLegOut + 3) / 4;     // 7: the 27 leg -> base floats, padded
+constexpr int kBcStateVec = 4;                 // R(9) v0(6) pz(1) = logical bc[6 .. 22)
+constexpr int kBcA0Vec = 2;                    // a0(6) + 2 pad   = logical bc[0 .. 6)
 struct WsSmem {
-  float part[4][kLegOut][32];   // leg -> base, per sub-step
-  float bc[kBaseOut][32];       // base -> legs, per sub-step
-  float ej[4][32];              // per-leg squared joint error (end of rollout)
+  float4 part[4][kLegVec][32];                     // leg -> base, per sub-step
+  float4 bc[kBcStateVec + kBcA0Vec][32];           // base -> legs, per sub-step: [0,4) state of the sub-step, [4,6) a0
+  float ej[4][32];                                 // per-leg squared joint error (end of rollout)
   int finite[4][32];
 };
+static_assert(kBaseOut - kBcR == 4 * kBcStateVec && kBcR == 6 && kBcA0 == 0, "bc packing");
+
+// a shared-memory read the scheduler may not move across a barrier or merge with an earlier register copy
+__device__ __forceinline__ float4 ws_lds_volatile(const float4* p) {
+  float4 v;
+  asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ws_load_state(const WsSmem& sm, int lane, float* bc) {     // bc[6 .. 22) <- shared
+#pragma unroll
+  for (int v = 0; v < kBcStateVec; v++) {
+    const float4 t = sm.bc[v][lane];
+    bc[kBcR + 4 * v] = t.x; bc[kBcR + 4 * v + 1] = t.y; bc[kBcR + 4 * v + 2] = t.z; bc[kBcR + 4 * v + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void ws_store_state(WsSmem& sm, int lane, const float* bc) {    // shared <- bc[6 .. 22)
+#pragma unroll
+  for (int v = 0; v < kBcStateVec; v++)
+    sm.bc[v][lane] = make_float4(bc[kBcR + 4 * v], bc[kBcR + 4 * v + 1], bc[kBcR + 4 * v + 2], bc[kBcR + 4 * v + 3]);
+}
+__device__ __forceinline__ void ws_load_a0(const WsSmem& sm, int lane, float* a0) {
+  const float4 t0 = sm.bc[kBcStateVec][lane], t1 = sm.bc[kBcStateVec + 1][lane];
+  a0[0] = t0.x; a0[1] = t0.y; a0[2] = t0.z; a0[3] = t0.w; a0[4] = t1.x; a0[5] = t1.y;
+}
+__device__ __forceinline__ void ws_store_a0(WsSmem& sm, int lane, const float* a0) {
+  sm.bc[kBcStateVec][lane] = make_float4(a0[0], a0[1], a0[2], a0[3]);
+  sm.bc[kBcStateVec + 1][lane] = make_float4(a0[4], a0[5], 0.f, 0.f);
+}
 
 __device__ __forceinline__ bool finite_acc(float acc) { return acc == 0.f; }  // NaN/Inf * 0 = NaN
 
@@ -96,16 +131,16 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, int lan
       leg_torques(S, L, act, s.q, s.qd, kp, kd, motor, A.motor_model, A.flags, tau);
       for (int n = 0; n < S.nsub; n++) {
         float bc[kBaseOut];
-#pragma unroll
-        for (int i = kBcR; i < kBaseOut; i++) bc[i] = sm.bc[i][lane];
-        float out[kLegOut];
+        ws_load_state(sm, lane, bc);
+        float out[4 * kLegVec];
+        out[4 * kLegVec - 1] = 0.f;
         leg_phase1(S, L, bc, s, tau, K, out, nullptr);
 #pragma unroll
-        for (int i = 0; i < kLegOut; i++) sm.part[LEG][i][lane] = out[i];
+        for (int v = 0; v < kLegVec; v++)
+          sm.part[LEG][v][lane] = make_float4(out[4 * v], out[4 * v + 1], out[4 * v + 2], out[4 * v + 3]);
         ws_barrier();   // [A]  leg contributions are in shared memory
         ws_barrier();   // [B1] the base role has published a0
-#pragma unroll
-        for (int i = 0; i < 6; i++) bc[kBcA0 + i] = sm.bc[kBcA0 + i][lane];
+        ws_load_a0(sm, lane, bc + kBcA0);
         leg_phase2(L, bc, K, s, h);
         ws_barrier();   // [B2] the base role has published R / v0 / pz of the new state
       }
@@ -155,8 +190,7 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, int la
 #pragma unroll
   for (int i = 0; i < 6; i++) bc[i] = 0.f;
   base_publish(s, bc);
-#pragma unroll
-  for (int i = kBcR; i < kBaseOut; i++) sm.bc[i][lane] = bc[i];
+  ws_store_state(sm, lane, bc);
   float pb[6];
   base_bias(B, bc, pb);
   ws_barrier();   // [S0]
@@ -165,28 +199,35 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, int la
     for (int d = 0; d < A.decimation; d++) {
       for (int n = 0; n < S.nsub; n++) {
         ws_barrier();   // [A]
-        float legsum[kLegOut];
+        float legsum[4 * kLegVec];
 #pragma unroll
-        for (int i = 0; i < kLegOut; i++)
-          legsum[i] = (sm.part[0][i][lane] + sm.part[1][i][lane]) + (sm.part[2][i][lane] + sm.part[3][i][lane]);
+        for (int v = 0; v < kLegVec; v++) {
+          const float4 p0 = sm.part[0][v][lane], p1 = sm.part[1][v][lane], p2 = sm.part[2][v][lane], p3 = sm.part[3][v][lane];
+          legsum[4 * v] = (p0.x + p1.x) + (p2.x + p3.x);
+          legsum[4 * v + 1] = (p0.y + p1.y) + (p2.y + p3.y);
+          legsum[4 * v + 2] = (p0.z + p1.z) + (p2.z + p3.z);
+          legsum[4 * v + 3] = (p0.w + p1.w) + (p2.w + p3.w);
+        }
         float a0[6];
         base_solve(B, legsum, pb, a0);
-#pragma unroll
-        for (int i = 0; i < 6; i++) sm.bc[kBcA0 + i][lane] = a0[i];
+        ws_store_a0(sm, lane, a0);
         ws_barrier();   // [B1] the legs start their acceleration pass
         // keep the integration BEHIND the barrier: it only needs registers, so ptxas would otherwise schedule it between
         // the a0 stores and the barrier and delay the legs by ~90 instructions.  Reading a0 back from shared memory is a
         // dependency the scheduler cannot move across bar.sync (6 LDS, off the critical path).
-#pragma unroll
-        for (int i = 0; i < 6; i++) a0[i] = *(volatile float*)&sm.bc[kBcA0 + i][lane];
+        {
+          const float4 t0 = ws_lds_volatile(&sm.bc[kBcStateVec][lane]), t1 = ws_lds_volatile(&sm.bc[kBcStateVec + 1][lane]);
+          a0[0] = t0.x; a0[1] = t0.y; a0[2] = t0.z; a0[3] = t0.w; a0[4] = t1.x; a0[5] = t1.y;
+        }
         base_advance(S, a0, s, h, bc);
-#pragma unroll
-        for (int i = kBcR; i < kBaseOut; i++) sm.bc[i][lane] = bc[i];
+        ws_store_state(sm, lane, bc);
         ws_barrier();   // [B2]
         // velocity-product bias of the next sub-step: after the barrier, so that it overlaps the legs' phase 1 instead
         // of delaying their release (re-read through shared memory for the same reason as a0 above)
-#pragma unroll
-        for (int i = kBcV0; i < kBcV0 + 6; i++) bc[i] = *(volatile float*)&sm.bc[i][lane];
+        {                                              // logical bc[15 .. 21) = floats 9 .. 14 of the packed state
+          const float4 t2 = ws_lds_volatile(&sm.bc[2][lane]), t3 = ws_lds_volatile(&sm.bc[3][lane]);
+          bc[kBcV0] = t2.y; bc[kBcV0 + 1] = t2.z; bc[kBcV0 + 2] = t2.w; bc[kBcV0 + 3] = t3.x; bc[kBcV0 + 4] = t3.y; bc[kBcV0 + 5] = t3.z;
+        }
         base_bias(B, bc, pb);
       }
     }
