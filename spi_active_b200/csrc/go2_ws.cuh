@@ -137,6 +137,12 @@ WS_HD void sym_mulv(const float* S, const float* v, float* o) {
   o[1] = S[3] * v[0] + S[1] * v[1] + S[5] * v[2];
   o[2] = S[4] * v[0] + S[5] * v[1] + S[2] * v[2];
 }
+// o += a x b
+WS_HD void add_cross(const float* a, const float* b, float* o) {
+  o[0] = fmaf(a[1], b[2], fmaf(-a[2], b[1], o[0]));
+  o[1] = fmaf(a[2], b[0], fmaf(-a[0], b[2], o[1]));
+  o[2] = fmaf(a[0], b[1], fmaf(-a[1], b[0], o[2]));
+}
 // o += a x r   with r sparse
 template <int MASK> WS_HD void add_cross_ar(const float* a, const float* r, float* o) {
 #pragma unroll
@@ -193,17 +199,17 @@ WS_HD void joint_outward(const Twist& vp, const float* r, float q, float qd, flo
   k.cab = v.a[c] * qd;  k.cac = -(v.a[b] * qd);
   k.clb = v.l[c] * qd;  k.clc = -(v.l[b] * qd);
   // momentum: n = Io w + h x v,  f = m v - h x w ;  pA = [w x n + v x f ; w x f]
-  float n[3], f[3], hv[3], hw[3], t1[3], t2[3];
+  // (cross products that are only ever added to something are accumulated as FMA chains: the kernel is bound by issue
+  // slots, and a separate FMUL / FADD per component costs a slot each)
+  float n[3], f[3], hw[3];
   sym_mulv(Io, v.a, n);
-  cross3(h, v.l, hv);
+  add_cross(h, v.l, n);
   cross3(h, v.a, hw);
 #pragma unroll
-  for (int i = 0; i < 3; i++) { n[i] += hv[i]; f[i] = mass * v.l[i] - hw[i]; }
-  cross3(v.a, n, t1);
-  cross3(v.l, f, t2);
+  for (int i = 0; i < 3; i++) f[i] = mass * v.l[i] - hw[i];
+  cross3(v.a, n, pA.a);
+  add_cross(v.l, f, pA.a);
   cross3(v.a, f, pA.l);
-#pragma unroll
-  for (int i = 0; i < 3; i++) pA.a[i] = t1[i] + t2[i];
 }
 
 // articulated inertia [[I, H], [H^T, M]], I and M symmetric
@@ -224,15 +230,16 @@ struct Proj { float Ibb, Ibc, Icc, Hb[3], Hc[3], Ma[6]; };
 
 // ---- transform a projected inertia + force to the parent and accumulate -------------------------------
 // pa = pA + Ia c + U u / D must be given; IAp / pAp already hold the parent's own inertia / bias force.
-template <int AX, int MASK>
+// PARENT_ZERO: IAp / pAp hold nothing yet (the hip's parent is the base, whose own inertia the base role adds) — the results
+// are assigned instead of added to zeros.
+template <int AX, int MASK, bool PARENT_ZERO = false>
 WS_HD void project_to_parent(const Proj& P, const float* pa_a, const float* pa_l, float cs, float sn, const float* r,
                              ABI& IAp, Twist& pAp) {
   constexpr int a = Ax<AX>::a, b = Ax<AX>::b, c = Ax<AX>::c;
   // rotate the blocks to parent orientation:  X' = R X R^T
-  //   I: only the (b,c) 2x2 block is non-zero
+  //   I: only the (b,c) 2x2 block is non-zero; its second rotation is folded into the accumulation of Ip below
   const float t1 = cs * P.Ibb - sn * P.Ibc, t2 = cs * P.Ibc - sn * P.Icc;
   const float t3 = sn * P.Ibb + cs * P.Ibc, t4 = sn * P.Ibc + cs * P.Icc;
-  const float I2bb = t1 * cs - t2 * sn, I2bc = t1 * sn + t2 * cs, I2cc = t3 * sn + t4 * cs;
   //   H: rows b, c non-zero
   float Xb[3], Xc[3], H2b[3], H2c[3];
 #pragma unroll
@@ -271,11 +278,14 @@ WS_HD void project_to_parent(const Proj& P, const float* pa_a, const float* pa_l
   for (int i = 0; i < 3; i++)
 #pragma unroll
     for (int j = i; j < 3; j++) {
-      // Ip[i][j] = I2[i][j] + (r x H2row_j)_i - (Hprow_i x r)_j
-      float v = 0.f;
-      bool have = false;
+      // Ip[i][j] = parent + I2[i][j] + (r x H2row_j)_i - (Hprow_i x r)_j, one FMA chain starting from the parent's entry
+      // (I2bb = t1 cs - t2 sn, I2bc = t1 sn + t2 cs, I2cc = t3 sn + t4 cs)
+      float v = PARENT_ZERO ? 0.f : IAp.I[sidx(i, j)];
+      bool have = !PARENT_ZERO;
       if (i != a && j != a) {
-        v = (i == b && j == b) ? I2bb : ((i == c && j == c) ? I2cc : I2bc);
+        const float x1 = (i == c && j == c) ? t3 : t1, x2 = (i == c && j == c) ? t4 : t2;
+        const float y1 = (i == b && j == b) ? cs : sn, y2 = (i == b && j == b) ? -sn : cs;     // bb: cs, -sn; bc / cc: sn, cs
+        v = have ? fmaf(x1, y1, fmaf(x2, y2, v)) : fmaf(x1, y1, x2 * y2);
         have = true;
       }
       // (r x x)_i = r[i1] x[i2] - r[i2] x[i1],  x = row j of H2 (zero when j == a)
@@ -294,29 +304,39 @@ WS_HD void project_to_parent(const Proj& P, const float* pa_a, const float* pa_l
           if ((MASK >> j1) & 1) { v = have ? fmaf(Hp[3 * i + j2], r[j1], v) : Hp[3 * i + j2] * r[j1]; have = true; }
         }
       }
-      if (have) IAp.I[sidx(i, j)] += v;
+      if (have) IAp.I[sidx(i, j)] = v;
+      else if (PARENT_ZERO) IAp.I[sidx(i, j)] = 0.f;
     }
 #pragma unroll
   for (int i = 0; i < 3; i++) {
     const bool row_zero = (i == a) && !((MASK >> ((i + 1) % 3)) & 1) && !((MASK >> ((i + 2) % 3)) & 1);
-    if (!row_zero) {
 #pragma unroll
-      for (int j = 0; j < 3; j++) IAp.H[3 * i + j] += Hp[3 * i + j];
+    for (int j = 0; j < 3; j++) {
+      if (PARENT_ZERO) IAp.H[3 * i + j] = row_zero ? 0.f : Hp[3 * i + j];
+      else if (!row_zero) IAp.H[3 * i + j] += Hp[3 * i + j];
     }
   }
 #pragma unroll
-  for (int i = 0; i < 6; i++) IAp.M[i] += M2[i];
-  // force to the parent
-  float fl[3], fa[3];
+  for (int i = 0; i < 6; i++) IAp.M[i] = PARENT_ZERO ? M2[i] : IAp.M[i] + M2[i];
+  // force to the parent: the rotated linear force is needed by itself (r x f), the torque only as a sum
+  float fl[3];
   rot_up<AX>(cs, sn, pa_l, fl);
-  rot_up<AX>(cs, sn, pa_a, fa);
-  add_cross_rf<MASK>(r, fl, fa);
+  if (PARENT_ZERO) {
+    rot_up<AX>(cs, sn, pa_a, pAp.a);
 #pragma unroll
-  for (int i = 0; i < 3; i++) { pAp.a[i] += fa[i]; pAp.l[i] += fl[i]; }
+    for (int i = 0; i < 3; i++) pAp.l[i] = fl[i];
+  } else {
+    pAp.a[a] += pa_a[a];
+    pAp.a[b] = fmaf(cs, pa_a[b], fmaf(-sn, pa_a[c], pAp.a[b]));
+    pAp.a[c] = fmaf(sn, pa_a[b], fmaf(cs, pa_a[c], pAp.a[c]));
+#pragma unroll
+    for (int i = 0; i < 3; i++) pAp.l[i] += fl[i];
+  }
+  add_cross_rf<MASK>(r, fl, pAp.a);
 }
 
 // ---- inward pass for a joint with a state-dependent articulated inertia (hip, thigh) ------------------------
-template <int AX, int MASK>
+template <int AX, int MASK, bool PARENT_ZERO = false>
 WS_HD void joint_inward(const ABI& IA, const Twist& pA, float tau, const float* r, Keep& k, ABI& IAp, Twist& pAp) {
   constexpr int a = Ax<AX>::a, b = Ax<AX>::b, c = Ax<AX>::c;
 #pragma unroll
@@ -348,7 +368,7 @@ WS_HD void joint_inward(const ABI& IA, const Twist& pA, float tau, const float* 
 #pragma unroll
   for (int j = 0; j < 3; j++)
     pa_l[j] = pA.l[j] + P.Hb[j] * k.cab + P.Hc[j] * k.cac + P.Ma[sidx(j, b)] * k.clb + P.Ma[sidx(j, c)] * k.clc + ud * k.Ul[j];
-  project_to_parent<AX, MASK>(P, pa_a, pa_l, k.cs, k.sn, r, IAp, pAp);
+  project_to_parent<AX, MASK, PARENT_ZERO>(P, pa_a, pa_l, k.cs, k.sn, r, IAp, pAp);
 }
 
 // ---- inward pass for the calf (leaf, axis y): the projection is the per-leg constant in LegK -----------------
@@ -462,13 +482,7 @@ WS_HD void leg_phase1(const SimK& S, const LegK& L, const float* bc, const LegSt
   abi_from_rigid(L.m[0], L.h[0], L.Io[0], A1);
   joint_inward<1, kMaskThigh>(A2, p2, tau[1], r1, K.k2, A1, p1);
   Twist p0;
-#pragma unroll
-  for (int i = 0; i < 6; i++) { A0.I[i] = 0.f; A0.M[i] = 0.f; }
-#pragma unroll
-  for (int i = 0; i < 9; i++) A0.H[i] = 0.f;
-#pragma unroll
-  for (int i = 0; i < 3; i++) { p0.a[i] = 0.f; p0.l[i] = 0.f; }
-  joint_inward<0, kMaskHip>(A1, p1, tau[0], r0, K.k1, A0, p0);
+  joint_inward<0, kMaskHip, true>(A1, p1, tau[0], r0, K.k1, A0, p0);
 #pragma unroll
   for (int i = 0; i < 6; i++) { out[i] = A0.I[i]; out[15 + i] = A0.M[i]; }
 #pragma unroll
