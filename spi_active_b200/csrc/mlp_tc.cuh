@@ -88,26 +88,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
-// the same copy delivered to the same CTA-relative offset (data and mbarrier) of every CTA in cta_mask
-__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-      "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
-      : "memory");
-}
-// tcgen05.commit whose mbarrier arrive is delivered to the same barrier of every CTA in cta_mask
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(cta_mask)
-               : "memory");
-}
-__device__ __forceinline__ void cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctaid_x() { uint32_t v; asm volatile("mov.u32 %0, %%cluster_ctaid.x;" : "=r"(v)); return v; }
-__device__ __forceinline__ uint32_t cluster_ctaid_y() { uint32_t v; asm volatile("mov.u32 %0, %%cluster_ctaid.y;" : "=r"(v)); return v; }
-
 // TMA 1-D bulk copy shared -> global (bulk-group completion)
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
@@ -149,11 +129,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 
-// development only: in-kernel timestamps of CTA (0, 0) (globaltimer ns): 0 start, 1 set-up done, 2 accumulators promoted
-// (= main loop done), 3 epilogue done, 4 exit; printed by spi_b200_policy_forward when SPI_B200_MLP_STAMPS is set
+// Development instrumentation, compiled in only with -DSPI_B200_MLP_DEV (tools/ and profiles/README.md r1_d): in-kernel
+// timestamps of CTA (0, 0) (globaltimer ns: 0 start, 1 set-up done, 2 accumulators promoted = main loop done, 5 epilogue
+// computed, 3 epilogue done, 4 exit) and the isolation switches L.dbg (bit 0: issue no MMAs, bit 1: copy no operands,
+// bit 2: no accumulator promotion — results are garbage, only the timing means something).
+#if defined(SPI_B200_MLP_DEV)
 __device__ unsigned long long g_stamps[3][8];
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define MLP_STAMP(i) do { if (L.stamp >= 0 && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) g_stamps[L.stamp][i] = gtimer(); } while (0)
+#define MLP_DBG(bit) (L.dbg & (bit))
+#else
+#define MLP_STAMP(i) do { } while (0)
+#define MLP_DBG(bit) 0
+#endif
 
 struct LayerArgs {
   const float* a_hi; const float* a_lo;    // [Mp, Kp] activations, split, tiled_layout.cuh
@@ -163,8 +151,7 @@ struct LayerArgs {
   float* out_hi; float* out_lo; int out_stride;   // MODE 0: ELU(a w^T + b) split, tiled [Mp, out_stride]
   const float* w_out; const float* b_out; int n_out; float* out; int M;   // MODE 1: + output layer -> out [M, n_out]
   const int* rot; size_t rot_stride; int n_rot;   // device int selecting one of n_rot weight copies rot_stride floats apart, or null
-  int stamp;    // development only: row of g_stamps, or -1
-  int dbg;      // development only (SPI_B200_MLP_DBG): 1 = issue no MMAs, 2 = copy no operands — timing experiments, results are garbage
+  int stamp, dbg;   // development instrumentation (SPI_B200_MLP_DEV builds only)
 };
 
 // One 128 x BN tile of  A W^T  per CTA (BN = 256 for the wide layers, 128 otherwise);  grid = (Mp / 128, N / BN).
@@ -236,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
         const int s = kb % kS;
         if (kb >= kS) mbar_wait(smem_u32(empty + s), (uint32_t)((kb / kS - 1) & 1));
         const uint32_t bar = smem_u32(full + s), stage = smem_base + (uint32_t)s * kSB;
-        if (L.dbg & 2) { mbar_arrive(bar); continue; }
+        if (MLP_DBG(2)) { mbar_arrive(bar); continue; }
         mbar_expect_tx(bar, kSB);
         const size_t ko = (size_t)kb * tiled::kTileFloats;
         bulk_g2s(stage, L.a_hi + a_tile + ko, kOperandBytes, bar);
@@ -266,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
         const uint32_t tacc = tmem_d + (uint32_t)((g & 1) * kAccCols);
 #pragma unroll
         for (int k = 0; k < kBK / 8; k++) {
-          if (L.dbg & 1) break;
+          if (MLP_DBG(1)) break;
           const uint64_t off = (uint64_t)(k * 2);     // 32 bytes >> 4, inside the 14-bit start-address field
           const uint32_t first = (!group_start || k > 0) ? 1u : 0u;
           if (BN == 256) {
@@ -305,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int cb = 0; cb < 4; cb++) {     // 2 halves x 2 x 32 columns
-        if (L.dbg & 4) break;
+        if (MLP_DBG(4)) break;
         uint32_t v[32];
         const int half = cb >> 1, sub = cb & 1;
         tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((g & 1) * kAccCols + half * kTile + c0 + sub * 32), v);

@@ -1023,17 +1023,27 @@ static cudaError_t mlp_set_attributes() {
 // mode 0: hidden layer -> split activations (128 x 256 tiles when the width allows, else 128 x 128); mode 1: last hidden
 // layer + output layer.  `layer` only labels the development timestamps.
 static cudaError_t mlp_launch(int mode, int layer, mlptc::LayerArgs L, int m_tiles, cudaStream_t st) {
-  static int dbg = -1, layers = 7, stamps = 0, wide = 0;
-  if (dbg < 0) {   // development knobs (profiles/README.md)
-    const char* e = std::getenv("SPI_B200_MLP_DBG"); dbg = e ? std::atoi(e) : 0;
-    const char* l = std::getenv("SPI_B200_MLP_LAYERS"); layers = l ? std::atoi(l) : 7;
+  static int wide = -1;
+  if (wide < 0) {
     // 128 x 256 tiles: 25 % fewer operand bytes per flop but only 2 pipeline stages fit -> measured SLOWER (0.138 vs 0.112 ms)
     const char* w = std::getenv("SPI_B200_MLP_WIDE"); wide = w ? std::atoi(w) : 0;
-    stamps = std::getenv("SPI_B200_MLP_STAMPS") ? 1 : 0;
   }
-  L.dbg = dbg;
-  if (!((layers >> layer) & 1)) return cudaSuccess;
-  L.stamp = stamps ? layer : -1;
+  L.dbg = 0; L.stamp = -1;
+#if defined(SPI_B200_MLP_DEV)
+  {
+    static int dbg = -1, layers = 7, stamps = 0;
+    if (dbg < 0) {
+      const char* e = std::getenv("SPI_B200_MLP_DBG"); dbg = e ? std::atoi(e) : 0;
+      const char* l = std::getenv("SPI_B200_MLP_LAYERS"); layers = l ? std::atoi(l) : 7;
+      stamps = std::getenv("SPI_B200_MLP_STAMPS") ? 1 : 0;
+    }
+    L.dbg = dbg;
+    if (!((layers >> layer) & 1)) return cudaSuccess;
+    L.stamp = stamps ? layer : -1;
+  }
+#else
+  (void)layer;
+#endif
   if (mode == 1) {
     mlptc::mlp_layer_kernel<1, 128><<<dim3(m_tiles, 1), mlptc::kThreads, mlptc::kSmemBytes, st>>>(L);
   } else if (wide && L.N % 256 == 0) {
@@ -1242,7 +1252,8 @@ static int policy_forward_impl(spi_b200_policy* p, const float* x_hi, const floa
       CUDA_OK(cudaStreamWaitEvent(st, p->join[c - 1], 0));
     }
   }
-  if (std::getenv("SPI_B200_MLP_STAMPS")) {   // development only
+#if defined(SPI_B200_MLP_DEV)
+  if (std::getenv("SPI_B200_MLP_STAMPS")) {
     unsigned long long h[3][8];
     cudaStreamSynchronize(st);
     cudaMemcpyFromSymbol(h, mlptc::g_stamps, sizeof(h));
@@ -1250,6 +1261,7 @@ static int policy_forward_impl(spi_b200_policy* p, const float* x_hi, const floa
       std::fprintf(stderr, "[mlp stamps] layer %d: setup %llu  mainloop %llu  epilogue %llu (compute %llu)  exit %llu  | start-to-next-start %lld ns\n", l + 1,
                    h[l][1] - h[l][0], h[l][2] - h[l][1], h[l][3] - h[l][2], h[l][5] - h[l][2], h[l][4] - h[l][3], l < 2 ? (long long)(h[l + 1][0] - h[l][0]) : 0ll);
   }
+#endif
   return check_launch("mlp_layer_kernel<1> (layers 3 + 4)");
 }
 
