@@ -46,6 +46,9 @@ def main() -> None:
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--fim-mode", default="auto", choices=["auto", "step", "tensor"],
                     help="per-step CUDA-core J J^T or deferred tensor-core contraction (spi_b200_fim_contract)")
+    ap.add_argument("--pipelines", type=int, default=3,
+                    help="independent sub-populations whose control steps are interleaved on their own CUDA streams "
+                         "(active.PipelinedExploration; 1 = one explorer)")
     args = ap.parse_args()
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -61,7 +64,8 @@ def main() -> None:
     cfg = act.ActiveConfig(exploration_params=args.exploration_params, delta_param=args.delta_param,
                            ksync_steps=args.ksync_steps, motor_model=args.motor_model,
                            rollout_length=args.rollout_length, seed=args.seed, fim_mode=args.fim_mode)
-    ex = act.ActiveExploration(eng, policy, args.num_envs, cfg)
+    ex = (act.PipelinedExploration(eng, policy, args.num_envs, cfg, n_pipelines=args.pipelines)
+          if args.pipelines > 1 and args.num_envs >= 64 * args.pipelines else act.ActiveExploration(eng, policy, args.num_envs, cfg))
     if rank == 0:
         print(f"Active SysID: {world} GPU(s) x {args.num_envs} main envs x (1 + {ex.param_dim}) = {world * ex.num_envs} envs, "
               f"{ex.total_steps} steps/rollout, FIM mode {ex.fim_mode}")

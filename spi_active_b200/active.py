@@ -454,7 +454,21 @@ class ActiveExploration:
         self.counter.zero_()
 
     # ---- reset ---------------------------------------------------------------------------------------------------------------
-    def reset_all(self, main_commands: torch.Tensor, total_steps: Optional[int] = None):
+    @staticmethod
+    def initial_main_states(M: int, model, cfg: "ActiveConfig") -> torch.Tensor:
+        """[M, 37] reset states of the main envs (go2.yaml:52-55 + the reset distribution of
+        legged_robot_base.py:737-784), seeded: trial j of a population gets the same draw however the population is cut."""
+        g = torch.Generator().manual_seed(cfg.seed)
+        s = torch.zeros(M, gm.STATE_DIM)
+        s[:, 2], s[:, 6] = 0.34, 1.0                                       # go2.yaml:52-55
+        s[:, 13:25] = torch.tensor(model.q_default)
+        if cfg.randomize_reset:                                            # legged_robot_base.py:737-784
+            s[:, 7:13] = torch.rand(M, 6, generator=g) - 0.5
+            s[:, 13:25] *= 0.5 + torch.rand(M, 12, generator=g)
+        return s
+
+    def reset_all(self, main_commands: torch.Tensor, total_steps: Optional[int] = None,
+                  initial_main_states: Optional[torch.Tensor] = None):
         """active_sysid_openloop.py:116-131 + base_task.py:90-100: reset, then ONE env step with zero actions."""
         c, N, P1 = self.cfg, self.num_envs, self.param_dim + 1
         mc = main_commands.to(self.device, torch.float32)
@@ -467,14 +481,9 @@ class ActiveExploration:
             self.expanded_main_commands = self.main_commands.repeat_interleave(P1, dim=0)
         self.step_idx = 0
         self.commands.copy_(self.main_commands[:, 0, :].repeat_interleave(P1, dim=0))
-        g = torch.Generator().manual_seed(c.seed)
         M = self.num_main_envs
-        s = torch.zeros(M, gm.STATE_DIM)
-        s[:, 2], s[:, 6] = 0.34, 1.0                                       # go2.yaml:52-55
-        s[:, 13:25] = torch.tensor(self.model.q_default)
-        if c.randomize_reset:                                              # legged_robot_base.py:737-784
-            s[:, 7:13] = torch.rand(M, 6, generator=g) - 0.5
-            s[:, 13:25] *= 0.5 + torch.rand(M, 12, generator=g)
+        s = initial_main_states if initial_main_states is not None else self.initial_main_states(M, self.model, c)
+        assert tuple(s.shape) == (M, gm.STATE_DIM)
         self.state.copy_(s.repeat_interleave(P1, dim=0).to(self.device))    # every env of a group starts from the main's draw
         for t in (self.actions, self.history, self.gait_indices, self.clock, self.total_reward, self.jtj, self.step_reward):
             t.zero_()
@@ -510,34 +519,49 @@ class ActiveExploration:
     def evaluate_policy(self, commands: torch.Tensor, total_steps: Optional[int] = None, use_cuda_graph: Optional[bool] = None):
         """commands[M, T, 14] -> {"total_reward": [N] mean FIM reward per step (main env j at j * (P + 1)),
         "fim": [M, P, P] accumulated J J^T / steps}  (active_sysid.py:528-600)."""
+        n = self.begin_rollout(commands, total_steps, use_cuda_graph)
+        for _ in range(n):
+            self.advance_rollout()
+        return self.finish_rollout()
+
+    # the three pieces of evaluate_policy, exposed so that PipelinedExploration can interleave several explorers
+    @torch.no_grad()
+    def begin_rollout(self, commands: torch.Tensor, total_steps: Optional[int] = None, use_cuda_graph: Optional[bool] = None,
+                      initial_main_states: Optional[torch.Tensor] = None) -> int:
+        """Reset + the reset step (+ capture of the step graph); returns the number of advance_rollout() calls of the rollout."""
         total_steps = int(total_steps or self.total_steps)
         assert commands.shape[0] == self.num_main_envs and commands.shape[2] == 14
-        self.reset_all(commands, total_steps)
+        self.reset_all(commands, total_steps, initial_main_states)
         self.total_reward.zero_(); self.jtj.zero_()
-        tensor = self.fim_mode == "tensor"
-        fused = self.step_impl == "fused"
-        if tensor:
+        if self.fim_mode == "tensor":
             self.trace_acc.zero_(); self.dead_steps.zero_()
             self._hist_count = 0                      # the reset step's record is dropped, like its reward (:545-548)
-        graph_ok = self.device.type == "cuda" if use_cuda_graph is None else use_cuda_graph
-        step = 1
-        if graph_ok and self._graph is None:
+        self._graph_ok = self.device.type == "cuda" if use_cuda_graph is None else use_cuda_graph
+        self._steps_done = 1
+        if self._graph_ok and self._graph is None:
             self._capture()
-        for _ in range(1, total_steps - 1):
-            if fused:
-                self.step_idx += 1
-            else:
-                self._advance_inputs()
-            if graph_ok:
-                self._graph.replay()
-            else:
-                self._policy_step()
-            step += 1
-            if tensor:
-                self._hist_count += 1
-                if self._hist_count == self.hist.shape[0]:
-                    self._flush_fim()
-        if tensor:
+        return max(0, total_steps - 2)                # the reference's loop is range(1, total_steps - 1)
+
+    @torch.no_grad()
+    def advance_rollout(self):
+        if self.step_impl == "fused":
+            self.step_idx += 1
+        else:
+            self._advance_inputs()
+        if self._graph_ok:
+            self._graph.replay()
+        else:
+            self._policy_step()
+        self._steps_done += 1
+        if self.fim_mode == "tensor":
+            self._hist_count += 1
+            if self._hist_count == self.hist.shape[0]:
+                self._flush_fim()
+
+    @torch.no_grad()
+    def finish_rollout(self):
+        step = self._steps_done
+        if self.fim_mode == "tensor":
             self._flush_fim()
             self.total_reward.copy_(self.trace_acc.repeat_interleave(self.param_dim + 1)
                                     + self.cfg.termination_rew * self.dead_steps)
@@ -571,6 +595,57 @@ class ActiveExploration:
 
 
 # ---- command samplers (active_sysid.py:259-400) ------------------------------------------------------------------------------
+class PipelinedExploration:
+    """The M trials of an evaluate_policy call cut into `n_pipelines` independent explorers whose captured control steps
+    are replayed round-robin on their own CUDA streams.  A control step is a serial chain (actor -> physics -> post-step)
+    whose physics / bookkeeping part is latency-bound (0.3 - 0.6 waves of the GPU); two chains that are free to drift
+    against each other fill those gaps with the other chain's actor GEMMs.  Trials are independent, the initial states
+    are drawn once for the whole population and sliced, and every kernel is deterministic per row, so the result is the
+    same as ActiveExploration's on the uncut population."""
+
+    def __init__(self, backend, policy: "PolicyMLP", num_main_envs: int, cfg: Optional["ActiveConfig"] = None,
+                 n_pipelines: int = 2, **kw):
+        n = max(1, min(int(n_pipelines), int(num_main_envs)))
+        cuts = [int(num_main_envs) * i // n for i in range(n + 1)]
+        self.slices = [slice(cuts[i], cuts[i + 1]) for i in range(n)]
+        self.subs = [ActiveExploration(backend, policy, sl.stop - sl.start, cfg, **kw) for sl in self.slices]
+        e = self.subs[0]
+        self.cfg, self.model, self.device, self.dt = e.cfg, e.model, e.device, e.dt
+        self.param_dim, self.param_names, self.total_steps = e.param_dim, e.param_names, e.total_steps
+        self.num_main_envs = int(num_main_envs)
+        self.num_envs = self.num_main_envs * (self.param_dim + 1)
+        self.fim_mode, self.step_impl = e.fim_mode, e.step_impl
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.subs] if self.device.type == "cuda" else None
+
+    @torch.no_grad()
+    def evaluate_policy(self, commands: torch.Tensor, total_steps: Optional[int] = None, use_cuda_graph: Optional[bool] = None):
+        assert commands.shape[0] == self.num_main_envs
+        init = ActiveExploration.initial_main_states(self.num_main_envs, self.model, self.cfg)
+        import contextlib
+        if self.streams is not None:
+            cur = torch.cuda.current_stream(self.device)
+            for st in self.streams:
+                st.wait_stream(cur)
+        ctx = (lambda i: torch.cuda.stream(self.streams[i])) if self.streams is not None else (lambda i: contextlib.nullcontext())
+        n = 0
+        for i, (sub, sl) in enumerate(zip(self.subs, self.slices)):
+            with ctx(i):
+                n = sub.begin_rollout(commands[sl], total_steps, use_cuda_graph, init[sl])
+        for _ in range(n):
+            for i, sub in enumerate(self.subs):
+                with ctx(i):
+                    sub.advance_rollout()
+        outs = []
+        for i, sub in enumerate(self.subs):
+            with ctx(i):
+                outs.append(sub.finish_rollout())
+        if self.streams is not None:
+            for st in self.streams:
+                torch.cuda.current_stream(self.device).wait_stream(st)
+        return {"total_reward": np.concatenate([o["total_reward"] for o in outs]),
+                "fim": np.concatenate([o["fim"] for o in outs]), "steps": outs[0]["steps"]}
+
+
 def expand_commands(sampled: np.ndarray, sampling_idxs=COMMAND_SAMPLING_IDXS, default_command=DEFAULT_COMMAND) -> np.ndarray:
     """sampled[T, len(idxs)] -> full[T, 14] with the defaults elsewhere (:284-293)."""
     full = np.zeros((sampled.shape[0], len(default_command)), dtype=np.float32)

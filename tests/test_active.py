@@ -138,6 +138,22 @@ def test_evaluate_policy_on_oracle_backend(blob, nominal_model):
     np.testing.assert_array_equal(r2, out["total_reward"])
 
 
+def test_pipelined_exploration_equals_single_explorer_on_oracle(blob, nominal_model):
+    """PipelinedExploration cuts the trials into independent explorers; the seeded reset draw is made once for the whole
+    population, so trial j scores the same as in the uncut explorer."""
+    cfg = act.ActiveConfig(exploration_params=["mass", "comx"], ksync_steps=5, seed=3)
+    cmds = _commands(5, 30, seed=4)
+    be = OracleActiveBackend(blob, nominal_model)
+    one = act.ActiveExploration(be, act.PolicyMLP.random("cpu", seed=1), 5, cfg).evaluate_policy(cmds, total_steps=12)
+    pipe = act.PipelinedExploration(be, act.PolicyMLP.random("cpu", seed=1), 5, cfg, n_pipelines=2)
+    assert [sl.stop - sl.start for sl in pipe.slices] == [2, 3] and pipe.num_envs == 15
+    two = pipe.evaluate_policy(cmds, total_steps=12)
+    assert two["steps"] == one["steps"]
+    # (torch's CPU GEMM blocks a 6-row and a 15-row batch differently: last-bit differences in the actor output)
+    np.testing.assert_allclose(two["total_reward"], one["total_reward"], rtol=2e-5)
+    np.testing.assert_allclose(two["fim"], one["fim"], rtol=2e-5, atol=1e-6 * np.abs(one["fim"]).max())
+
+
 def test_deferred_tensor_fim_equals_per_step_fim(blob, nominal_model):
     """fim_mode='tensor' (record states, contract every fim_chunk steps) gives the per-step accumulation's numbers,
     including a group that terminates mid-rollout (its later steps score termination_rew = 0)."""
@@ -388,3 +404,21 @@ def test_evaluate_policy_fused_matches_torch_path(engine):
         # closed loop over 24 steps: cuBLAS inside / outside a graph already differs by 1 % on the torch path itself
         np.testing.assert_allclose(r["total_reward"], ref["total_reward"], rtol=3e-2, err_msg=str(key))
         np.testing.assert_allclose(r["fim"], ref["fim"], rtol=5e-2, atol=2e-3 * np.abs(ref["fim"]).max(), err_msg=str(key))
+
+
+@pytest.mark.gpu
+def test_pipelined_exploration_matches_single_explorer_gpu(engine):
+    """Two independent explorers replaying their captured steps on two streams give the same rewards / Fisher blocks as one
+    explorer on the whole population (every kernel is deterministic per row; only the FIM chunking of the tensor-core
+    contraction sees a different tile composition: 8 main envs per CTA)."""
+    cfg = act.ActiveConfig(exploration_params=["mass", "comx", "motor_model_calf_a"], ksync_steps=5, seed=3, fim_chunk=8)
+    cmds = _commands(24, 40, seed=6)
+    pol = act.PolicyMLP.random(engine.device, seed=1)
+    one = act.ActiveExploration(engine, pol, 24, cfg).evaluate_policy(cmds, total_steps=30)
+    pipe = act.PipelinedExploration(engine, pol, 24, cfg, n_pipelines=2)
+    two = pipe.evaluate_policy(cmds, total_steps=30)
+    again = pipe.evaluate_policy(cmds, total_steps=30)
+    assert two["steps"] == one["steps"] == 29
+    np.testing.assert_array_equal(again["total_reward"], two["total_reward"])
+    np.testing.assert_allclose(two["total_reward"], one["total_reward"], rtol=1e-5)
+    np.testing.assert_allclose(two["fim"], one["fim"], rtol=1e-5, atol=1e-6 * np.abs(one["fim"]).max())

@@ -28,3 +28,14 @@ for graph in (True, False):
     rew = out["total_reward"][::ex.param_dim + 1]
     print(f"fim={ex.fim_mode} graph={graph} M={M} P={ex.param_dim} envs={ex.num_envs} steps={out['steps']}: {dt:.3f} s  -> "
           f"{ex.num_envs * out['steps'] / dt:.3e} env-steps/s; reward mean {rew.mean():.4g} alive {(rew > 0).mean():.2f}")
+
+# two independent pipelines on two streams (PipelinedExploration)
+for n_pipe in (2, 3, 4, 6):
+    pipe = act.PipelinedExploration(eng, act.PolicyMLP.random(eng.device, seed=0, gain=0.3), M, cfg, n_pipelines=n_pipe)
+    for rep in range(2):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        out = pipe.evaluate_policy(cmds, total_steps=steps, use_cuda_graph=True)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    rew = out["total_reward"][::pipe.param_dim + 1]
+    print(f"pipelines={n_pipe} graph=True M={M} envs={pipe.num_envs} steps={out['steps']}: {dt:.3f} s  -> "
+          f"{pipe.num_envs * out['steps'] / dt:.3e} env-steps/s; reward mean {rew.mean():.4g} alive {(rew > 0).mean():.2f}")
