@@ -88,6 +88,52 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
+// ---- CTA pairs (cta_group::2): helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t v; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(v)); return v; }
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(bar), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// one MMA over both SMs of a pair: M = 256 (128 rows per CTA), B rows split between the two CTAs' shared memories
+__device__ __forceinline__ void mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// tcgen05.commit of a pair's MMAs, the arrive delivered to the same mbarrier of both CTAs
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__host__ __device__ constexpr uint32_t idesc_tf32_pair(int n) {   // M = 256 over the pair
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
 // TMA 1-D bulk copy shared -> global (bulk-group completion)
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
@@ -165,20 +211,23 @@ struct LayerArgs {
 //   promotion (256 thr)   wait accfull -> tcgen05.ld -> fp32 add into registers -> arrive accempty;  then the epilogue
 // What bounds the loop (measured, profiles/README.md): L2 -> SM operand bytes at the chip-wide L2 throughput when every SM
 // streams, then the shared-memory reads of the SS-mode MMAs; BN = 256 moves 25 % fewer bytes per flop than BN = 128.
-template <int BN> struct Cfg {
-  static constexpr int kWTiles = BN / kTile;                                  // 16 KB tiles per W operand and k-block
+// PAIR: two CTAs of a cluster (cta_group::2) compute a 256 x 256 tile: each CTA owns 128 rows of A and of the output,
+// holds HALF of the 256 weight rows (so a stage is the same 64 KB as for BN = 128: three stages fit) and the leader's MMA
+// lane issues M = 256 MMAs that read both shared memories — half the L2 -> SM operand bytes per flop of the 128 x 128 tiles.
+template <int BN, bool PAIR = false> struct Cfg {
+  static constexpr int kWTiles = PAIR ? 1 : BN / kTile;                       // 16 KB tiles per W operand and k-block IN THIS CTA
   static constexpr int kStageBytes = (2 + 2 * kWTiles) * kOperandBytes;       // a_hi, a_lo, w_hi[..], w_lo[..]
-  static constexpr int kStages = (BN == 256) ? 2 : 3;                         // 192 KB of stages either way
+  static constexpr int kStages = (mlptc::kStages * mlptc::kStageBytes) / ((2 + 2 * kWTiles) * kOperandBytes);   // 192 KB of stages either way
   static constexpr int kCols = BN / 2;                                        // output columns per epilogue thread
 };
-static_assert(Cfg<128>::kStages * Cfg<128>::kStageBytes == kStages * kStageBytes, "stage budget");
-static_assert(Cfg<256>::kStages * Cfg<256>::kStageBytes == kStages * kStageBytes, "stage budget");
+static_assert(Cfg<128>::kStages == 3 && Cfg<256>::kStages == 2 && Cfg<256, true>::kStages == 3, "stage budget");
 
-template <int MODE, int BN>
+template <int MODE, int BN, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs L) {
   using namespace fimtc;
-  using C = Cfg<BN>;
+  using C = Cfg<BN, PAIR>;
   static_assert(MODE == 0 || BN == kTile, "the fused output layer needs the whole hidden layer in one 128-wide tile");
+  static_assert(!PAIR || (MODE == 0 && BN == 256), "CTA pairs: 256 x 256 tiles of a hidden layer");
   constexpr int kS = C::kStages, kSB = C::kStageBytes, kWT = C::kWTiles, kNC = C::kCols;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* tail = smem + kStages * kStageBytes;
@@ -186,7 +235,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
   uint64_t* empty = full + 3;                              // [kS] MMA -> producer
   uint64_t* accfull = empty + 3;                           // [2] MMA -> promotion
   uint64_t* accempty = accfull + 2;                        // [2] promotion -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
+  uint64_t* peer_full = accempty + 2;                      // [kS] PAIR, leader only: the peer CTA's stage has landed
+  uint64_t* peer_accempty = peer_full + 3;                 // [2]  PAIR, leader only: the peer CTA has drained an accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_accempty + 2);
+  const uint32_t pair_rank = PAIR ? cluster_ctarank() : 0u;         // 0 = leader: issues the MMAs of the pair
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * kTile, n0 = blockIdx.y * BN;
   MLP_STAMP(0);
@@ -195,16 +247,26 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
   float* wout_s = reinterpret_cast<float*>(tail + kTailWout);     // [n_out][128]
   float* bout_s = reinterpret_cast<float*>(tail + kTailBout);     // [n_out]
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   if (tid == 32) {
-    for (int s = 0; s < kS; s++) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(smem_u32(accfull + a), 1); mbar_init(smem_u32(accempty + a), kEpilogue); }
+    for (int s = 0; s < kS; s++) {
+      mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); mbar_init(smem_u32(peer_full + s), 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(smem_u32(accfull + a), 1); mbar_init(smem_u32(accempty + a), kEpilogue); mbar_init(smem_u32(peer_accempty + a), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (PAIR) cluster_sync();        // the peer's barriers and TMEM exist before anything is signalled / issued across the pair
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *tmem_slot;
   MLP_STAMP(1);
@@ -218,7 +280,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
       size_t w_copy = 0;
       if (L.rot) { const int r = *L.rot; w_copy = (size_t)(r < 0 ? 0 : (r >= L.n_rot ? L.n_rot - 1 : r)) * L.rot_stride; }
       const size_t a_tile = (size_t)blockIdx.x * n_blocks * tiled::kTileFloats;
-      const size_t w_tile = w_copy + (size_t)blockIdx.y * kWT * n_blocks * tiled::kTileFloats;   // first of kWT 128-row tiles
+      // first of this CTA's kWT 128-row weight tiles (a pair splits the 256 rows of its n-tile between its two CTAs)
+      const size_t w_tile = w_copy + (size_t)(PAIR ? blockIdx.y * 2 + pair_rank : blockIdx.y * kWT) * n_blocks * tiled::kTileFloats;
       for (int kb = 0; kb < n_blocks; kb++) {
         const int s = kb % kS;
         if (kb >= kS) mbar_wait(smem_u32(empty + s), (uint32_t)((kb / kS - 1) & 1));
@@ -238,12 +301,28 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
     }
   } else if (warp == kEpilogue / 32) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (PAIR && lane == 0 && pair_rank != 0) {
+      // peer CTA of a pair: it issues no MMAs; this lane only tells the leader when this CTA's stages have landed and its
+      // accumulators are drained (the leader's MMAs read this CTA's shared memory and write its tensor memory)
+      for (int kb = 0; kb < n_blocks; kb++) {
+        const int s = kb % kS, g = kb / kGroup;
+        if ((kb % kGroup) == 0 && g >= 2) {
+          mbar_wait(smem_u32(accempty + (g & 1)), (uint32_t)(((g - 2) >> 1) & 1));
+          mbar_arrive_remote(smem_u32(peer_accempty + (g & 1)), 0);
+        }
+        mbar_wait(smem_u32(full + s), (uint32_t)((kb / kS) & 1));
+        mbar_arrive_remote(smem_u32(peer_full + s), 0);
+      }
+    } else if (lane == 0) {
       for (int kb = 0; kb < n_blocks; kb++) {
         const int s = kb % kS, g = kb / kGroup;
         const bool group_start = (kb % kGroup) == 0, group_end = ((kb + 1) % kGroup) == 0 || kb == n_blocks - 1;
-        if (group_start && g >= 2) mbar_wait(smem_u32(accempty + (g & 1)), (uint32_t)(((g - 2) >> 1) & 1));
+        if (group_start && g >= 2) {
+          mbar_wait(smem_u32(accempty + (g & 1)), (uint32_t)(((g - 2) >> 1) & 1));
+          if (PAIR) mbar_wait_cluster(smem_u32(peer_accempty + (g & 1)), (uint32_t)(((g - 2) >> 1) & 1));
+        }
         mbar_wait(smem_u32(full + s), (uint32_t)((kb / kS) & 1));
+        if (PAIR) mbar_wait_cluster(smem_u32(peer_full + s), (uint32_t)((kb / kS) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t stage = smem_base + (uint32_t)s * kSB;
         // a W operand of BN rows = BN / 128 adjacent 16 KB tiles (8-row groups 1024 bytes apart throughout); for BN = 128 the
@@ -256,7 +335,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
           if (MLP_DBG(1)) break;
           const uint64_t off = (uint64_t)(k * 2);     // 32 bytes >> 4, inside the 14-bit start-address field
           const uint32_t first = (!group_start || k > 0) ? 1u : 0u;
-          if (BN == 256) {
+          if (PAIR) {              // M = 256 over the pair, N = 256: this CTA's 128 weight rows + the peer's
+            mma_tf32_pair(tacc, al + off, wh + off, idesc_tf32_pair(256), first);
+            mma_tf32_pair(tacc, ah + off, wl + off, idesc_tf32_pair(256), 1u);
+            mma_tf32_pair(tacc, ah + off, wh + off, idesc_tf32_pair(256), 1u);
+          } else if (BN == 256) {
             mma_tf32_n(tacc, al + off, wh + off, idesc_tf32(256), first);
             mma_tf32_n(tacc, ah + off, wl + off, idesc_tf32(256), 1u);
             mma_tf32_n(tacc, ah + off, wh + off, idesc_tf32(256), 1u);
@@ -265,8 +348,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
             mma_tf32_n(tacc, al + off, wh + off, idesc_tf32(128), 1u);      // [0,128) += a_lo w_hi
           }
         }
-        umma_commit(smem_u32(empty + s));
-        if (group_end) umma_commit(smem_u32(accfull + (g & 1)));
+        if (PAIR) {
+          umma_commit_pair(smem_u32(empty + s));
+          if (group_end) umma_commit_pair(smem_u32(accfull + (g & 1)));
+        } else {
+          umma_commit(smem_u32(empty + s));
+          if (group_end) umma_commit(smem_u32(accfull + (g & 1)));
+        }
       }
     }
   } else {
@@ -379,7 +467,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   MLP_STAMP(4);
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+  if (PAIR) {
+    cluster_sync();                // neither CTA of the pair leaves (or frees tensor memory) while the other may still signal it
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+  } else if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+  }
 }
 
 // x [M, K] fp32 row-major -> hi / lo in the tiled layout [Mp, Kp] (padding is left as it is: zero-initialised by the owner)

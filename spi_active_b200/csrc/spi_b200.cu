@@ -1017,14 +1017,20 @@ static cudaError_t mlp_set_attributes() {
   cudaError_t e = cudaFuncSetAttribute(mlptc::mlp_layer_kernel<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlptc::kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mlptc::mlp_layer_kernel<0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlptc::kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mlptc::mlp_layer_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlptc::kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlptc::mlp_layer_kernel<0, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlptc::kSmemBytes);
   return e;
 }
 
 // mode 0: hidden layer -> split activations (128 x 256 tiles when the width allows, else 128 x 128); mode 1: last hidden
 // layer + output layer.  `layer` only labels the development timestamps.
 static cudaError_t mlp_launch(int mode, int layer, mlptc::LayerArgs L, int m_tiles, cudaStream_t st) {
-  static int wide = -1;
+  static int wide = -1, pair = 0;
   if (wide < 0) {
+    // SPI_B200_MLP_PAIR=1: CTA pairs (cta_group::2, 256 x 256 tiles per pair) for the wide layers.  Parity-tested, half the
+    // operand bytes per flop and a 19 % shorter main loop per flop — but the 176 / 88 pair tiles of the config-5 batch quantise
+    // worse over 148 SMs and clusters co-schedule less freely than single CTAs: 0.142 ms vs 0.108 ms per forward
+    // (profiles/README.md r1_d), so it is off by default.
+    const char* pe = std::getenv("SPI_B200_MLP_PAIR"); pair = pe ? std::atoi(pe) : 0;
     // 128 x 256 tiles: 25 % fewer operand bytes per flop but only 2 pipeline stages fit -> measured SLOWER (0.138 vs 0.112 ms)
     const char* w = std::getenv("SPI_B200_MLP_WIDE"); wide = w ? std::atoi(w) : 0;
   }
@@ -1046,6 +1052,16 @@ static cudaError_t mlp_launch(int mode, int layer, mlptc::LayerArgs L, int m_til
 #endif
   if (mode == 1) {
     mlptc::mlp_layer_kernel<1, 128><<<dim3(m_tiles, 1), mlptc::kThreads, mlptc::kSmemBytes, st>>>(L);
+  } else if (pair && L.N % 256 == 0 && m_tiles % 2 == 0) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(m_tiles, L.N / 256); cfg.blockDim = dim3(mlptc::kThreads); cfg.dynamicSmemBytes = mlptc::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, mlptc::mlp_layer_kernel<0, 256, true>, L);
   } else if (wide && L.N % 256 == 0) {
     mlptc::mlp_layer_kernel<0, 256><<<dim3(m_tiles, L.N / 256), mlptc::kThreads, mlptc::kSmemBytes, st>>>(L);
   } else {

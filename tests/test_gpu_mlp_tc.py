@@ -97,3 +97,30 @@ def test_policy_forward_ring_permutes_the_first_layer():
         ref = _mlp64(x_eff.numpy(), [w.numpy() for w in ws], [b.numpy() for b in bs])
         err = np.abs(y.cpu().numpy() - ref).max() / np.abs(ref).max()
         assert err < 5e-6, (r, err)
+
+
+@pytest.mark.parametrize("knob", ["SPI_B200_MLP_PAIR", "SPI_B200_MLP_WIDE"])
+def test_alternative_tile_shapes_keep_parity(knob):
+    """The measured-but-not-default tile shapes of the actor kernel (cta_group::2 CTA pairs on 256 x 256 tiles; single-CTA
+    128 x 256 tiles) are selected by an environment variable read once per process, so they are exercised in a child
+    process: same fp32-grade parity as the default path."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import os, subprocess, sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np, torch\n"
+        "from test_gpu_mlp_tc import _make, _mlp64\n"
+        "from spi_active_b200.engine import TensorCorePolicy\n"
+        "dims, M = (900, 512, 256, 128, 12), 2048\n"
+        "ws, bs = _make(dims, seed=7)\n"
+        "x = torch.randn(M, 900, generator=torch.Generator().manual_seed(2)) * 1.5\n"
+        "y = TensorCorePolicy(ws, bs, torch.device('cuda:0'))(x.cuda()).cpu().numpy()\n"
+        "ref = _mlp64(x.numpy(), [w.numpy() for w in ws], [b.numpy() for b in bs])\n"
+        "err = float(np.abs(y - ref).max() / np.abs(ref).max())\n"
+        "print('ERR', err); assert err < 5e-6, err\n") % (str(root), str(root / "tests"))
+    env = dict(os.environ, **{knob: "1"})
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "ERR" in res.stdout, res.stdout + res.stderr
