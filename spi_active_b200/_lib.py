@@ -18,7 +18,7 @@ HEADERS = [_PKG / "csrc" / "aba_leg.cuh", _PKG / "csrc" / "go2_ws.cuh", _PKG / "
            _PKG / "csrc" / "fim_tc.cuh", _PKG / "csrc" / "active_step.cuh", _PKG / "csrc" / "mlp_tc.cuh", _PKG / "csrc" / "tiled_layout.cuh",
            _PKG.parent / "include" / "spi_b200.h"]
 # SPI_WS_FAST_SINCOS: joint sin/cos through MUFU after a 2-constant reduction to [-pi, pi]; measured deviation from
-# the fp64 oracle stays at the fp32 noise floor of the oracle itself (profiles/README.md, tools/dev_accuracy.py)
+# the fp64 oracle stays at the fp32 noise floor of the oracle itself (profiles/README.md, tests/tools/dev_accuracy.py)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-DSPI_WS_FAST_SINCOS",
               "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
 

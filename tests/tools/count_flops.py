@@ -6,7 +6,7 @@ counts 1 (an FMA therefore counts 2).  The figure is independent of how the CUDA
 parallelised and excludes any recomputation the kernel adds.  Test/measurement infrastructure: this is
 the only thing the script uses oracle/ for.
 
-    python tools/count_flops.py            # writes profiles/roofline.json
+    python tests/tools/count_flops.py            # writes profiles/roofline.json
 """
 from __future__ import annotations
 
@@ -16,7 +16,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 

@@ -2,7 +2,7 @@
 (per-sample errors and mean costs), to size the parity tolerances and compare sincos variants."""
 import sys, os
 from pathlib import Path
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent)); sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tests"))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent)); sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np, torch
 import synth
 from oracle import oracle as orc
