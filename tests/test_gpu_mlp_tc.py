@@ -124,3 +124,26 @@ def test_alternative_tile_shapes_keep_parity(knob):
     env = dict(os.environ, **{knob: "1"})
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "ERR" in res.stdout, res.stdout + res.stderr
+
+
+def test_policy_ring_argument_errors():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from spi_active_b200._lib import SpiB200Error
+    from spi_active_b200.engine import TensorCorePolicy
+    dev = torch.device("cuda:0")
+    ws, bs = _make((900, 512, 256, 128, 12), 0)
+    pol = TensorCorePolicy(ws, bs, dev)
+    hi, lo = pol.alloc_input(128)
+    rot = torch.zeros(1, dtype=torch.int32, device=dev)
+    with pytest.raises(SpiB200Error):                       # no ring copies yet
+        pol.forward_ring(hi, lo, 128, rot)
+    bad = np.tile(np.arange(900, dtype=np.int32), (2, 1))
+    bad[1, 5] = 900                                         # column index outside [-1, in)
+    with pytest.raises(SpiB200Error):
+        pol.enable_ring(bad)
+    pol.enable_ring(np.tile(np.arange(900, dtype=np.int32), (2, 1)))
+    rot.fill_(7)                                            # out-of-range head positions are clamped on the device, not read out of bounds
+    y = pol.forward_ring(hi, lo, 128, rot)
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all()
