@@ -142,6 +142,33 @@ def test_recording_schema_roundtrip(tmp_path, oracle_lib, blob, nominal_model):
     assert total == 15 and ds["motion_ends"].sum() == 1 and ds["motion_ends"][-1]
 
 
+def test_record_data_cli_writes_files_the_loader_reads(tmp_path, oracle_lib, blob, nominal_model, monkeypatch):
+    """scripts/record_data.py (counterpart of the reference's scripts/data/*.py): file names and directory layout are what
+    scripts/config/*.yaml / landscape.load_config resolve, the schema is what load_dataset reads.  The oracle stands in for
+    the engine here (no GPU)."""
+    import importlib.util
+    from oracle import oracle as orc
+    from spi_active_b200 import dataset as dsmod, go2_model as gm, landscape
+    spec = importlib.util.spec_from_file_location("record_data", ROOT / "scripts" / "record_data.py")
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    monkeypatch.setitem(recorders.DURATION_STEPS, "stand", 30)
+    monkeypatch.setitem(recorders.DURATION_STEPS, "sine", 30)
+
+    def rollout_fn(init, actions):
+        st = orc.rollout_states(blob, np.array([[nominal_model.base.mass]], np.float32), [gm.PARAM_IDS["mass"]], init[None],
+                                actions[None])
+        return st[0, 0]
+    out_dir = tmp_path / landscape.DATA_SUBDIR
+    out_dir.mkdir(parents=True)
+    for n in ("stand", "sine"):
+        p = mod.record_to_file(n, rollout_fn, nominal_model, out_dir)
+        assert p.name == f"go2_{n}_data.npz"
+    assert landscape.load_config("stand", tmp_path) == [out_dir / "go2_stand_data.npz"]
+    total, ds = dsmod.load_dataset([out_dir / "go2_stand_data.npz", out_dir / "go2_sine_data.npz"], 5)
+    assert total == 50 and ds["motion_ends"].sum() == 2
+    np.testing.assert_allclose(ds["pd_gain_kp"][0], nominal_model.kp[0]); np.testing.assert_allclose(ds["pd_gain_kd"][0], nominal_model.kd[0])
+
+
 def test_bench_reference_arm_runs_without_gpu():
     """`bench.py --impl reference` is CPU-only and prints the contract's JSON line."""
     import json
