@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SPI_B200_VERSION 102 /* major*100 + minor */
+#define SPI_B200_VERSION 103 /* major*100 + minor */
 
 /* ------------------------------------------------------------------------------------------
  * Model blob layout (fp32[SPI_BLOB_SIZE]).  Built on the host from the URDF
@@ -239,7 +239,7 @@ int spi_b200_fim_reward(spi_b200_model* model, const float* states, int M, int P
  *   q_default [12] HOST.  1 <= P1 <= 17.                                                                          */
 int spi_b200_active_post_step(spi_b200_model* model, float* state, const float* raw_actions, unsigned char* done,
                               const float* main_commands, int T, float* commands, float* actions, float* gait,
-                              float* clock, float* history, float* obs, float* obs_hi, float* obs_lo, int obs_stride,
+                              float* clock, float* history, float* obs, void* obs_hi, void* obs_lo, int obs_stride,
                               int ring_slots, const int* hist_index, float* fim_hist,
                               unsigned char* fim_live, float* dead_steps, const int* schedule, int* counter, int* ctrl,
                               int M, int P1, float dt, float action_clip, float clip_obs, float grav_x, float grav_y,
@@ -247,25 +247,27 @@ int spi_b200_active_post_step(spi_b200_model* model, float* state, const float* 
 
 /* The locomotion policy (actor MLP: Linear-ELU x3 + Linear; spigym/agents/modules/modules.py:47-63,
  * config/algo/ppo.yaml:32-40, evaluated per control step at agents/sysid/active_sysid.py:555-562) on the tensor cores
- * with fp32-grade accuracy (tcgen05.mma kind::tf32, 3xTF32 split).  Constraints: 3 hidden layers, widths h1, h2
- * multiples of 128, h3 = 128, <= 16 outputs (the reference's 900-512-256-128-12 actor qualifies).
+ * with fp32-grade accuracy: tcgen05.mma kind::f16 on fp16 PAIRS (x s = hi + lo, products hi.hi + hi.lo + lo.hi accumulated in
+ * fp32: ~2^-22 relative, where plain fp16 / TF32 would be 2^-11).  Constraints: 3 hidden layers, widths h1, h2 multiples of
+ * 128, h3 = 128, <= 16 outputs (the reference's 900-512-256-128-12 actor qualifies); |weights| < 255 and |activations| < 4000
+ * (the pairs are scaled by 256 / 16 to keep the low halves out of the fp16 subnormals; observations are clipped to +-100).
  *   dims [5] = in, h1, h2, h3, out; weights[l] [dims[l+1], dims[l]] row-major (torch Linear layout), biases[l]: HOST.
- * The input is passed PRE-SPLIT (x = x_hi + x_lo, x_hi rounded to tf32) in two buffers of rows * stride floats
- * (spi_b200_policy_input_layout: rows = M rounded up to 128, stride = in rounded up to 32; zero-initialised by the owner)
- * whose element order is OPAQUE: 128 x 32 tiles stored as the swizzled shared-memory image the tensor core reads, so that a
- * pipeline stage is four contiguous 16 KB TMA bulk copies (csrc/tiled_layout.cuh).  spi_b200_active_post_step writes the
- * observation in that form directly; spi_b200_policy_split_input / _unsplit_input convert from / to a plain row-major
- * [M, in] matrix.  out [M, out] fp32.                                                                              */
+ * The input is passed PRE-SPLIT in two OPAQUE buffers of rows * stride 2-byte elements each
+ * (spi_b200_policy_input_layout: rows = M rounded up to 128, stride = in rounded up to 64; zero-initialised by the owner):
+ * 128 x 64 tiles stored as the swizzled shared-memory image the tensor core reads, so that a pipeline stage is four
+ * contiguous 16 KB TMA bulk copies (csrc/tiled_layout.cuh).  spi_b200_active_post_step writes the observation in that form
+ * directly; spi_b200_policy_split_input / _unsplit_input convert from / to a plain row-major [M, in] fp32 matrix.
+ * out [M, out] fp32.                                                                                              */
 typedef struct spi_b200_policy spi_b200_policy;
 int spi_b200_policy_create(const int* dims, const float* const* weights, const float* const* biases,
                            spi_b200_policy** out_policy);
 int spi_b200_policy_destroy(spi_b200_policy* policy);
 int spi_b200_policy_input_layout(spi_b200_policy* policy, int M, int* out_rows, int* out_stride);
-int spi_b200_policy_split_input(spi_b200_policy* policy, const float* x, int M, float* x_hi, float* x_lo,
+int spi_b200_policy_split_input(spi_b200_policy* policy, const float* x, int M, void* x_hi, void* x_lo,
                                 void* cuda_stream);
-int spi_b200_policy_unsplit_input(spi_b200_policy* policy, const float* x_hi, const float* x_lo, int M, float* x,
+int spi_b200_policy_unsplit_input(spi_b200_policy* policy, const void* x_hi, const void* x_lo, int M, float* x,
                                   void* cuda_stream);
-int spi_b200_policy_forward(spi_b200_policy* policy, const float* x_hi, const float* x_lo, int M, float* out,
+int spi_b200_policy_forward(spi_b200_policy* policy, const void* x_hi, const void* x_lo, int M, float* out,
                             void* cuda_stream);
 
 /* Ring-ordered input (active exploration): the actor's input [frame | per-key blocks of the 14 previous frames] is a
@@ -276,7 +278,7 @@ int spi_b200_policy_forward(spi_b200_policy* policy, const float* x_hi, const fl
  * element k when the head is at position r (-1 = unused element).  rot_dev: DEVICE int holding the head position of
  * this forward (read by the kernel, so a captured step needs no host work), or NULL for position 0.                  */
 int spi_b200_policy_enable_ring(spi_b200_policy* policy, const int* col_map, int n_rot);
-int spi_b200_policy_forward_ring(spi_b200_policy* policy, const float* x_hi, const float* x_lo, int M,
+int spi_b200_policy_forward_ring(spi_b200_policy* policy, const void* x_hi, const void* x_lo, int M,
                                  const int* rot_dev, float* out, void* cuda_stream);
 
 /* Accumulated Fisher information of whole rollouts on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 split =

@@ -17,6 +17,7 @@
 // The arithmetic follows spi_active_b200/active.py (the torch statement of the same step, pinned to the reference's
 // own code by tests/golden/active_obs.npz) operation by operation, so the two paths agree to fp32 rounding.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -40,7 +41,8 @@ struct Args {
   float* clock;                    // [N,4] in/out
   float* history;                  // [N,14,60] in/out, newest first
   float* obs;                      // [N,900] out
-  float* obs_hi; float* obs_lo;    // [rows, obs_stride] (tiled_layout.cuh) or null: pre-split input of spi_b200_policy_forward
+  __half* obs_hi; __half* obs_lo;  // [rows, obs_stride] (tiled_layout.cuh) or null: pre-split input of spi_b200_policy_forward
+  float obs_scale;                 // power of two applied before the fp16 split (mlptc::kActScale)
   int obs_stride;
   // ring_slots > 0 (= 15): obs_hi / obs_lo ARE the observation state — a ring of 15 frames per env, K position
   // slot * 60 + term; this step's frame goes to slot ctrl[3] and nothing else is touched (history / obs / hist_index
@@ -168,13 +170,11 @@ __global__ void __launch_bounds__(32 * kMaxGroup) active_post_step_kernel(const 
     __syncwarp();
     const int k0 = A.ctrl[3] * kFrame;
     for (int i = lane; i < kFrame; i += 32) {
-      const float o = fminf(fmaxf(sm.frame(w)[i], -A.clip_obs), A.clip_obs);
-      uint32_t hb;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(o));
-      const float h = __uint_as_float(hb);
+      const float o = fminf(fmaxf(sm.frame(w)[i], -A.clip_obs), A.clip_obs) * A.obs_scale;
+      const __half h = __float2half_rn(o);
       const size_t at = tiled::offset(env, k0 + i, A.obs_stride);
       A.obs_hi[at] = h;
-      A.obs_lo[at] = o - h;
+      A.obs_lo[at] = __float2half_rn(o - __half2float(h));
     }
   } else {
   // ---- observation = [frame | gathered history], clip; then push the frame -----------------------------------------------
@@ -187,12 +187,11 @@ __global__ void __launch_bounds__(32 * kMaxGroup) active_post_step_kernel(const 
     const float o = fminf(fmaxf(v, -A.clip_obs), A.clip_obs);
     orow[i] = o;
     if (A.obs_hi) {
-      uint32_t hb;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(o));
-      const float h = __uint_as_float(hb);
+      const float os = o * A.obs_scale;
+      const __half h = __float2half_rn(os);
       const size_t at = tiled::offset(env, i, A.obs_stride);
       A.obs_hi[at] = h;
-      A.obs_lo[at] = o - h;
+      A.obs_lo[at] = __float2half_rn(os - __half2float(h));
     }
   }
   for (int i = lane; i < kHistLen * kFrame; i += 32) hrow[i] = (i < kFrame) ? sm.frame(w)[i] : sm.hist(w)[i - kFrame];

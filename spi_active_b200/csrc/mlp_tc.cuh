@@ -5,20 +5,26 @@
 // step for every env (agents/sysid/active_sysid.py:555-562): 1.25 MFLOP per env-step, 14 GFLOP per step at 1024 x 11
 // envs — after the physics and the bookkeeping were fused this GEMM chain is ~3/4 of a step on cuBLAS' fp32 SIMT path.
 //
-// Here every Linear is a tcgen05.mma.kind::tf32 GEMM with the 3xTF32 split (x = hi + lo, both tf32:
-// x.w ~= hi.hi + hi.lo + lo.hi, error ~2^-22 relative, i.e. fp32 grade — plain TF32 would be 2^-11):
+// Here every Linear is a tcgen05.mma.kind::f16 GEMM on fp16 PAIRS — the "3 x FP16" split: x * s = hi + lo with hi = fp16(x s),
+// lo = fp16(x s - hi) (s a power of two that keeps lo out of the fp16 subnormals; undone exactly in the epilogue), and
+// x.w ~= hi.hi + hi.lo + lo.hi with exact fp16 x fp16 products accumulated in fp32: error ~2^-22 relative, i.e. fp32 grade
+// (plain fp16 / TF32 would be 2^-11).  Against the 3 x TF32 split of r1_c this moves half the operand bytes (2 x 2 B instead of
+// 2 x 4 B per value) and runs on the twice-as-fast f16 MMA — and L2 -> SM operand bytes and shared-memory operand reads are
+// exactly what bounded that kernel (profiles/README.md):
 //   * operands are PRE-SPLIT in global memory, K-major: the weights once at creation, the activations by the epilogue
 //     of the layer (or of the observation kernel) that produces them, so the GEMM's producer is a pure copy:
 //     the global arrays are stored tile by tile as the SWIZZLE_128B K-major shared-memory image (tiled_layout.cuh) and a
 //     stage is four contiguous 16 KB TMA bulk copies (cp.async.bulk + mbarrier complete_tx), 3-stage ring with
 //     full / empty mbarriers (tcgen05.commit releases a stage);
-//   * a dedicated warp issues 8 MMAs per stage (4 k-steps x {a_hi [w_hi; w_lo] at N = 256, a_lo w_hi at N = 128}) into a 256-column
-//     fp32 TMEM tile whose two halves are added during the promotion;
+//   * a dedicated warp issues 8 MMAs per stage (4 k-steps of 16 x {a_hi [w_hi; w_lo] at N = 256, a_lo w_hi at N = 128}) into a
+//     256-column fp32 TMEM tile whose two halves are added during the promotion;
 //   * the tensor core's accumulation truncates (measured: a 1e-5 bias over K = 928), so two TMEM accumulators alternate
-//     between groups of 4 k-blocks and are promoted into fp32 registers (tcgen05.ld + round-to-nearest add);
-//   * epilogue (thread = row): + bias -> ELU -> split -> hi / lo of the next layer's input; the last hidden layer (128
-//     wide = one tile) also applies the 128 -> 12 output layer in registers (fp32 FMA).
+//     between groups of k-blocks and are promoted into fp32 registers (tcgen05.ld + round-to-nearest add);
+//   * epilogue (thread = row x column half): x 1 / (s_a s_w) -> + bias -> ELU -> split -> hi / lo of the next layer's input,
+//     assembled in shared memory and stored with bulk copies; the last hidden layer (128 wide = one tile) also applies the
+//     128 -> 12 output layer in registers (fp32 FMA).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -34,10 +40,11 @@ constexpr int kHalfCols = 64;
 constexpr int kThreads = kEpilogue + 64;     // warp 8: MMA issuer, warp 9: bulk-copy producer (one elected lane each)
 constexpr int kAccCols = 256;                // one accumulator: columns [0,128) = a_hi w_hi + a_lo w_hi, [128,256) = a_hi w_lo
 constexpr int kTmemCols = 2 * kAccCols;      // two accumulators, used alternately by groups of k-blocks (all of TMEM)
-constexpr int kKAlign = 32;                  // the padded K of every operand is a multiple of this
-constexpr int kBK = 32;                      // fp32 elements of K per stage = one 128-byte swizzle atom per row
+constexpr int kKAlign = 64;                  // the padded K of every operand is a multiple of this
+constexpr int kBK = 64;                      // halves of K per stage = one 128-byte swizzle atom per row
+constexpr float kActScale = 16.0f, kWeightScale = 256.0f;   // powers of two applied before the fp16 split (exact to undo)
 constexpr int kStages = 3;
-constexpr int kOperandBytes = kTile * kBK * 4;               // 16 KB = one tile of tiled_layout.cuh
+constexpr int kOperandBytes = kTile * kBK * 2;               // 16 KB = one tile of tiled_layout.cuh
 constexpr int kStageBytes = 4 * kOperandBytes;               // A_hi, A_lo, W_hi, W_lo
 constexpr int kMaxOut = 16;
 // shared-memory tail behind the stages: barriers + TMEM slot (256 B) | bias of this n-tile (<= 256 floats) | output layer:
@@ -50,7 +57,7 @@ constexpr int kGroup = 4;
 
 // K-major SWIZZLE_128B (cute::UMMA::LayoutType::SWIZZLE_128B = 2): rows are 128 bytes (32 fp32 of K), an 8-row group is
 // 1024 contiguous bytes, the 16-byte chunk c of row r sits at chunk position c ^ (r & 7); SBO = 1024 between row groups,
-// the leading-dimension field is 1 (unused: one swizzle atom spans the tile's K extent); a k-step of 8 fp32 advances the
+// the leading-dimension field is 1 (unused: one swizzle atom spans the tile's K extent); a k-step of 16 halves advances the
 // start address by 32 bytes inside the atom.  Tile bases are 1024-byte aligned (base_offset 0).  Measured: the no-swizzle
 // canonical layout runs the same 128 x 128 x 8 MMA in ~256 cycles instead of ~65.
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr) {
@@ -63,14 +70,15 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr) {
   return d;
 }
 
-// instruction descriptors (cute::UMMA::InstrDescriptor, see fim_tc.cuh): tf32 x tf32 -> f32, K-major operands, M = 128
-__host__ __device__ constexpr uint32_t idesc_tf32(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24); }
+// instruction descriptors (cute::UMMA::InstrDescriptor, see fim_tc.cuh): c_format F32 (1) at [4,6), a / b_format F16 (0) at
+// [7,10) / [10,13), K-major operands, N >> 3 at [17,23), M >> 4 at [24,29); M = 128
+__host__ __device__ constexpr uint32_t idesc_tf32(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24); }
 __device__ __forceinline__ void mma_tf32_n(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -120,7 +128,7 @@ __device__ __forceinline__ void mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, u
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -131,7 +139,7 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
                : "memory");
 }
 __host__ __device__ constexpr uint32_t idesc_tf32_pair(int n) {   // M = 256 over the pair
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
 // TMA 1-D bulk copy shared -> global (bulk-group completion)
@@ -190,13 +198,13 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
 #endif
 
 struct LayerArgs {
-  const float* a_hi; const float* a_lo;    // [Mp, Kp] activations, split, tiled_layout.cuh
-  const float* w_hi; const float* w_lo;    // [N, Kp] weights (torch Linear layout [out, in]), split, tiled_layout.cuh
+  const __half* a_hi; const __half* a_lo;  // [Mp, Kp] activations x kActScale, split, tiled_layout.cuh
+  const __half* w_hi; const __half* w_lo;  // [N, Kp] weights (torch Linear layout [out, in]) x kWeightScale, split, tiled
   const float* bias;                       // [N]
   int Kp, N;
-  float* out_hi; float* out_lo; int out_stride;   // MODE 0: ELU(a w^T + b) split, tiled [Mp, out_stride]
+  __half* out_hi; __half* out_lo; int out_stride;   // MODE 0: ELU(a w^T + b) x kActScale split, tiled [Mp, out_stride]
   const float* w_out; const float* b_out; int n_out; float* out; int M;   // MODE 1: + output layer -> out [M, n_out]
-  const int* rot; size_t rot_stride; int n_rot;   // device int selecting one of n_rot weight copies rot_stride floats apart, or null
+  const int* rot; size_t rot_stride; int n_rot;   // device int selecting one of n_rot weight copies rot_stride elements apart, or null
   int stamp, dbg;   // development instrumentation (SPI_B200_MLP_DEV builds only)
 };
 
@@ -279,21 +287,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
     if (lane == 0) {
       size_t w_copy = 0;
       if (L.rot) { const int r = *L.rot; w_copy = (size_t)(r < 0 ? 0 : (r >= L.n_rot ? L.n_rot - 1 : r)) * L.rot_stride; }
-      const size_t a_tile = (size_t)blockIdx.x * n_blocks * tiled::kTileFloats;
+      const size_t a_tile = (size_t)blockIdx.x * n_blocks * tiled::kTileElems;
       // first of this CTA's kWT 128-row weight tiles (a pair splits the 256 rows of its n-tile between its two CTAs)
-      const size_t w_tile = w_copy + (size_t)(PAIR ? blockIdx.y * 2 + pair_rank : blockIdx.y * kWT) * n_blocks * tiled::kTileFloats;
+      const size_t w_tile = w_copy + (size_t)(PAIR ? blockIdx.y * 2 + pair_rank : blockIdx.y * kWT) * n_blocks * tiled::kTileElems;
       for (int kb = 0; kb < n_blocks; kb++) {
         const int s = kb % kS;
         if (kb >= kS) mbar_wait(smem_u32(empty + s), (uint32_t)((kb / kS - 1) & 1));
         const uint32_t bar = smem_u32(full + s), stage = smem_base + (uint32_t)s * kSB;
         if (MLP_DBG(2)) { mbar_arrive(bar); continue; }
         mbar_expect_tx(bar, kSB);
-        const size_t ko = (size_t)kb * tiled::kTileFloats;
+        const size_t ko = (size_t)kb * tiled::kTileElems;
         bulk_g2s(stage, L.a_hi + a_tile + ko, kOperandBytes, bar);
         bulk_g2s(stage + kOperandBytes, L.a_lo + a_tile + ko, kOperandBytes, bar);
 #pragma unroll
         for (int t = 0; t < kWT; t++) {
-          const size_t wo = w_tile + (size_t)t * n_blocks * tiled::kTileFloats + ko;
+          const size_t wo = w_tile + (size_t)t * n_blocks * tiled::kTileElems + ko;
           bulk_g2s(stage + (uint32_t)(2 + t) * kOperandBytes, L.w_hi + wo, kOperandBytes, bar);
           bulk_g2s(stage + (uint32_t)(2 + kWT + t) * kOperandBytes, L.w_lo + wo, kOperandBytes, bar);
         }
@@ -331,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
                        wh = make_desc_sw128(stage + 2 * kOperandBytes), wl = make_desc_sw128(stage + (2 + kWT) * kOperandBytes);
         const uint32_t tacc = tmem_d + (uint32_t)((g & 1) * kAccCols);
 #pragma unroll
-        for (int k = 0; k < kBK / 8; k++) {
+        for (int k = 0; k < kBK / 16; k++) {
           if (MLP_DBG(1)) break;
           const uint64_t off = (uint64_t)(k * 2);     // 32 bytes >> 4, inside the 14-bit start-address field
           const uint32_t first = (!group_start || k > 0) ? 1u : 0u;
@@ -394,36 +402,42 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
     MLP_STAMP(2);
     // every MMA has retired (the last accfull arrived) and every copy has landed: the stages are free
     if (MODE == 0) {
-      // ELU(acc + b) -> tf32 hi / lo, written as the next layer's operand tiles (tiled_layout.cuh): 128 output columns are
-      // 4 k-blocks x {hi, lo} = 8 tiles of 16 KB, assembled in shared memory and stored with 8 contiguous bulk copies
+      // ELU(acc / (s_a s_w) + b) x s_a -> fp16 hi / lo, written as the next layer's operand tiles (tiled_layout.cuh): 128
+      // output columns are 2 k-blocks x {hi, lo} = 4 tiles of 16 KB, assembled in shared memory, stored with 4 bulk copies
+      constexpr float kInv = 1.0f / (kActScale * kWeightScale);
 #pragma unroll
       for (int half = 0; half < BN / kTile; half++) {
         if (half > 0) epi_barrier();                 // the previous half has left shared memory (tid 0 waited for the reads)
 #pragma unroll
-        for (int i = 0; i < kHalfCols; i += 4) {
+        for (int i = 0; i < kHalfCols; i += 8) {
           const int col = c0 + i;                    // within this 128-column half
           const float* a = acc + half * kHalfCols + i;
-          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + half * kTile + col);
-          const float h0 = elu(a[0] + b4.x), h1 = elu(a[1] + b4.y), h2 = elu(a[2] + b4.z), h3 = elu(a[3] + b4.w);
-          float4 vh, vl;
-          vh.x = tf32_round(h0); vl.x = h0 - vh.x;
-          vh.y = tf32_round(h1); vl.y = h1 - vh.y;
-          vh.z = tf32_round(h2); vl.z = h2 - vh.z;
-          vh.w = tf32_round(h3); vl.w = h3 - vh.w;
-          const int ob = col >> 5, ch = (col & 31) >> 2;
+          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + half * kTile + col);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias_s + half * kTile + col + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          __half2 ph[4], pl[4];
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const float h0 = elu(fmaf(a[j], kInv, bb[j])) * kActScale, h1 = elu(fmaf(a[j + 1], kInv, bb[j + 1])) * kActScale;
+            const __half2 hh = __floats2half2_rn(h0, h1);
+            const float2 hf2 = __half22float2(hh);
+            ph[j >> 1] = hh;
+            pl[j >> 1] = __floats2half2_rn(h0 - hf2.x, h1 - hf2.y);
+          }
+          const int ob = col >> 6, ch = (col & 63) >> 3;
           unsigned char* dst = smem + ob * kOperandBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4);
-          *reinterpret_cast<float4*>(dst) = vh;
-          *reinterpret_cast<float4*>(dst + 4 * kOperandBytes) = vl;
+          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(ph);
+          *reinterpret_cast<uint4*>(dst + 2 * kOperandBytes) = *reinterpret_cast<const uint4*>(pl);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the bulk-copy engine
         epi_barrier();
         if (half == 0) MLP_STAMP(5);
         if (tid == 0) {
-          const size_t t0 = ((size_t)blockIdx.x * (size_t)(L.out_stride >> 5) + (size_t)((n0 + half * kTile) >> 5)) * tiled::kTileFloats;
+          const size_t t0 = ((size_t)blockIdx.x * (size_t)(L.out_stride >> 6) + (size_t)((n0 + half * kTile) >> 6)) * tiled::kTileElems;
 #pragma unroll
-          for (int ob = 0; ob < 4; ob++) {
-            bulk_s2g(L.out_hi + t0 + (size_t)ob * tiled::kTileFloats, smem_base + (uint32_t)ob * kOperandBytes, kOperandBytes);
-            bulk_s2g(L.out_lo + t0 + (size_t)ob * tiled::kTileFloats, smem_base + (uint32_t)(4 + ob) * kOperandBytes, kOperandBytes);
+          for (int ob = 0; ob < 2; ob++) {
+            bulk_s2g(L.out_hi + t0 + (size_t)ob * tiled::kTileElems, smem_base + (uint32_t)ob * kOperandBytes, kOperandBytes);
+            bulk_s2g(L.out_lo + t0 + (size_t)ob * tiled::kTileElems, smem_base + (uint32_t)(2 + ob) * kOperandBytes, kOperandBytes);
           }
           bulk_commit_wait_read();
         }
@@ -435,8 +449,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
 #pragma unroll
       for (int i = 0; i < kHalfCols; i += 4) {
         const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + i);
-        acc[i] = elu(acc[i] + b4.x); acc[i + 1] = elu(acc[i + 1] + b4.y);
-        acc[i + 2] = elu(acc[i + 2] + b4.z); acc[i + 3] = elu(acc[i + 3] + b4.w);
+        constexpr float kInv = 1.0f / (kActScale * kWeightScale);
+        acc[i] = elu(fmaf(acc[i], kInv, b4.x)); acc[i + 1] = elu(fmaf(acc[i + 1], kInv, b4.y));
+        acc[i + 2] = elu(fmaf(acc[i + 2], kInv, b4.z)); acc[i + 3] = elu(fmaf(acc[i + 3], kInv, b4.w));
       }
       const int row = m0 + r;
       float yv[kMaxOut];
@@ -475,25 +490,30 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
   }
 }
 
-// x [M, K] fp32 row-major -> hi / lo in the tiled layout [Mp, Kp] (padding is left as it is: zero-initialised by the owner)
-__global__ void split_kernel(const float* x, int M, int K, float* hi, float* lo, int Kp) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)M * K) return;
-  const int m = (int)(idx / K), k = (int)(idx - (size_t)m * K);
-  const float v = x[idx];
-  const float h = fimtc::tf32_round(v);
-  const size_t o = tiled::offset(m, k, Kp);
-  hi[o] = h;
-  lo[o] = v - h;
+// the fp16 pair of x * scale
+__device__ __forceinline__ void split_half(float x, float scale, __half* hi, __half* lo) {
+  const float v = x * scale;
+  const __half h = __float2half_rn(v);
+  *hi = h;
+  *lo = __float2half_rn(v - __half2float(h));
 }
 
-// hi + lo in the tiled layout -> x [M, K] row-major (inspection / tests)
-__global__ void unsplit_kernel(const float* hi, const float* lo, int M, int K, int Kp, float* x) {
+// x [M, K] fp32 row-major -> hi / lo in the tiled layout [Mp, Kp] (padding is left as it is: zero-initialised by the owner)
+__global__ void split_kernel(const float* x, int M, int K, __half* hi, __half* lo, int Kp) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)M * K) return;
   const int m = (int)(idx / K), k = (int)(idx - (size_t)m * K);
   const size_t o = tiled::offset(m, k, Kp);
-  x[idx] = hi[o] + lo[o];
+  split_half(x[idx], kActScale, hi + o, lo + o);
+}
+
+// (hi + lo) / scale in the tiled layout -> x [M, K] row-major (inspection / tests; exact to ~2^-22 relative)
+__global__ void unsplit_kernel(const __half* hi, const __half* lo, int M, int K, int Kp, float* x) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)M * K) return;
+  const int m = (int)(idx / K), k = (int)(idx - (size_t)m * K);
+  const size_t o = tiled::offset(m, k, Kp);
+  x[idx] = (__half2float(hi[o]) + __half2float(lo[o])) * (1.0f / kActScale);
 }
 
 }  // namespace mlptc

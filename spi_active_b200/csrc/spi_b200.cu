@@ -942,7 +942,7 @@ int spi_b200_fim_reward(spi_b200_model* m, const float* states, int Mn, int P, f
 
 int spi_b200_active_post_step(spi_b200_model* m, float* state, const float* raw_actions, unsigned char* done,
                               const float* main_commands, int T, float* commands, float* actions, float* gait,
-                              float* clock, float* history, float* obs, float* obs_hi, float* obs_lo, int obs_stride,
+                              float* clock, float* history, float* obs, void* obs_hi, void* obs_lo, int obs_stride,
                               int ring_slots, const int* hist_index, float* fim_hist,
                               unsigned char* fim_live, float* dead_steps, const int* schedule, int* counter, int* ctrl,
                               int Mn, int P1, float dt, float action_clip, float clip_obs, float grav_x, float grav_y,
@@ -968,7 +968,8 @@ int spi_b200_active_post_step(spi_b200_model* m, float* state, const float* raw_
   activestep::Args A;
   A.state = state; A.raw_actions = raw_actions; A.done = done; A.main_commands = main_commands; A.commands = commands;
   A.actions = actions; A.gait = gait; A.clock = clock; A.history = history; A.obs = obs; A.hist_index = hist_index;
-  A.obs_hi = obs_hi; A.obs_lo = obs_lo; A.obs_stride = obs_stride; A.ring_slots = ring_slots;
+  A.obs_hi = static_cast<__half*>(obs_hi); A.obs_lo = static_cast<__half*>(obs_lo); A.obs_stride = obs_stride;
+  A.obs_scale = mlptc::kActScale; A.ring_slots = ring_slots;
   A.fim_hist = fim_hist; A.fim_live = fim_live; A.dead_steps = dead_steps; A.ctrl = ctrl;
   A.M = Mn; A.P1 = P1; A.T = T; A.dt = dt; A.action_clip = action_clip; A.clip_obs = clip_obs;
   A.grav_x = grav_x; A.grav_y = grav_y;
@@ -984,16 +985,16 @@ int spi_b200_active_post_step(spi_b200_model* m, float* state, const float* raw_
 struct spi_b200_policy {
   int dims[5] = {0, 0, 0, 0, 0};       // in, h1, h2, h3 (= 128), out
   int Kp = 0;                          // padded input width (multiple of 32)
-  float* w_hi[3] = {nullptr, nullptr, nullptr};
-  float* w_lo[3] = {nullptr, nullptr, nullptr};
+  __half* w_hi[3] = {nullptr, nullptr, nullptr};   // x kWeightScale, fp16 pair, tiled
+  __half* w_lo[3] = {nullptr, nullptr, nullptr};
   float* bias[3] = {nullptr, nullptr, nullptr};
   float* w_out = nullptr; float* b_out = nullptr;
-  float* act[4] = {nullptr, nullptr, nullptr, nullptr};   // h1 hi, h1 lo, h2 hi, h2 lo
+  __half* act[4] = {nullptr, nullptr, nullptr, nullptr};  // h1 hi, h1 lo, h2 hi, h2 lo
   size_t act_rows = 0;
   std::vector<float> w1_host;          // layer-1 weights [h1, in] (ring copies are built from it)
-  float* ring_hi = nullptr; float* ring_lo = nullptr;   // [n_rot] tiled copies of layer 1 with permuted columns
+  __half* ring_hi = nullptr; __half* ring_lo = nullptr; // [n_rot] tiled copies of layer 1 with permuted columns
   int n_rot = 0;
-  size_t rot_stride = 0;               // floats between two copies
+  size_t rot_stride = 0;               // elements between two copies
   // row chunks of a forward run as independent layer chains on side streams (policy_forward_impl)
   static constexpr int kMaxChunks = 8;
   cudaStream_t side[kMaxChunks - 1] = {};
@@ -1070,12 +1071,12 @@ static cudaError_t mlp_launch(int mode, int layer, mlptc::LayerArgs L, int m_til
   return cudaGetLastError();
 }
 
-static float tf32_rna_host(float x) {   // round to nearest, ties away: the value cvt.rna.tf32.f32 produces
-  uint32_t u; std::memcpy(&u, &x, 4);
-  if ((u & 0x7F800000u) == 0x7F800000u) return x;
-  u = (u + 0x1000u) & 0xFFFFE000u;
-  float r; std::memcpy(&r, &u, 4);
-  return r;
+// the fp16 pair of w * kWeightScale (host side of mlptc::split_half)
+static void split_half_host(float w, __half* hi, __half* lo) {
+  const float v = w * mlptc::kWeightScale;
+  const __half h = __float2half_rn(v);
+  *hi = h;
+  *lo = __float2half_rn(v - __half2float(h));
 }
 
 int spi_b200_policy_create(const int* dims, const float* const* weights, const float* const* biases,
@@ -1095,15 +1096,13 @@ int spi_b200_policy_create(const int* dims, const float* const* weights, const f
   cudaError_t e = cudaSuccess;
   for (int l = 0; l < 3 && e == cudaSuccess; l++) {
     const int N = dims[l + 1], K = dims[l], Kp = (l == 0) ? p->Kp : K;
-    std::vector<float> hi((size_t)N * Kp, 0.f), lo((size_t)N * Kp, 0.f);
+    std::vector<__half> hi((size_t)N * Kp, __float2half_rn(0.f)), lo((size_t)N * Kp, __float2half_rn(0.f));
     for (int n = 0; n < N; n++)
       for (int k = 0; k < K; k++) {
-        const float w = weights[l][(size_t)n * K + k];
-        const float h = tf32_rna_host(w);
         const size_t o = tiled::offset(n, k, Kp);
-        hi[o] = h; lo[o] = w - h;
+        split_half_host(weights[l][(size_t)n * K + k], &hi[o], &lo[o]);
       }
-    const size_t bytes = hi.size() * sizeof(float);
+    const size_t bytes = hi.size() * sizeof(__half);
     e = cudaMalloc((void**)&p->w_hi[l], bytes);
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->w_lo[l], bytes);
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->bias[l], (size_t)N * sizeof(float));
@@ -1138,19 +1137,19 @@ int spi_b200_policy_input_layout(spi_b200_policy* p, int M, int* out_rows, int* 
   return 0;
 }
 
-int spi_b200_policy_split_input(spi_b200_policy* p, const float* x, int M, float* x_hi, float* x_lo, void* cuda_stream) {
+int spi_b200_policy_split_input(spi_b200_policy* p, const float* x, int M, void* x_hi, void* x_lo, void* cuda_stream) {
   if (!p) return fail(-1, "policy handle is NULL");
   if (M <= 0 || !x || !x_hi || !x_lo) return fail(-3, "bad arguments");
   const size_t n = (size_t)M * p->dims[0];
-  mlptc::split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(x, M, p->dims[0], x_hi, x_lo, p->Kp);
+  mlptc::split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(x, M, p->dims[0], static_cast<__half*>(x_hi), static_cast<__half*>(x_lo), p->Kp);
   return check_launch("split_kernel");
 }
 
-int spi_b200_policy_unsplit_input(spi_b200_policy* p, const float* x_hi, const float* x_lo, int M, float* x, void* cuda_stream) {
+int spi_b200_policy_unsplit_input(spi_b200_policy* p, const void* x_hi, const void* x_lo, int M, float* x, void* cuda_stream) {
   if (!p) return fail(-1, "policy handle is NULL");
   if (M <= 0 || !x || !x_hi || !x_lo) return fail(-3, "bad arguments");
   const size_t n = (size_t)M * p->dims[0];
-  mlptc::unsplit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(x_hi, x_lo, M, p->dims[0], p->Kp, x);
+  mlptc::unsplit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(static_cast<const __half*>(x_hi), static_cast<const __half*>(x_lo), M, p->dims[0], p->Kp, x);
   return check_launch("unsplit_kernel");
 }
 
@@ -1161,50 +1160,50 @@ int spi_b200_policy_enable_ring(spi_b200_policy* p, const int* col_map, int n_ro
   for (size_t i = 0; i < (size_t)n_rot * K; i++)
     if (col_map[i] < -1 || col_map[i] >= K) return fail(-3, "col_map entry outside [-1, in)");
   const size_t stride = (size_t)N * Kp;
-  std::vector<float> hi(stride * n_rot, 0.f), lo(stride * n_rot, 0.f);
+  std::vector<__half> hi(stride * n_rot, __float2half_rn(0.f)), lo(stride * n_rot, __float2half_rn(0.f));
   for (int r = 0; r < n_rot; r++)
     for (int n = 0; n < N; n++)
       for (int k = 0; k < K; k++) {
         const int c = col_map[(size_t)r * K + k];
         if (c < 0) continue;
-        const float w = p->w1_host[(size_t)n * K + c];
-        const float h = tf32_rna_host(w);
         const size_t o = (size_t)r * stride + tiled::offset(n, k, Kp);
-        hi[o] = h; lo[o] = w - h;
+        split_half_host(p->w1_host[(size_t)n * K + c], &hi[o], &lo[o]);
       }
   cudaFree(p->ring_hi); cudaFree(p->ring_lo);
   p->ring_hi = p->ring_lo = nullptr; p->n_rot = 0;
-  CUDA_OK(cudaMalloc((void**)&p->ring_hi, hi.size() * sizeof(float)));
-  CUDA_OK(cudaMalloc((void**)&p->ring_lo, lo.size() * sizeof(float)));
-  CUDA_OK(cudaMemcpy(p->ring_hi, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(p->ring_lo, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc((void**)&p->ring_hi, hi.size() * sizeof(__half)));
+  CUDA_OK(cudaMalloc((void**)&p->ring_lo, lo.size() * sizeof(__half)));
+  CUDA_OK(cudaMemcpy(p->ring_hi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(p->ring_lo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice));
   p->n_rot = n_rot; p->rot_stride = stride;
   return 0;
 }
 
-static int policy_forward_impl(spi_b200_policy* p, const float* x_hi, const float* x_lo, int M, bool ring,
+static int policy_forward_impl(spi_b200_policy* p, const void* x_hi, const void* x_lo, int M, bool ring,
                                const int* rot_dev, float* out, void* cuda_stream);
 
-int spi_b200_policy_forward(spi_b200_policy* p, const float* x_hi, const float* x_lo, int M, float* out,
+int spi_b200_policy_forward(spi_b200_policy* p, const void* x_hi, const void* x_lo, int M, float* out,
                             void* cuda_stream) {
   return policy_forward_impl(p, x_hi, x_lo, M, false, nullptr, out, cuda_stream);
 }
 
-int spi_b200_policy_forward_ring(spi_b200_policy* p, const float* x_hi, const float* x_lo, int M, const int* rot_dev,
+int spi_b200_policy_forward_ring(spi_b200_policy* p, const void* x_hi, const void* x_lo, int M, const int* rot_dev,
                                  float* out, void* cuda_stream) {
   if (p && !p->n_rot) return fail(-3, "spi_b200_policy_enable_ring has not been called");
   return policy_forward_impl(p, x_hi, x_lo, M, true, rot_dev, out, cuda_stream);
 }
 
-static int policy_forward_impl(spi_b200_policy* p, const float* x_hi, const float* x_lo, int M, bool ring,
+static int policy_forward_impl(spi_b200_policy* p, const void* x_hi_v, const void* x_lo_v, int M, bool ring,
                                const int* rot_dev, float* out, void* cuda_stream) {
+  const __half* x_hi = static_cast<const __half*>(x_hi_v);
+  const __half* x_lo = static_cast<const __half*>(x_lo_v);
   if (!p) return fail(-1, "policy handle is NULL");
   if (M <= 0 || !x_hi || !x_lo || !out) return fail(-3, "bad arguments");
   const int Mp = (M + mlptc::kTile - 1) / mlptc::kTile * mlptc::kTile;
   if (p->act_rows < (size_t)Mp) {
     for (int i = 0; i < 4; i++) { cudaFree(p->act[i]); p->act[i] = nullptr; }
     p->act_rows = 0;
-    for (int i = 0; i < 4; i++) CUDA_OK(cudaMalloc((void**)&p->act[i], (size_t)Mp * p->dims[1 + i / 2] * sizeof(float)));
+    for (int i = 0; i < 4; i++) CUDA_OK(cudaMalloc((void**)&p->act[i], (size_t)Mp * p->dims[1 + i / 2] * sizeof(__half)));
     p->act_rows = (size_t)Mp;
   }
   cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -1237,9 +1236,9 @@ static int policy_forward_impl(spi_b200_policy* p, const float* x_hi, const floa
     if (tiles <= 0 || row0 >= M) continue;
     cudaStream_t cs = (c == 0) ? st : p->side[c - 1];
     if (c > 0) CUDA_OK(cudaStreamWaitEvent(cs, p->fork, 0));
-    const size_t in_off = (size_t)t0 * (size_t)(p->Kp / 32) * tiled::kTileFloats;
-    const size_t h1_off = (size_t)t0 * (size_t)(p->dims[1] / 32) * tiled::kTileFloats;
-    const size_t h2_off = (size_t)t0 * (size_t)(p->dims[2] / 32) * tiled::kTileFloats;
+    const size_t in_off = (size_t)t0 * (size_t)(p->Kp / 64) * tiled::kTileElems;
+    const size_t h1_off = (size_t)t0 * (size_t)(p->dims[1] / 64) * tiled::kTileElems;
+    const size_t h2_off = (size_t)t0 * (size_t)(p->dims[2] / 64) * tiled::kTileElems;
     mlptc::LayerArgs L;
     std::memset(&L, 0, sizeof(L));
     // layer 1

@@ -41,7 +41,7 @@ def motor_model_id(name_or_id) -> int:
 
 class TensorCorePolicy:
     """The actor MLP (Linear-ELU x3 + Linear) on the tensor cores with fp32-grade accuracy (spi_b200_policy_*,
-    3xTF32).  `weights[l]` is the torch Linear weight [out, in]; the reference's 900-512-256-128-12 actor qualifies
+    fp16 pairs: 3 x FP16).  `weights[l]` is the torch Linear weight [out, in]; the reference's 900-512-256-128-12 actor qualifies
     (h1, h2 multiples of 128, h3 = 128, <= 16 outputs) — anything else raises and the caller keeps its cuBLAS path."""
 
     def __init__(self, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], device: torch.device):
@@ -85,8 +85,8 @@ class TensorCorePolicy:
 
     def alloc_input(self, M: int):
         rows, stride = self.input_layout(M)
-        return (torch.zeros(rows, stride, device=self.device, dtype=torch.float32),
-                torch.zeros(rows, stride, device=self.device, dtype=torch.float32))
+        return (torch.zeros(rows, stride, device=self.device, dtype=torch.float16),
+                torch.zeros(rows, stride, device=self.device, dtype=torch.float16))
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
