@@ -488,6 +488,7 @@ struct spi_b200_model {
   bool ws_ok = false;       // the blob has the Go2-family structure the fast path is compiled for
   int kernel = SPI_KERNEL_AUTO;
   int device = 0;
+  int sm_count = 148;
   // workspaces (grown on demand)
   float* d_partial = nullptr; size_t partial_cap = 0;
   int* d_bad = nullptr; size_t bad_cap = 0;
@@ -645,7 +646,12 @@ int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C
   const int minb = minb_choice();
   if (record) {
     A.out_states = out_states;
-    ws::rollout_ws_kernel<true, 2><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
+    // 2 CTAs per SM (no register cap) is the faster kernel per CTA; once the grid does not fit in one wave of it (296 CTAs:
+    // e.g. the 352 CTAs of a config-5 control step) the 4-CTAs-per-SM build keeps the step in a single wave
+    static const int rec_minb = [] { const char* e = getenv("SPI_B200_RECORD_MINB"); return e ? atoi(e) : 0; }();
+    const bool four = rec_minb ? (rec_minb == 4) : (n_cta > 2LL * m->sm_count);
+    if (four) ws::rollout_ws_kernel<true, 4><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
+    else ws::rollout_ws_kernel<true, 2><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
     return check_launch("rollout_ws_kernel<record>");
   }
   if (int rc = ensure(&m->d_partial, &m->partial_cap, (size_t)C * A.n_cta_per_cand * 3)) return rc;
@@ -759,6 +765,7 @@ int spi_b200_model_create(const float* model_blob, int n_floats, spi_b200_model*
     return fail(-5, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0"));
   }
   e = cudaGetDevice(&m->device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device);
   if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_model, sizeof(DeviceModel));
   if (e == cudaSuccess) e = cudaMemcpy(m->d_model, &m->host_model, sizeof(DeviceModel), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
