@@ -196,3 +196,45 @@ def test_compute_torques_matches_oracle(engine, oracle_lib, blob, motor):
                                      torch.from_numpy(gains), torch.from_numpy(mp), motor, flags).cpu().numpy()
         ref = oracle_lib.compute_torques(blob, a, q, qd, gains, mp, gm.MOTOR_MODELS[motor], flags, precision=32)
         np.testing.assert_allclose(out, ref, rtol=2e-6, atol=2e-5)
+
+
+def test_argument_errors_and_degenerate_sizes(engine, oracle_lib, blob):
+    """The C-ABI's error behaviour (negative code + message, no exception across the boundary, nothing launched) and the
+    smallest legal problem: C = 1, S = 1, H = 1, no parameters at all (the nominal model)."""
+    import ctypes as C
+    lib = engine.lib
+    S, ds = synth.dataset("stand", 1)
+    init, act, tgt, gains, mask, denom = synth.pack_numpy(ds)
+    dev = engine.device
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_init, d_act, d_tgt, d_gains, d_mask = t(init[:1]), t(act[:1]), t(tgt[:1]), t(gains[:1]), t(mask[:1])
+    cost = torch.zeros(1, 3, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    p = lambda x: None if x is None else C.c_void_p(x.data_ptr())
+    ids = (C.c_int * 1)(0)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def call(model=engine._handle, params=None, Cn=1, P=0, init_=d_init, S_=1, H_=1, motor=0, out=cost):
+        return lib.spi_b200_eval_candidates(model, p(params), Cn, P, ids, p(init_), p(d_act), p(d_tgt), p(d_gains), p(d_mask),
+                                            S_, H_, 4, motor, 0, C.c_float(1.0), p(out), None, p(status), stream)
+    before = engine.launch_count()
+    wide = torch.zeros(1, 17, device=dev)
+    bad_id = (C.c_int * 1)(999)
+    for kwargs, needle in [(dict(model=None), b"NULL"), (dict(Cn=0), b"positive"), (dict(S_=0), b"positive"),
+                           (dict(H_=0), b"positive"), (dict(init_=None), b"NULL"), (dict(out=None), b"NULL"),
+                           (dict(P=1), b"params is NULL"), (dict(motor=9), b"motor_model"),
+                           (dict(params=wide, P=17), b"[0,16]")]:
+        rc = call(**kwargs)
+        assert rc < 0, kwargs
+        assert needle in lib.spi_b200_last_error(), (kwargs, lib.spi_b200_last_error())
+    rc = lib.spi_b200_eval_candidates(engine._handle, p(wide), 1, 1, bad_id, p(d_init), p(d_act), p(d_tgt), p(d_gains), p(d_mask),
+                                      1, 1, 4, 0, 0, C.c_float(1.0), p(cost), None, p(status), stream)
+    assert rc < 0 and b"param id" in lib.spi_b200_last_error()
+    assert engine.launch_count() == before                      # nothing was launched by the rejected calls
+    assert call() == 0                                          # C = S = H = 1, P = 0: the nominal model
+    torch.cuda.synchronize()
+    nominal = np.array([[engine.model.base.mass]], np.float32)   # the same model, stated as a 1-parameter candidate
+    ref, _ = oracle_lib.eval_candidates(blob, nominal, [0], init[:1], act[:1, :1], tgt[:1], gains[:1], mask[:1],
+                                        cost_denominator=1.0)
+    np.testing.assert_allclose(cost.cpu().numpy(), ref, rtol=5e-5, atol=2e-6)
+    assert int(status.item()) == 0
