@@ -18,6 +18,9 @@ host cores, bounded sample), `e2e` (the same metric through the host-pointer C-A
 spi_b200_eval_candidates_host: H2D of candidates + dataset and D2H of the costs inside the timed
 region), `gpu_launches`, `clocks`.
 
+`--workload active` (optional, NOT the headline): the active-exploration rollout of BASELINE config 5 — one "step" = one
+evaluate_policy call of 1024 command trajectories per GPU x 11 envs x 1249 closed-loop control steps; reports env steps/s.
+
 `--impl reference`: the reference's own implementation of this path is Isaac Gym (closed source, not
 installable: DESIGN.md §5), so this arm times the CPU restatement (oracle/, fp32, all host threads)
 on bounded samples of the same workload.  This and the cpu_baseline leg are the only places bench.py
@@ -416,6 +419,64 @@ def emit(obj):
         print(line, flush=True)
 
 
+# ------------------------------------------------------------------------------------------------
+# optional second workload (NOT the headline metric): the active-exploration rollout of BASELINE config 5
+# ------------------------------------------------------------------------------------------------
+def run_active(args):
+    """`--workload active`: a "step" is one evaluate_policy call — 1024 command trajectories per GPU x (1 + 10) envs x
+    1249 closed-loop control steps (actor MLP on the tensor cores, physics, fused post-step, Fisher contraction), the trials
+    cut into 3 pipelines (active.PipelinedExploration).  Reports env-steps/s; same barrier / max-over-ranks timing."""
+    import torch
+    import torch.distributed as dist
+
+    from spi_active_b200 import active as act
+    from spi_active_b200.engine import RolloutEngine
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    eng = RolloutEngine(device=torch.device(f"cuda:{local_rank}"))
+    M, T = 1024, 1250
+    cfg = act.ActiveConfig(exploration_params=list(act.ActiveExploration.PARAM_ORDER), seed=rank)
+    ex = act.PipelinedExploration(eng, act.PolicyMLP.random(eng.device, seed=0, gain=0.3), M, cfg, n_pipelines=3)
+    rng = np.random.default_rng(rank)
+    r = np.asarray(act.COMMAND_RANGES)
+    vals = rng.uniform(r[act.COMMAND_SAMPLING_IDXS, 0], r[act.COMMAND_SAMPLING_IDXS, 1], (M, 5, 3)).astype(np.float32)
+    cmds = torch.from_numpy(np.stack([act.expand_commands(act.commands_constant(v, 250)) for v in vals]))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 1)):
+        out = ex.evaluate_policy(cmds, total_steps=T)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = ex.evaluate_policy(cmds, total_steps=T)
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], device=eng.device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    s_per = float(t[0]) / args.steps
+    if rank == 0:
+        rew = out["total_reward"][::ex.param_dim + 1]
+        emit({"metric": "active_env_steps_per_s", "value": world * ex.num_envs * out["steps"] / s_per, "unit": "env steps/s",
+              "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * s_per,
+              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (actor: fp16 pairs, fp32-grade)",
+              "data": "synthetic",
+              "config": {"workload": "active-exploration rollout (BASELINE config 5): 1024 command trajectories per GPU x "
+                                     "(1 + 10) envs x 1249 closed-loop control steps, 900-512-256-128-12 actor, 3 pipelines",
+                         "main_envs_per_gpu": M, "envs_per_gpu": ex.num_envs, "control_steps": out["steps"]},
+              "reward_mean": float(rew.mean()), "note": "secondary workload; the headline metric is the default run"})
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     global _GUARD
     ap = argparse.ArgumentParser()
@@ -423,6 +484,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="sysid", choices=["sysid", "active"],
+                    help="sysid (default) = the headline metric; active = the config-5 exploration rollout (secondary)")
     args = ap.parse_args()
     if not (args.gpus > 1 and "WORLD_SIZE" not in os.environ and args.impl != "reference"):
         _GUARD = _StdoutGuard()
@@ -434,7 +497,11 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(port), str(Path(__file__).resolve()),
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        if args.workload != "sysid":
+            cmd += ["--workload", args.workload]
         return subprocess.call(cmd)
+    if args.workload == "active":
+        return run_active(args)
     return run_b200(args)
 
 
