@@ -1098,6 +1098,15 @@ int spi_b200_policy_create(const int* dims, const float* const* weights, const f
   spi_b200_policy* p = new (std::nothrow) spi_b200_policy();
   if (!p) return fail(-4, "out of host memory");
   for (int i = 0; i < 5; i++) p->dims[i] = dims[i];
+  // the fp16 pairs carry weights x 256: anything a trained actor holds fits, a weight beyond +-255 would overflow to inf
+  for (int l = 0; l < 3; l++) {
+    const size_t n = (size_t)dims[l + 1] * dims[l];
+    for (size_t i = 0; i < n; i++)
+      if (!(std::fabs(weights[l][i]) * mlptc::kWeightScale < 65504.0f)) {
+        delete p;
+        return fail(-3, "tensor-core policy: a hidden-layer weight is not finite or exceeds +-255 (fp16-pair range)");
+      }
+  }
   p->Kp = (dims[0] + mlptc::kKAlign - 1) / mlptc::kKAlign * mlptc::kKAlign;
   p->w1_host.assign(weights[0], weights[0] + (size_t)dims[1] * dims[0]);
   cudaError_t e = cudaSuccess;

@@ -64,6 +64,13 @@ def test_policy_rejects_unsupported_shapes():
     ws, bs = _make((900, 512, 256, 64, 12), 0)
     with pytest.raises(SpiB200Error):
         TensorCorePolicy(ws, bs, torch.device("cuda:0"))
+    ws, bs = _make((900, 512, 256, 128, 12), 0)
+    ws[1][3, 5] = 300.0                                     # outside the fp16-pair range of the weights (+-255)
+    with pytest.raises(SpiB200Error):
+        TensorCorePolicy(ws, bs, torch.device("cuda:0"))
+    ws[1][3, 5] = float("nan")
+    with pytest.raises(SpiB200Error):
+        TensorCorePolicy(ws, bs, torch.device("cuda:0"))
 
 
 def test_policy_forward_ring_permutes_the_first_layer():
