@@ -19,7 +19,10 @@ HEADERS = [_PKG / "csrc" / "aba_leg.cuh", _PKG / "csrc" / "go2_ws.cuh", _PKG / "
            _PKG.parent / "include" / "spi_b200.h"]
 # SPI_WS_FAST_SINCOS: joint sin/cos through MUFU after a 2-constant reduction to [-pi, pi]; measured deviation from
 # the fp64 oracle stays at the fp32 noise floor of the oracle itself (profiles/README.md, tests/tools/dev_accuracy.py)
+# SPI_WS_FAST_TANH: the motor model's tanh through one ex2 + one reciprocal (|error| <= 2e-7 absolute, i.e. 4e-6 N m on a
+# torque of ~20 N m = its fp32 rounding); +0.6 % throughput, deviation from the fp64 oracle unchanged (profiles/README.md)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-DSPI_WS_FAST_SINCOS",
+              "-DSPI_WS_FAST_TANH",
               "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
 
 _lib = None

@@ -50,7 +50,7 @@ WS_HD float rsqrt_fast(float x) {
   return 1.0f / std::sqrt(x);
 #endif
 }
-// (off by default: measured neutral on B200, profiles/README.md)  tanh through one ex2 and one reciprocal: |abs error| <= ~2e-7 (the motor model a * tanh(tau / a) only needs an
+// (on by default, spi_active_b200/_lib.py)  tanh through one ex2 and one reciprocal: |abs error| <= ~2e-7 (the motor model a * tanh(tau / a) only needs an
 // absolute accuracy: 2e-7 * a ~ 4e-6 N m).  tanh(x) = sign(x) (1 - 2 / (exp(2|x|) + 1))
 WS_HD float tanh_fast(float x) {
 #if defined(__CUDA_ARCH__) && defined(SPI_WS_FAST_TANH)
