@@ -28,7 +28,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "fim_tc.cuh"   // smem_u32, mbarrier / tcgen05 helpers, tf32_round
+#include "fim_tc.cuh"   // smem_u32, mbarrier / tcgen05 helpers
 #include "tiled_layout.cuh"
 
 namespace mlptc {
@@ -52,7 +52,7 @@ constexpr int kMaxOut = 16;
 constexpr int kTailBias = 256, kTailWout = kTailBias + 1024, kTailBout = kTailWout + kMaxOut * kTile * 4;
 constexpr int kSmemBytes = kStages * kStageBytes + kTailBout + 64;
 // k-blocks per accumulator group: the tensor core's accumulation truncates (a ~3e-8 relative bias per MMA), so an
-// accumulator only ever holds 48 MMAs before it is added to the fp32 running sums in registers
+// accumulator only ever holds 32 MMAs (K = 256) before it is added to the fp32 running sums in registers
 constexpr int kGroup = 4;
 
 // K-major SWIZZLE_128B (cute::UMMA::LayoutType::SWIZZLE_128B = 2): rows are 128 bytes (32 fp32 of K), an 8-row group is
@@ -72,8 +72,8 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr) {
 
 // instruction descriptors (cute::UMMA::InstrDescriptor, see fim_tc.cuh): c_format F32 (1) at [4,6), a / b_format F16 (0) at
 // [7,10) / [10,13), K-major operands, N >> 3 at [17,23), M >> 4 at [24,29); M = 128
-__host__ __device__ constexpr uint32_t idesc_tf32(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24); }
-__device__ __forceinline__ void mma_tf32_n(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__host__ __device__ constexpr uint32_t idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24); }
+__device__ __forceinline__ void mma_f16_n(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -123,7 +123,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
   } while (!ok);
 }
 // one MMA over both SMs of a pair: M = 256 (128 rows per CTA), B rows split between the two CTAs' shared memories
-__device__ __forceinline__ void mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -138,7 +138,7 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
                "h"((uint16_t)3)
                : "memory");
 }
-__host__ __device__ constexpr uint32_t idesc_tf32_pair(int n) {   // M = 256 over the pair
+__host__ __device__ constexpr uint32_t idesc_f16_pair(int n) {   // M = 256 over the pair
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
@@ -344,16 +344,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
           const uint64_t off = (uint64_t)(k * 2);     // 32 bytes >> 4, inside the 14-bit start-address field
           const uint32_t first = (!group_start || k > 0) ? 1u : 0u;
           if (PAIR) {              // M = 256 over the pair, N = 256: this CTA's 128 weight rows + the peer's
-            mma_tf32_pair(tacc, al + off, wh + off, idesc_tf32_pair(256), first);
-            mma_tf32_pair(tacc, ah + off, wl + off, idesc_tf32_pair(256), 1u);
-            mma_tf32_pair(tacc, ah + off, wh + off, idesc_tf32_pair(256), 1u);
+            mma_f16_pair(tacc, al + off, wh + off, idesc_f16_pair(256), first);
+            mma_f16_pair(tacc, ah + off, wl + off, idesc_f16_pair(256), 1u);
+            mma_f16_pair(tacc, ah + off, wh + off, idesc_f16_pair(256), 1u);
           } else if (BN == 256) {
-            mma_tf32_n(tacc, al + off, wh + off, idesc_tf32(256), first);
-            mma_tf32_n(tacc, ah + off, wl + off, idesc_tf32(256), 1u);
-            mma_tf32_n(tacc, ah + off, wh + off, idesc_tf32(256), 1u);
+            mma_f16_n(tacc, al + off, wh + off, idesc_f16(256), first);
+            mma_f16_n(tacc, ah + off, wl + off, idesc_f16(256), 1u);
+            mma_f16_n(tacc, ah + off, wh + off, idesc_f16(256), 1u);
           } else {
-            mma_tf32_n(tacc, ah + off, wh + off, idesc_tf32(256), first);   // [0,128) += a_hi w_hi, [128,256) += a_hi w_lo
-            mma_tf32_n(tacc, al + off, wh + off, idesc_tf32(128), 1u);      // [0,128) += a_lo w_hi
+            mma_f16_n(tacc, ah + off, wh + off, idesc_f16(256), first);   // [0,128) += a_hi w_hi, [128,256) += a_hi w_lo
+            mma_f16_n(tacc, al + off, wh + off, idesc_f16(128), 1u);      // [0,128) += a_lo w_hi
           }
         }
         if (PAIR) {
