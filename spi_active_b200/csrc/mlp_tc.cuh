@@ -55,7 +55,7 @@ constexpr int kSmemBytes = kStages * kStageBytes + kTailBout + 64;
 // accumulator only ever holds 32 MMAs (K = 256) before it is added to the fp32 running sums in registers
 constexpr int kGroup = 4;
 
-// K-major SWIZZLE_128B (cute::UMMA::LayoutType::SWIZZLE_128B = 2): rows are 128 bytes (32 fp32 of K), an 8-row group is
+// K-major SWIZZLE_128B (cute::UMMA::LayoutType::SWIZZLE_128B = 2): rows are 128 bytes (64 halves of K), an 8-row group is
 // 1024 contiguous bytes, the 16-byte chunk c of row r sits at chunk position c ^ (r & 7); SBO = 1024 between row groups,
 // the leading-dimension field is 1 (unused: one swizzle atom spans the tile's K extent); a k-step of 16 halves advances the
 // start address by 32 bytes inside the atom.  Tile bases are 1024-byte aligned (base_offset 0).  Measured: the no-swizzle
