@@ -135,10 +135,25 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, int lan
         float out[4 * kLegVec];
         out[4 * kLegVec - 1] = 0.f;
         leg_phase1(S, L, bc, s, tau, K, out, nullptr);
+        // the four legs are summed pairwise: the even leg of a pair publishes and signals (bar.arrive on the pair's own named
+        // barrier, 64 threads), the odd leg waits for it, adds its own contribution and publishes the pair sum — the base
+        // role then only adds two vectors in its serial section ((p0 + p1) + (p2 + p3), the same order as before)
+        if ((LEG & 1) == 0) {
 #pragma unroll
-        for (int v = 0; v < kLegVec; v++)
-          sm.part[LEG][v][lane] = make_float4(out[4 * v], out[4 * v + 1], out[4 * v + 2], out[4 * v + 3]);
-        ws_barrier();   // [A]  leg contributions are in shared memory
+          for (int v = 0; v < kLegVec; v++)
+            sm.part[LEG][v][lane] = make_float4(out[4 * v], out[4 * v + 1], out[4 * v + 2], out[4 * v + 3]);
+          if (LEG < 2) asm volatile("bar.arrive 2, 64;" ::: "memory");
+          else asm volatile("bar.arrive 3, 64;" ::: "memory");
+        } else {
+          if (LEG < 2) asm volatile("bar.sync 2, 64;" ::: "memory");
+          else asm volatile("bar.sync 3, 64;" ::: "memory");
+#pragma unroll
+          for (int v = 0; v < kLegVec; v++) {
+            const float4 p = sm.part[LEG - 1][v][lane];
+            sm.part[LEG][v][lane] = make_float4(p.x + out[4 * v], p.y + out[4 * v + 1], p.z + out[4 * v + 2], p.w + out[4 * v + 3]);
+          }
+        }
+        ws_barrier();   // [A]  the pair sums are in shared memory
         ws_barrier();   // [B1] the base role has published a0
         ws_load_a0(sm, lane, bc + kBcA0);
         leg_phase2(L, bc, K, s, h);
@@ -202,11 +217,11 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, int la
         float legsum[4 * kLegVec];
 #pragma unroll
         for (int v = 0; v < kLegVec; v++) {
-          const float4 p0 = sm.part[0][v][lane], p1 = sm.part[1][v][lane], p2 = sm.part[2][v][lane], p3 = sm.part[3][v][lane];
-          legsum[4 * v] = (p0.x + p1.x) + (p2.x + p3.x);
-          legsum[4 * v + 1] = (p0.y + p1.y) + (p2.y + p3.y);
-          legsum[4 * v + 2] = (p0.z + p1.z) + (p2.z + p3.z);
-          legsum[4 * v + 3] = (p0.w + p1.w) + (p2.w + p3.w);
+          const float4 p01 = sm.part[1][v][lane], p23 = sm.part[3][v][lane];      // pair sums (written by the odd legs)
+          legsum[4 * v] = p01.x + p23.x;
+          legsum[4 * v + 1] = p01.y + p23.y;
+          legsum[4 * v + 2] = p01.z + p23.z;
+          legsum[4 * v + 3] = p01.w + p23.w;
         }
         float a0[6];
         base_solve(B, legsum, pb, a0);
