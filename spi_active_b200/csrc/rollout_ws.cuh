@@ -23,7 +23,9 @@ struct WsArgs {
   const unsigned char* seg_mask;
   int S, H, decimation, motor_model; unsigned flags;
   int n_cta_per_cand;
+  int C_grid;          // number of candidate rows of the grid (C; 1 in paired mode)
   int rotate_roles;
+  int token_mode;
   int paired;          // 1: rollout r uses candidate row r AND segment r (one env per rollout; C == 1 for the grid)
   float* partial;      // [C][n_cta_per_cand][3]
   float* per_seg;      // [C][S][3] or null
@@ -80,12 +82,51 @@ __device__ __forceinline__ bool finite_acc(float acc) { return acc == 0.f; }  //
 // (every role executes the same number of ws_barrier() calls).
 __device__ __forceinline__ void ws_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kWsThreads) : "memory"); }
 
+// Named-barrier plan.  HALVES == 1 (one 32-rollout group per CTA): barrier 1 = the group's 160 threads, 2 / 3 = the leg pairs.
+// HALVES == 2 (two groups per CTA, DESIGN.md 4.2 "anti-phase pairing"): group g uses 1 + 3 g, 2 + 3 g, 3 + 3 g, and the two
+// groups hand a token back and forth on barriers 7 / 8 (256 = the 8 leg warps) so that their leg phases 1 never overlap:
+// resident CTAs of this kernel otherwise fall into lock-step (all legs in phase 1, then all waiting for their base role),
+// which left 22 % of the issue slots empty although 2.1 warps per scheduler were eligible on average (profiles/README.md r2).
+template <int HALVES> struct WsBars {
+  int g;
+  int mode;   // experiment switch: 2 = token on every sub-step, 1 = first sub-step only (initial stagger), 0 = none
+  __device__ __forceinline__ void cta() const {
+    if (HALVES == 1) ws_barrier();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + 3 * g), "n"(kWsThreads) : "memory");
+  }
+  __device__ __forceinline__ void pair_arrive(int leg) const {
+    if (HALVES == 1) {
+      if (leg < 2) asm volatile("bar.arrive 2, 64;" ::: "memory");
+      else asm volatile("bar.arrive 3, 64;" ::: "memory");
+    } else asm volatile("bar.arrive %0, 64;" ::"r"(2 + 3 * g + (leg >> 1)) : "memory");
+  }
+  __device__ __forceinline__ void pair_sync(int leg) const {
+    if (HALVES == 1) {
+      if (leg < 2) asm volatile("bar.sync 2, 64;" ::: "memory");
+      else asm volatile("bar.sync 3, 64;" ::: "memory");
+    } else asm volatile("bar.sync %0, 64;" ::"r"(2 + 3 * g + (leg >> 1)) : "memory");
+  }
+  // phase-1 token: group 0 owns it first.  wait = before phase 1 (n = index of the sub-step), pass = after phase 1.
+  __device__ __forceinline__ void token_wait(int n) const {
+    if (HALVES == 1 || mode == 0) return;
+    if (mode == 1) { if (g == 1 && n == 0) asm volatile("bar.sync 7, 256;" ::: "memory"); return; }
+    if (g == 0) { if (n > 0) asm volatile("bar.sync 8, 256;" ::: "memory"); }
+    else asm volatile("bar.sync 7, 256;" ::: "memory");
+  }
+  __device__ __forceinline__ void token_pass(int n, int n_total) const {
+    if (HALVES == 1 || mode == 0) return;
+    if (mode == 1) { if (g == 0 && n == 0) asm volatile("bar.arrive 7, 256;" ::: "memory"); return; }
+    if (g == 0) asm volatile("bar.arrive 7, 256;" ::: "memory");
+    else if (n + 1 < n_total) asm volatile("bar.arrive 8, 256;" ::: "memory");
+  }
+};
+
 // LEG is a warp-uniform run-time value (one code copy for the four legs: four template copies overflow the
 // instruction cache — profiles/README.md, experiment ws-templated); the leg's constants are then fetched through
 // the constant bank with a uniform offset.
-template <bool RECORD>
-__device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, int lane, const int LEG, int c, int seg,
-                                            bool active) {
+template <bool RECORD, int HALVES>
+__device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, const WsBars<HALVES> bars, int lane, const int LEG,
+                                            int c, int seg, bool active) {
   const SimK& S = A.M.sim;
   const LegK& L = A.M.leg[LEG];
   // this leg's motor parameters (act2tau_scalar uses one gain for every joint)
@@ -120,7 +161,9 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, int lan
   const float* act_row = A.seg_actions + (size_t)seg * A.H * 12 + 3 * LEG;
   LegKeep K;
   const bool zero_act = A.zero_mask && A.zero_mask[seg] != 0;
-  ws_barrier();   // [S0] the base role has published R / v0 / pz of the initial state
+  bars.cta();   // [S0] the base role has published R / v0 / pz of the initial state
+  const int n_sub_total = A.H * A.decimation * S.nsub;
+  int i_sub = 0;
   for (int k = 0; k < A.H; k++) {
     float act[3];
 #pragma unroll
@@ -129,12 +172,14 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, int lan
     for (int d = 0; d < A.decimation; d++) {
       float tau[3];
       leg_torques(S, L, act, s.q, s.qd, kp, kd, motor, A.motor_model, A.flags, tau);
-      for (int n = 0; n < S.nsub; n++) {
+      for (int n = 0; n < S.nsub; n++, i_sub++) {
+        bars.token_wait(i_sub);      // HALVES == 2: the other group's legs have finished their phase 1
         float bc[kBaseOut];
         ws_load_state(sm, lane, bc);
         float out[4 * kLegVec];
         out[4 * kLegVec - 1] = 0.f;
         leg_phase1(S, L, bc, s, tau, K, out, nullptr);
+        bars.token_pass(i_sub, n_sub_total);
         // the four legs are summed pairwise: the even leg of a pair publishes and signals (bar.arrive on the pair's own named
         // barrier, 64 threads), the odd leg waits for it, adds its own contribution and publishes the pair sum — the base
         // role then only adds two vectors in its serial section ((p0 + p1) + (p2 + p3), the same order as before)
@@ -142,22 +187,20 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, int lan
 #pragma unroll
           for (int v = 0; v < kLegVec; v++)
             sm.part[LEG][v][lane] = make_float4(out[4 * v], out[4 * v + 1], out[4 * v + 2], out[4 * v + 3]);
-          if (LEG < 2) asm volatile("bar.arrive 2, 64;" ::: "memory");
-          else asm volatile("bar.arrive 3, 64;" ::: "memory");
+          bars.pair_arrive(LEG);
         } else {
-          if (LEG < 2) asm volatile("bar.sync 2, 64;" ::: "memory");
-          else asm volatile("bar.sync 3, 64;" ::: "memory");
+          bars.pair_sync(LEG);
 #pragma unroll
           for (int v = 0; v < kLegVec; v++) {
             const float4 p = sm.part[LEG - 1][v][lane];
             sm.part[LEG][v][lane] = make_float4(p.x + out[4 * v], p.y + out[4 * v + 1], p.z + out[4 * v + 2], p.w + out[4 * v + 3]);
           }
         }
-        ws_barrier();   // [A]  the pair sums are in shared memory
-        ws_barrier();   // [B1] the base role has published a0
+        bars.cta();   // [A]  the pair sums are in shared memory
+        bars.cta();   // [B1] the base role has published a0
         ws_load_a0(sm, lane, bc + kBcA0);
         leg_phase2(L, bc, K, s, h);
-        ws_barrier();   // [B2] the base role has published R / v0 / pz of the new state
+        bars.cta();   // [B2] the base role has published R / v0 / pz of the new state
       }
     }
     if (RECORD) {
@@ -166,7 +209,7 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, int lan
 #pragma unroll
         for (int j = 0; j < 3; j++) { row[13 + 3 * LEG + j] = s.q[j]; row[25 + 3 * LEG + j] = s.qd[j]; }
       }
-      ws_barrier();   // [R] keeps the barrier count of the base role (which writes its rows here)
+      bars.cta();   // [R] keeps the barrier count of the base role (which writes its rows here)
     }
   }
   if (RECORD) return;
@@ -181,12 +224,12 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, int lan
   }
   sm.ej[LEG][lane] = ej;
   sm.finite[LEG][lane] = finite_acc(acc) ? 1 : 0;
-  ws_barrier();   // [C]
+  bars.cta();   // [C]
 }
 
-template <bool RECORD>
-__device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, int lane, int c, int cta_in_cand, int seg,
-                                             bool active) {
+template <bool RECORD, int HALVES>
+__device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, const WsBars<HALVES> bars, int lane, int c,
+                                             int cta_in_cand, int seg, bool active, bool group_live) {
   const SimK& S = A.M.sim;
   BaseInertia B;
   {
@@ -208,12 +251,12 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, int la
   ws_store_state(sm, lane, bc);
   float pb[6];
   base_bias(B, bc, pb);
-  ws_barrier();   // [S0]
+  bars.cta();   // [S0]
   const float h = S.dt / (float)S.nsub;
   for (int k = 0; k < A.H; k++) {
     for (int d = 0; d < A.decimation; d++) {
       for (int n = 0; n < S.nsub; n++) {
-        ws_barrier();   // [A]
+        bars.cta();   // [A]
         float legsum[4 * kLegVec];
 #pragma unroll
         for (int v = 0; v < kLegVec; v++) {
@@ -226,7 +269,7 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, int la
         float a0[6];
         base_solve(B, legsum, pb, a0);
         ws_store_a0(sm, lane, a0);
-        ws_barrier();   // [B1] the legs start their acceleration pass
+        bars.cta();   // [B1] the legs start their acceleration pass
         // keep the integration BEHIND the barrier: it only needs registers, so ptxas would otherwise schedule it between
         // the a0 stores and the barrier and delay the legs by ~90 instructions.  Reading a0 back from shared memory is a
         // dependency the scheduler cannot move across bar.sync (6 LDS, off the critical path).
@@ -236,7 +279,7 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, int la
         }
         base_advance(S, a0, s, h, bc);
         ws_store_state(sm, lane, bc);
-        ws_barrier();   // [B2]
+        bars.cta();   // [B2]
         // velocity-product bias of the next sub-step: after the barrier, so that it overlaps the legs' phase 1 instead
         // of delaying their release (re-read through shared memory for the same reason as a0 above)
         {                                              // logical bc[15 .. 21) = floats 9 .. 14 of the packed state
@@ -254,7 +297,7 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, int la
 #pragma unroll
         for (int i = 0; i < 4; i++) row[3 + i] = s.quat[i];
       }
-      ws_barrier();   // [R]
+      bars.cta();   // [R]
     }
   }
   if (RECORD) return;
@@ -273,7 +316,7 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, int la
     eq += e * e;
     acc += s.quat[i] * 0.f;
   }
-  ws_barrier();   // [C]
+  bars.cta();   // [C]
   const float ej = (sm.ej[0][lane] + sm.ej[1][lane]) + (sm.ej[2][lane] + sm.ej[3][lane]);
   const bool ok = finite_acc(acc) && (sm.finite[0][lane] & sm.finite[1][lane] & sm.finite[2][lane] & sm.finite[3][lane]);
   float err[3] = {sqrtf(ep), sqrtf(eq), sqrtf(ej)};
@@ -290,31 +333,55 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, int la
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     err[i] = v;
   }
-  if (lane == 0) {
+  if (lane == 0 && group_live) {
     float* o = A.partial + ((size_t)c * A.n_cta_per_cand + cta_in_cand) * 3;
     o[0] = err[0]; o[1] = err[1]; o[2] = err[2];
   }
 }
 
-template <bool RECORD>
+// HALVES == 1: blockIdx = one group of 32 rollouts, warps 0..3 = legs, warp 4 = base.
+// HALVES == 2: blockIdx = two consecutive groups; warps 0..3 / 4..7 = the legs of group 0 / 1 (leg i of both groups shares a
+// sub-partition, and the phase-1 token makes them take turns on it), warps 8 / 9 = the two base roles (highest warp ids: the
+// arbiter favours them).  An odd group count leaves the last CTA's second group without work: it replays the last group with
+// every write suppressed (the token protocol needs both groups).
+template <bool RECORD, int HALVES>
 __device__ __forceinline__ void rollout_ws_body(const WsArgs& A) {
-  __shared__ WsSmem sm;
+  __shared__ WsSmem sm_all[HALVES];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int role = __shfl_sync(0xffffffffu, A.rotate_roles ? (warp + blockIdx.x) % kWsWarps : warp, 0);  // warp-uniform
-  const int cg = blockIdx.x / A.n_cta_per_cand;
-  const int cta_in_cand = blockIdx.x - cg * A.n_cta_per_cand;
+  int role, g;
+  if (HALVES == 1) {
+    role = __shfl_sync(0xffffffffu, A.rotate_roles ? (warp + blockIdx.x) % kWsWarps : warp, 0);  // warp-uniform
+    g = 0;
+  } else {
+    const int w = __shfl_sync(0xffffffffu, warp, 0);
+    role = (w < 8) ? (w & 3) : 4;
+    g = (w < 8) ? (w >> 2) : (w - 8);
+  }
+  const long long n_groups = (long long)A.C_grid * A.n_cta_per_cand;
+  long long grp = (long long)blockIdx.x * HALVES + g;
+  const bool group_live = grp < n_groups;
+  if (!group_live) grp = n_groups - 1;
+  const int cg = (int)(grp / A.n_cta_per_cand);
+  const int cta_in_cand = (int)(grp - (long long)cg * A.n_cta_per_cand);
   const int seg_raw = cta_in_cand * kWsRollouts + lane;
-  const bool active = seg_raw < A.S;
-  const int seg = active ? seg_raw : A.S - 1;
+  const bool active = group_live && seg_raw < A.S;
+  const int seg = seg_raw < A.S ? seg_raw : A.S - 1;
   const int c = A.paired ? seg : cg;
-  if (role < 4) ws_leg_role<RECORD>(A, sm, lane, role, c, seg, active);
-  else ws_base_role<RECORD>(A, sm, lane, c, cta_in_cand, seg, active);
+  WsSmem& sm = sm_all[g];
+  const WsBars<HALVES> bars{g, A.token_mode};
+  if (role < 4) ws_leg_role<RECORD, HALVES>(A, sm, bars, lane, role, c, seg, active);
+  else ws_base_role<RECORD, HALVES>(A, sm, bars, lane, c, cta_in_cand, seg, active, group_live);
 }
 
 template <bool RECORD, int MINB>
 __global__ void __launch_bounds__(kWsThreads, MINB) rollout_ws_kernel(const __grid_constant__ WsArgs A) {
-  rollout_ws_body<RECORD>(A);
+  rollout_ws_body<RECORD, 1>(A);
 }
 
+// two anti-phased groups per CTA (evaluation only; the RECORD / paired launches are latency-bound single waves)
+template <int MINB>
+__global__ void __launch_bounds__(2 * kWsThreads, MINB) rollout_ws2_kernel(const __grid_constant__ WsArgs A) {
+  rollout_ws_body<false, 2>(A);
+}
 
 }  // namespace ws

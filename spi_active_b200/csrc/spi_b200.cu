@@ -639,7 +639,8 @@ int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C
   A.seg_init = seg_init; A.seg_actions = seg_actions; A.seg_target = seg_target; A.seg_gains = seg_gains;
   A.seg_mask = seg_mask; A.S = S; A.H = H; A.decimation = decimation; A.motor_model = motor_model; A.flags = flags;
   A.n_cta_per_cand = (S + ws::kWsRollouts - 1) / ws::kWsRollouts;
-  A.paired = paired; A.zero_mask = zero_mask;
+  A.paired = paired; A.zero_mask = zero_mask; A.C_grid = C;
+  { static const int tm = getenv("SPI_B200_WS_TOKEN") ? atoi(getenv("SPI_B200_WS_TOKEN")) : 2; A.token_mode = tm; }
   { static const int rot = getenv("SPI_B200_WS_ROT") ? atoi(getenv("SPI_B200_WS_ROT")) : 0; A.rotate_roles = rot; }
   const long long n_cta = (long long)C * A.n_cta_per_cand;
   if (n_cta > 2147483647LL) return fail(-3, "C * ceil(S/32) exceeds the grid limit");
@@ -663,7 +664,15 @@ int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C
     if (int rc = timing_events(m, &e0, &e1)) return rc;
     CUDA_OK(cudaEventRecord(e0, st));
   }
-  if (minb == 2) ws::rollout_ws_kernel<false, 2><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
+  // Two anti-phased 32-rollout groups per CTA (rollout_ws.cuh) once the grid fills the GPU more than once; below that
+  // the launch is a single partial wave and the one-group CTAs spread over more SMs.  SPI_B200_WS_HALVES = 1 / 2 forces.
+  static const int halves_env = [] { const char* e = getenv("SPI_B200_WS_HALVES"); return e ? atoi(e) : 0; }();
+  const bool two = halves_env ? (halves_env == 2) : (n_cta > 4LL * m->sm_count);
+  if (two) {
+    const unsigned n2 = (unsigned)((n_cta + 1) / 2);
+    if (minb == 1) ws::rollout_ws2_kernel<1><<<n2, 2 * ws::kWsThreads, 0, st>>>(A);
+    else ws::rollout_ws2_kernel<2><<<n2, 2 * ws::kWsThreads, 0, st>>>(A);
+  } else if (minb == 2) ws::rollout_ws_kernel<false, 2><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
   else if (minb == 3) ws::rollout_ws_kernel<false, 3><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
   else ws::rollout_ws_kernel<false, 4><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
   if (int rc = check_launch("rollout_ws_kernel")) return rc;

@@ -31,6 +31,12 @@ reference's real, unmodified code object, called with plain torch tensors:
                      averaging / PD-gain / control-decimation semantics end to end, including quirks D2
                      (chunk-dependent eval_mask) and D3 (gains of row 0 of each chunk).
 
+  urdf_blob.npz      the 312-float model blob built from the reference's own spigym/data/robots/go2/urdf/go2.urdf by
+                     spi_active_b200.go2_model.model_from_urdf (pins the typed-in table of go2_nominal())
+  ppo_actor.pt/.npz  a checkpoint in the layout of PPO.save (spigym/agents/ppo/ppo.py:155-166) holding the state dict of the
+                     reference's real PPOActor (agents/modules/ppo_modules.py, modules.py:47-63; a small 60-32-16-8-12 ELU
+                     instance of config/algo/ppo.yaml:31-39) + observations and its act_inference outputs
+
 What this cannot pin is the rigid-body physics itself: PhysX is not available.
 """
 from __future__ import annotations
@@ -362,8 +368,45 @@ def gen_active_obs(R, rng):
     print("active_obs.npz", np.stack(out["actor_obs"]).shape)
 
 
+def gen_urdf_blob():
+    from spi_active_b200 import go2_model as gm
+    urdf = REF / "spigym" / "data" / "robots" / "go2" / "urdf" / "go2.urdf"
+    m = gm.model_from_urdf(urdf)
+    blob = gm.build_model_blob(m)
+    np.savez(HERE / "urdf_blob.npz", blob=blob, body_masses=m.body_masses_isaac_order(), total_mass=np.float64(m.total_mass()))
+    print("urdf_blob.npz", blob.shape, "== go2_nominal():", bool(np.array_equal(blob, gm.build_model_blob(gm.go2_nominal()))))
+
+
+class AttrDict(dict):
+    """omegaconf / easydict stand-in: the reference indexes its module config both ways (modules.py:13, 19)."""
+    __getattr__ = dict.__getitem__
+
+
+def gen_ppo_actor():
+    from spigym.agents.modules.ppo_modules import PPOActor, PPOCritic
+    torch.manual_seed(5)
+    dims = dict(actor_obs=60, critic_obs=70)
+    layer = lambda: AttrDict(type="MLP", hidden_dims=[32, 16, 8], activation="ELU")      # ppo.yaml:31-39, scaled down
+    actor = PPOActor(obs_dim_dict=dims, module_config_dict=AttrDict(input_dim=["actor_obs"], output_dim=["robot_action_dim"],
+                                                                   layer_config=layer()), num_actions=12, init_noise_std=0.8)
+    critic = PPOCritic(dims, AttrDict(type="MLP", input_dim=["critic_obs"], output_dim=[1], layer_config=layer()))
+    with torch.no_grad():
+        for prm in actor.parameters():
+            prm.add_(0.3 * torch.randn_like(prm))          # non-trivial biases too
+    torch.save({"actor_model_state_dict": actor.state_dict(), "critic_model_state_dict": critic.state_dict(),
+                "actor_optimizer_state_dict": {}, "critic_optimizer_state_dict": {}, "iter": 123, "infos": None},
+               HERE / "ppo_actor.pt")
+    obs = torch.randn(9, 60) * 2.0
+    with torch.no_grad():
+        out = actor.act_inference(obs)
+    np.savez(HERE / "ppo_actor.npz", obs=obs.numpy(), actions=out.numpy(), keys=np.array(list(actor.state_dict().keys())))
+    print("ppo_actor.pt", list(actor.state_dict().keys()))
+
+
 def main():
     R = import_reference()
+    gen_urdf_blob()
+    gen_ppo_actor()
     rng = np.random.default_rng(20251017)
     gen_torques(R, rng)
     gen_windowing(R, rng)

@@ -124,3 +124,30 @@ def test_strict_mask_differs_from_default():
     expect[9:16] = False; expect[19:24] = False; expect[29:] = False
     assert torch.equal(chunked, expect)
     assert dsmod.reference_eval_mask(me, None, False).sum().item() == 27
+
+
+def test_model_blob_from_the_reference_urdf(nominal_model):
+    """The typed-in Go2 table (go2_nominal) against the blob built from the reference's own go2.urdf by model_from_urdf
+    (tests/golden/urdf_blob.npz, make_golden.gen_urdf_blob): bit-identical.  With the reference checkout present (build
+    container) the URDF is parsed again here."""
+    g = np.load(GOLD / "urdf_blob.npz")
+    blob = gm.build_model_blob(nominal_model)
+    assert blob.shape == (gm.BLOB["SIZE"],) and blob.dtype == np.float32
+    np.testing.assert_array_equal(blob, g["blob"])
+    np.testing.assert_array_equal(nominal_model.body_masses_isaac_order(), g["body_masses"])
+    assert abs(float(g["total_mass"]) - 15.019) < 1e-3
+    urdf = Path("/root/reference/spigym/data/robots/go2/urdf/go2.urdf")
+    if urdf.exists():
+        np.testing.assert_array_equal(gm.build_model_blob(gm.model_from_urdf(urdf)), g["blob"])
+
+
+def test_policy_from_reference_checkpoint():
+    """PolicyMLP.from_checkpoint on a checkpoint written in the layout of PPO.save (agents/ppo/ppo.py:155-166) from the
+    reference's real PPOActor; outputs = its act_inference (agents/modules/ppo_modules.py:73-75) to fp32 rounding."""
+    from spi_active_b200.active import PolicyMLP
+    g = np.load(GOLD / "ppo_actor.npz")
+    pol = PolicyMLP.from_checkpoint(GOLD / "ppo_actor.pt", "cpu")
+    assert [tuple(w.shape) for w in pol.weights] == [(32, 60), (16, 32), (8, 16), (12, 8)]
+    assert [k for k in g["keys"]][0] == "std"                       # the action-noise parameter is skipped
+    out = pol(torch.from_numpy(g["obs"]))
+    np.testing.assert_allclose(out.numpy(), g["actions"], rtol=1e-5, atol=1e-6)

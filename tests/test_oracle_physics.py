@@ -1,6 +1,11 @@
 """Physics invariants of the CPU oracle (the rigid-body part that no reference vector can pin):
-the ABA forward dynamics against an independent dense formulation, conservation laws in free flight, static
-equilibrium on the ground, and the go2 model constants against the numbers the reference documents."""
+  * all 18 accelerations of the ABA forward dynamics against an INDEPENDENT dense formulation (projected Newton-Euler /
+    Kane: mass matrix and velocity-product terms from plain forward kinematics of the 13 bodies, Jacobians by unit
+    velocities, their time derivative by central differences; 18 x 18 numpy solve) — `test_forward_dynamics_matches_dense`;
+  * power balance dE/dt = tau . qd and angular-momentum rate = gravity torque about the origin (both see the joint torques /
+    the internal forces, unlike the linear-momentum rate);
+  * conservation laws in free flight, static equilibrium on the ground, and the go2 model constants against the numbers the
+    reference documents."""
 import numpy as np
 import pytest
 
@@ -127,6 +132,113 @@ def test_forward_dynamics_matches_momentum_rate(oracle_lib, blob, nominal_model)
         M = nominal_model.total_mass()
         np.testing.assert_allclose((P1 - P0) / eps, [0, 0, -9.81 * M], atol=2e-3)
         assert all(isfinite(v) for v in qdd)
+
+
+def _quat_R(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def _world_accel(s, acc):
+    """oracle base acceleration (spatial, base coordinates: [ang3, lin3]) -> classical world-frame (lin, ang) of the origin."""
+    R = _quat_R(s[3:7])
+    wb, vb = R.T @ s[10:13], R.T @ s[7:10]
+    return R @ (acc[3:6] + np.cross(wb, vb)), R @ acc[0:3]
+
+
+def _advance_config(s, eps):
+    """q(t + eps) along the current generalized velocity, velocities untouched (exact quaternion exponential)."""
+    s2 = s.copy()
+    s2[0:3] += eps * s[7:10]
+    s2[13:25] += eps * s[25:37]
+    w = s[10:13]
+    th = np.linalg.norm(w) * eps
+    ax = w / max(np.linalg.norm(w), 1e-300)
+    dq = np.array([*(ax * np.sin(0.5 * th)), np.cos(0.5 * th)])          # world-frame rotation: q2 = dq * q
+    x1, y1, z1, w1 = dq; x2, y2, z2, w2 = s[3:7]
+    s2[3:7] = [w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2,
+               w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2, w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2]
+    return s2
+
+
+def _body_twists(model, s, nu=None):
+    """[(v_com, w)] of the 13 bodies for generalized velocity nu = (v_base_world, w_base_world, qd) at configuration s."""
+    t = s.copy()
+    if nu is not None:
+        t[7:10], t[10:13], t[25:37] = nu[0:3], nu[3:6], nu[6:18]
+    return [(b[2], b[4]) for b in _bodies_world(model, t)]
+
+
+def dense_forward_dynamics(model, s, tau, g=9.81):
+    """nu_dot[18] by projected Newton-Euler:  sum_b J_b^T [m (a_b - g); I_b alpha_b + w_b x I_b w_b] = S^T tau  with
+    a_b = Jv_b nu_dot + d/dt(Jv_b) nu etc.  Nothing here shares code or structure with the ABA."""
+    nu = np.concatenate([s[7:10], s[10:13], s[25:37]])
+    bodies = _bodies_world(model, s)
+    nb = len(bodies)
+    Jv = np.zeros((nb, 3, 18)); Jw = np.zeros((nb, 3, 18))
+    for i in range(18):
+        e = np.zeros(18); e[i] = 1.0
+        for b, (v, w) in enumerate(_body_twists(model, s, e)):
+            Jv[b, :, i], Jw[b, :, i] = v, w
+    eps = 1e-6
+    tp, tm = _body_twists(model, _advance_config(s, eps), nu), _body_twists(model, _advance_config(s, -eps), nu)
+    M = np.zeros((18, 18)); rhs = np.zeros(18)
+    rhs[6:18] = tau
+    for b, (m, c, v, R, w, Ic) in enumerate(bodies):
+        Iw = R @ Ic @ R.T
+        dv = (tp[b][0] - tm[b][0]) / (2 * eps); dw = (tp[b][1] - tm[b][1]) / (2 * eps)      # d/dt(J) nu
+        M += m * Jv[b].T @ Jv[b] + Jw[b].T @ Iw @ Jw[b]
+        rhs -= Jv[b].T @ (m * (dv + np.array([0.0, 0.0, g]))) + Jw[b].T @ (Iw @ dw + np.cross(w, Iw @ w))
+    return np.linalg.solve(M, rhs), M
+
+
+def test_forward_dynamics_matches_dense(oracle_lib, blob, nominal_model):
+    """All 18 accelerations (base linear / angular in the world frame, 12 joints) of the oracle's ABA against the dense
+    formulation above, on random states with random joint torques; also with a perturbed base-link candidate."""
+    rng = np.random.default_rng(23)
+    for trial in range(6):
+        s = _rand_state(rng, nominal_model, height=5.0)
+        tau = rng.uniform(-15, 15, 12)
+        acc, qdd, _ = oracle_lib.forward_dynamics(blob, s, tau, with_contact=False, with_gravity=True)
+        lin, ang = _world_accel(s, acc)
+        nud, M = dense_forward_dynamics(nominal_model, s, tau)
+        assert np.linalg.eigvalsh(M).min() > 0
+        np.testing.assert_allclose(np.concatenate([lin, ang, qdd]), nud, rtol=2e-6, atol=2e-5)
+    # a candidate with another base mass / com / inertia (INERTIA_KEEP so that the test can state the inertia directly)
+    import copy
+    m2 = copy.deepcopy(nominal_model)
+    m2.base = gm.Inertial(9.0, [0.05, -0.02, 0.03], [0.03, 0.12, 0.09, 0.0, 0.0, 0.0])
+    names = ["mass", "comx", "comy", "comz", "inertiax", "inertiay", "inertiaz", "inertiaxy", "inertiaxz", "inertiayz"]
+    p = [9.0, 0.05, -0.02, 0.03, 0.03, 0.12, 0.09, 0.0, 0.0, 0.0]
+    s = _rand_state(rng, nominal_model, height=5.0); tau = rng.uniform(-15, 15, 12)
+    acc, qdd, _ = oracle_lib.forward_dynamics(blob, s, tau, p, [gm.PARAM_IDS[n] for n in names], gm.FLAG_INERTIA_KEEP, False, True)
+    lin, ang = _world_accel(s, acc)
+    nud, _ = dense_forward_dynamics(m2, s, tau)
+    np.testing.assert_allclose(np.concatenate([lin, ang, qdd]), nud, rtol=2e-6, atol=2e-5)
+
+
+def test_power_balance_and_angular_momentum_rate(oracle_lib, blob, nominal_model):
+    """dE/dt = tau . qd (no contact: the joint torques are the only non-conservative forces) and dL/dt about the world origin =
+    sum r_com x m g.  Both depend on the joint accelerations, unlike dP/dt."""
+    rng = np.random.default_rng(29)
+    for _ in range(5):
+        s = _rand_state(rng, nominal_model, height=5.0)
+        tau = rng.uniform(-10, 10, 12)
+        acc, qdd, _ = oracle_lib.forward_dynamics(blob, s, tau, with_contact=False, with_gravity=True)
+        lin, ang = _world_accel(s, acc)
+
+        def at(eps):
+            t = _advance_config(s, eps)
+            t[7:10] += eps * lin; t[10:13] += eps * ang; t[25:37] += eps * qdd
+            return _momentum(nominal_model, t)
+        eps = 1e-5
+        (P1, L1, E1), (P0, L0, E0) = at(eps), at(-eps)
+        np.testing.assert_allclose((E1 - E0) / (2 * eps), tau @ s[25:37], rtol=1e-5, atol=1e-4)
+        torque = sum(np.cross(c, [0.0, 0.0, -9.81 * m]) for m, c, *_ in _bodies_world(nominal_model, s))
+        np.testing.assert_allclose((L1 - L0) / (2 * eps), torque, rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose((P1 - P0) / (2 * eps), [0, 0, -9.81 * nominal_model.total_mass()], atol=1e-4)
 
 
 def test_static_stand_supports_weight(oracle_lib, blob, nominal_model):
