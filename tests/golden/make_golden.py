@@ -37,6 +37,10 @@ reference's real, unmodified code object, called with plain torch tensors:
                      reference's real PPOActor (agents/modules/ppo_modules.py, modules.py:47-63; a small 60-32-16-8-12 ELU
                      instance of config/algo/ppo.yaml:31-39) + observations and its act_inference outputs
 
+  b1_env.npz         the reference's real mass_sweep / apply_base_mass / evaluate_batch driving its real
+                     LeggedRobotBase(BaseTask) env built by its real instantiate_env on the product's B200Sim plugin (oracle
+                     backend; tests/ref_harness.py, tests/test_b1_reference_env.py): recordings + costs for two chunkings
+
 What this cannot pin is the rigid-body physics itself: PhysX is not available.
 """
 from __future__ import annotations
@@ -403,9 +407,26 @@ def gen_ppo_actor():
     print("ppo_actor.pt", list(actor.state_dict().keys()))
 
 
+def gen_b1_env():
+    import test_b1_reference_env as tb
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        total, ds_np, ref_masses, res = tb.run_reference_sweep(d)
+    for i, r in enumerate(tb._recordings()):
+        for k in ("joint_positions", "joint_velocities", "actions", "base_positions", "base_orientations",
+                  "base_linear_velocities", "base_angular_velocities", "pd_gain_kp", "pd_gain_kd"):
+            out[f"rec{i}_{k}"] = np.asarray(r[k])
+    for B, (batch, costs) in res.items():
+        out[f"B{B}_costs"], out[f"B{B}_batch"] = costs, np.int64(batch)
+    out["scales"], out["ref_masses"], out["H"] = np.array([0.6, 1.0, 1.7]), ref_masses, np.int64(5)
+    np.savez(HERE / "b1_env.npz", **out)
+    print("b1_env.npz", {k: v.tolist() for k, v in out.items() if k.endswith("_costs")})
+
+
 def main():
     R = import_reference()
     gen_urdf_blob()
+    gen_b1_env()
     gen_ppo_actor()
     rng = np.random.default_rng(20251017)
     gen_torques(R, rng)

@@ -69,3 +69,43 @@ def test_mass_sweep_matches_reference_pipeline(engine, tmp_path, H, B):
     s_ref = landscape.summarize_landscape(g[f"H{H}_B{B}_costs"], g["scales"], 6.921, 15.019)
     s_gpu = landscape.summarize_landscape(res, g["scales"], 6.921, 15.019)
     assert s_ref.best_idx == s_gpu.best_idx
+
+
+@pytest.mark.parametrize("B", [16, 4096])
+def test_real_reference_env_golden(engine, tmp_path, nominal_model, B):
+    """tests/golden/b1_env.npz: costs produced by the reference's REAL `LeggedRobotBase` env (built by its real
+    `instantiate_env` on the B200Sim plugin, oracle backend) under its real `mass_sweep` / `apply_base_mass` /
+    `evaluate_batch` (tests/test_b1_reference_env.py runs that live in the build container).  Here, on the GPU: (a) the fused
+    operator `spi_b200_eval_candidates`, (b) the stepwise CUDA plugin path (B200Sim on `spi_b200_sim_step`, driven chunk by
+    chunk like evaluate_batch does: row-0 gains, chunk mask) — both within 2e-5 of the golden."""
+    from spi_active_b200.simulator import B200Sim
+    from test_simulator_plugin import _config, _replay
+    g = np.load(GOLD / "b1_env.npz")
+    H = int(g["H"])
+    paths = []
+    for i in range(3):
+        rec = {k[len(f"rec{i}_"):]: g[k] for k in g.files if k.startswith(f"rec{i}_")}
+        p = tmp_path / f"rec{i}.npz"
+        np.savez(p, **rec)
+        paths.append(p)
+    total, ds = dsmod.load_dataset(paths, H)
+    batch = min(B, total, landscape.MAX_SAFE_ENV_BATCH)
+    assert batch == int(g[f"B{B}_batch"])
+    segs = dsmod.pack_segments(dsmod.to_device(ds, engine.device), env_batch=batch, strict_reference=True)
+    res = landscape.mass_sweep(engine, segs, g["ref_masses"], g["scales"])
+    np.testing.assert_allclose(res, g[f"B{B}_costs"], rtol=0, atol=2e-5)
+    # (b) stepwise through the plugin on the CUDA backend, one candidate
+    sim = B200Sim(config=_config(batch), device=str(engine.device))
+    sim.set_headless(True); sim.setup(); sim.setup_terrain("plane"); sim.load_assets()
+    sim.create_envs(batch, torch.zeros(batch, 3), torch.tensor([0, 0, 0.34, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0], dtype=torch.float32))
+    sim.get_dof_limits_properties(); sim.prepare_sim()
+    mass = float(g["scales"][2] * g["ref_masses"][0])
+    sums, me = np.zeros(3), ds["motion_ends"]
+    for start in range(0, total, batch):
+        end = min(start + batch, total)
+        n = end - start
+        chunk = {k: np.concatenate([v[start:end], np.repeat(v[start:start + 1], batch - n, axis=0)]) for k, v in ds.items()}
+        per = _replay(sim, chunk, H, nominal_model, base_mass=mass)[:n]
+        mask = ~(np.cumsum(me[start:end]) > 0)                                   # scripts/eval.py:279-280
+        sums += (per * mask[:, None]).sum(axis=0)
+    np.testing.assert_allclose(sums / float((~me).sum()), g[f"B{B}_costs"][2], rtol=0, atol=2e-5)
