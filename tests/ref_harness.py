@@ -48,11 +48,13 @@ def import_reference():
     for p in (str(ROOT), str(ROOT / "tests"), str(REF), str(REF / "isaac_utils")):
         if p not in sys.path:
             sys.path.insert(0, p)
+    stubbed_here = []
     for name in STUBBED:
         try:
             importlib.import_module(name)
         except Exception:
             sys.modules[name] = mock.MagicMock(name=name)
+            stubbed_here.append(name)
     warnings.filterwarnings("ignore", category=SyntaxWarning)
     import scripts.eval as ev
     import scripts.mass_landscape as ml
@@ -70,6 +72,10 @@ def import_reference():
         ev.OmegaConf.create = mini_hydra._wrap
     if isinstance(bt.get_class, mock.MagicMock):
         bt.get_class = get_class
+    # the reference modules keep their own references to the stubs; take them out of sys.modules again so that product code
+    # probing for the real package (`import optuna` in landscape.optimize_mass) still sees it as absent
+    for name in stubbed_here:
+        sys.modules.pop(name, None)
     _R = SimpleNamespace(ev=ev, ml=ml, mo=mo, bt=bt, LeggedRobotBase=LeggedRobotBase, go2_omni=go2_omni_interface,
                          ActiveSysId=ActiveSysId_OpenLoop, tu=tu)
     return _R
