@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SPI_B200_VERSION 103 /* major*100 + minor */
+#define SPI_B200_VERSION 104 /* major*100 + minor */
 
 /* ------------------------------------------------------------------------------------------
  * Model blob layout (fp32[SPI_BLOB_SIZE]).  Built on the host from the URDF
@@ -235,14 +235,15 @@ int spi_b200_fim_reward(spi_b200_model* model, const float* states, int M, int P
  *   hist_index may be NULL — and the actor runs through spi_b200_policy_forward_ring with the matching head position;
  *   hist_index [840] device ints (short_history gather); fim_hist [K,M,P1,25] + fim_live [K,M] or NULL;
  *   dead_steps [N] or NULL (+= done); schedule [steps,4] device ints (command row, sync flag, FIM slot, ring head),
- *   counter [1] / ctrl [4] device ints: ctrl <- schedule[counter++] on the device before the step;
+ *   counter [1] / ctrl [4] device ints: ctrl <- schedule[counter++] on the device before the step; schedule has
+ *   `schedule_rows` rows of 4 ints — a step past the last row re-reads the last row instead of running off the buffer;
  *   q_default [12] HOST.  1 <= P1 <= 17.                                                                          */
 int spi_b200_active_post_step(spi_b200_model* model, float* state, const float* raw_actions, unsigned char* done,
                               const float* main_commands, int T, float* commands, float* actions, float* gait,
                               float* clock, float* history, float* obs, void* obs_hi, void* obs_lo, int obs_stride,
                               int ring_slots, const int* hist_index, float* fim_hist,
-                              unsigned char* fim_live, float* dead_steps, const int* schedule, int* counter, int* ctrl,
-                              int M, int P1, float dt, float action_clip, float clip_obs, float grav_x, float grav_y,
+                              unsigned char* fim_live, float* dead_steps, const int* schedule, int schedule_rows,
+                              int* counter, int* ctrl, int M, int P1, float dt, float action_clip, float clip_obs, float grav_x, float grav_y,
                               const float* q_default, void* cuda_stream);
 
 /* The locomotion policy (actor MLP: Linear-ELU x3 + Linear; spigym/agents/modules/modules.py:47-63,

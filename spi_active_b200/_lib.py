@@ -82,7 +82,7 @@ SIGNATURES = {
     "spi_b200_compute_torques": (C.c_int, [_V, _V, _V, _V, _V, _V, C.c_int, C.c_int, C.c_uint, _V, _V]),
     "spi_b200_fim_reward": (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_float, C.c_int, _V, _V, _V]),
     "spi_b200_active_post_step": (C.c_int, [_V, _V, _V, _V, _V, C.c_int, _V, _V, _V, _V, _V, _V, _V, _V, C.c_int, C.c_int, _V, _V,
-                                            _V, _V, _V, _V, _V, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                            _V, _V, _V, C.c_int, _V, _V, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                             C.c_float, C.c_float, _F, _V]),
     "spi_b200_policy_create": (C.c_int, [_I, C.POINTER(_F), C.POINTER(_F), C.POINTER(_V)]),
     "spi_b200_policy_destroy": (C.c_int, [_V]),

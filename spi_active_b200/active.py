@@ -26,8 +26,9 @@ Mirrors (same names, argument meaning, results):
   * :165-242                                             optimize (ask M trials -> evaluate -> tell -reward)
 
 The layer is device-agnostic torch around two engine calls (`env_step`, `fim_reward`), so the host logic runs on a CPU
-box against the oracle in tests; the product path is CUDA: physics = spi_b200_env_step, policy = cuBLAS GEMMs, FIM =
-spi_b200_fim_reward, one CUDA graph per control step.
+box against the oracle in tests; the product path is CUDA: physics = spi_b200_env_step, policy = the tcgen05 fp16-pair actor
+(spi_b200_policy_forward_ring; torch fp32 GEMMs only for actor shapes it does not support), bookkeeping =
+spi_b200_active_post_step, FIM = spi_b200_fim_contract, one CUDA graph per control step.
 
 Reference quirks: D10 absolute delta (default) — `relative_delta=True` for the documented
 "10 %"; D11 the reference's k-step sync never reaches the simulator — here it does (the intent), `ksync_steps=0`
@@ -292,9 +293,11 @@ class ActiveExploration:
             if c.policy_impl != "cublas" and hasattr(backend, "tensor_core_policy"):
                 try:
                     self.tc_policy = backend.tensor_core_policy(policy.weights, policy.biases)
-                except Exception:
+                except Exception as exc:
                     if c.policy_impl == "tensor":
                         raise
+                    import warnings
+                    warnings.warn(f"tensor-core actor unavailable for this policy ({exc}); using torch fp32 GEMMs", RuntimeWarning)
             elif c.policy_impl == "tensor":
                 raise ValueError("policy_impl='tensor' needs a backend with tensor_core_policy")
             self.ring = False
@@ -538,12 +541,14 @@ class ActiveExploration:
             self._hist_count = 0                      # the reset step's record is dropped, like its reward (:545-548)
         self._graph_ok = self.device.type == "cuda" if use_cuda_graph is None else use_cuda_graph
         self._steps_done = 1
+        self._steps_scheduled = total_steps
         if self._graph_ok and self._graph is None:
             self._capture()
         return max(0, total_steps - 2)                # the reference's loop is range(1, total_steps - 1)
 
     @torch.no_grad()
     def advance_rollout(self):
+        assert self._steps_done < self._steps_scheduled, "advance_rollout() called more often than begin_rollout() scheduled"
         if self.step_impl == "fused":
             self.step_idx += 1
         else:

@@ -86,10 +86,13 @@ inline size_t smem_bytes(int P1, bool ring = false) {
 // The per-step host inputs (command row, k-sync flag, FIM ring slot) come from a schedule uploaded once per rollout:
 // ctrl <- schedule[counter], counter += 1.  One thread; runs right before the post-step kernel of the same step, so a
 // captured step needs no host work between replays.
-__global__ void tick_kernel(const int* schedule, int* counter, int* ctrl) {
-  const int c = counter[0];
+// A step past the last scheduled row (an extra advance_rollout() / graph replay) re-reads the last row: stale inputs, but
+// never an index outside the command / FIM / observation rings.
+__global__ void tick_kernel(const int* schedule, int n_rows, int* counter, int* ctrl) {
+  const int c0 = counter[0];
+  const int c = c0 < n_rows ? c0 : n_rows - 1;
   ctrl[0] = schedule[4 * c]; ctrl[1] = schedule[4 * c + 1]; ctrl[2] = schedule[4 * c + 2]; ctrl[3] = schedule[4 * c + 3];
-  counter[0] = c + 1;
+  counter[0] = c0 < n_rows ? c0 + 1 : c0;
 }
 
 __global__ void __launch_bounds__(32 * kMaxGroup) active_post_step_kernel(const Args A) {
@@ -146,7 +149,8 @@ __global__ void __launch_bounds__(32 * kMaxGroup) active_post_step_kernel(const 
     float v;
     if (i < 12) {
       const float a = A.raw_actions[(size_t)env * 12 + i];
-      v = was_done ? 0.f : fminf(fmaxf(a, -A.action_clip), A.action_clip);
+      // a non-finite raw action (the reference's fp32 actor cannot produce one from finite, clipped observations) acts as 0
+      v = (was_done || !(fabsf(a) <= 3.0e38f)) ? 0.f : fminf(fmaxf(a, -A.action_clip), A.action_clip);
       A.actions[(size_t)env * 12 + i] = v;
     } else if (i < 15) v = ang[i - 12] * 0.25f;
     else if (i < 19) v = A.clock[(size_t)env * 4 + (i - 15)];

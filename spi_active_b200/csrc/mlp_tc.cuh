@@ -418,7 +418,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
           __half2 ph[4], pl[4];
 #pragma unroll
           for (int j = 0; j < 8; j += 2) {
-            const float h0 = elu(fmaf(a[j], kInv, bb[j])) * kActScale, h1 = elu(fmaf(a[j + 1], kInv, bb[j + 1])) * kActScale;
+            // clamp into the finite fp16 range before the split (an activation >= 65504 / 16 would make hi = inf, lo = NaN;
+            // ELU is bounded below by -1): the documented operating range is |activation| < 4000
+            const float h0 = fminf(elu(fmaf(a[j], kInv, bb[j])) * kActScale, 65000.0f);
+            const float h1 = fminf(elu(fmaf(a[j + 1], kInv, bb[j + 1])) * kActScale, 65000.0f);
             const __half2 hh = __floats2half2_rn(h0, h1);
             const float2 hf2 = __half22float2(hh);
             ph[j >> 1] = hh;

@@ -148,11 +148,13 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, const W
   LegState s;
   float kp[3], kd[3];
   {
+    // plain loads: in the paired RECORD launch of spi_b200_env_step the output rows alias seg_init, and ld.global.nc must not
+    // be used on memory the same kernel writes
     const float* row = A.seg_init + (size_t)seg * SPI_STATE_DIM;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-      s.q[j] = __ldg(row + 13 + 3 * LEG + j);
-      s.qd[j] = __ldg(row + 25 + 3 * LEG + j);
+      s.q[j] = *(row + 13 + 3 * LEG + j);
+      s.qd[j] = *(row + 25 + 3 * LEG + j);
       kp[j] = A.seg_gains ? __ldg(A.seg_gains + (size_t)seg * 24 + 3 * LEG + j) : A.M.kp[3 * LEG + j];
       kd[j] = A.seg_gains ? __ldg(A.seg_gains + (size_t)seg * 24 + 12 + 3 * LEG + j) : A.M.kd[3 * LEG + j];
     }
@@ -240,9 +242,9 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, const 
   {
     const float* row = A.seg_init + (size_t)seg * SPI_STATE_DIM;
 #pragma unroll
-    for (int i = 0; i < 3; i++) { s.p[i] = __ldg(row + i); s.v[i] = __ldg(row + 7 + i); s.w[i] = __ldg(row + 10 + i); }
+    for (int i = 0; i < 3; i++) { s.p[i] = *(row + i); s.v[i] = *(row + 7 + i); s.w[i] = *(row + 10 + i); }
 #pragma unroll
-    for (int i = 0; i < 4; i++) s.quat[i] = __ldg(row + 3 + i);
+    for (int i = 0; i < 4; i++) s.quat[i] = *(row + 3 + i);
   }
   float bc[kBaseOut];
 #pragma unroll

@@ -58,13 +58,14 @@ SPI_DEV void load_leg_const(const DeviceModel& M, int leg, LegConst& L) {
   }
 }
 
+// plain loads: sim_step_kernel and the in-place env step write the rows they read (no ld.global.nc on such memory)
 SPI_DEV void load_lane_state(const float* row, int leg, LaneState& s) {
 #pragma unroll
-  for (int i = 0; i < 3; i++) { s.p[i] = __ldg(row + i); s.v[i] = __ldg(row + 7 + i); s.w[i] = __ldg(row + 10 + i); }
+  for (int i = 0; i < 3; i++) { s.p[i] = *(row + i); s.v[i] = *(row + 7 + i); s.w[i] = *(row + 10 + i); }
 #pragma unroll
-  for (int i = 0; i < 4; i++) s.quat[i] = __ldg(row + 3 + i);
+  for (int i = 0; i < 4; i++) s.quat[i] = *(row + 3 + i);
 #pragma unroll
-  for (int j = 0; j < 3; j++) { s.q[j] = __ldg(row + 13 + 3 * leg + j); s.qd[j] = __ldg(row + 25 + 3 * leg + j); }
+  for (int j = 0; j < 3; j++) { s.q[j] = *(row + 13 + 3 * leg + j); s.qd[j] = *(row + 25 + 3 * leg + j); }
 }
 
 SPI_DEV void store_lane_state(float* row, int leg, const LaneState& s) {
@@ -519,6 +520,18 @@ int fail(int code, const std::string& msg) {
       return fail(-100, std::string(#expr) + ": " + cudaGetErrorString(_e));                      \
   } while (0)
 
+// cudaFuncSetAttribute is PER DEVICE: a process that drives several GPUs (one engine per device) must opt in on each of them,
+// so the "already done" state is a bitmap over the current device's index, not a process-wide flag.
+static bool attr_needed_on_current_device(std::atomic<unsigned long long>* done_mask, int* dev_out) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { *dev_out = -1; return true; }
+  *dev_out = dev;
+  return ((done_mask->load() >> dev) & 1ull) == 0;
+}
+static void attr_mark_done(std::atomic<unsigned long long>* done_mask, int dev) {
+  if (dev >= 0) done_mask->fetch_or(1ull << dev);
+}
+
 int check_launch(const char* what) {
   g_launches.fetch_add(1);
   cudaError_t e = cudaGetLastError();
@@ -960,7 +973,8 @@ int spi_b200_active_post_step(spi_b200_model* m, float* state, const float* raw_
                               const float* main_commands, int T, float* commands, float* actions, float* gait,
                               float* clock, float* history, float* obs, void* obs_hi, void* obs_lo, int obs_stride,
                               int ring_slots, const int* hist_index, float* fim_hist,
-                              unsigned char* fim_live, float* dead_steps, const int* schedule, int* counter, int* ctrl,
+                              unsigned char* fim_live, float* dead_steps, const int* schedule, int schedule_rows,
+                              int* counter, int* ctrl,
                               int Mn, int P1, float dt, float action_clip, float clip_obs, float grav_x, float grav_y,
                               const float* q_default, void* cuda_stream) {
   if (!m) return fail(-1, "model handle is NULL");
@@ -975,11 +989,12 @@ int spi_b200_active_post_step(spi_b200_model* m, float* state, const float* raw_
   if (ring_slots == 0 && (!history || !obs || !hist_index)) return fail(-3, "NULL buffer");
   if (fim_hist && !fim_live) return fail(-3, "fim_live is NULL");
   if (obs_hi && (!obs_lo || obs_stride < activestep::kObs)) return fail(-3, "obs_lo is NULL or obs_stride < 900");
-  static std::atomic<int> attr_done{0};
-  if (!attr_done.load()) {
+  static std::atomic<unsigned long long> attr_done{0};
+  int attr_dev = -1;
+  if (attr_needed_on_current_device(&attr_done, &attr_dev)) {
     CUDA_OK(cudaFuncSetAttribute(activestep::active_post_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)activestep::smem_bytes(activestep::kMaxGroup)));
-    attr_done.store(1);
+    attr_mark_done(&attr_done, attr_dev);
   }
   activestep::Args A;
   A.state = state; A.raw_actions = raw_actions; A.done = done; A.main_commands = main_commands; A.commands = commands;
@@ -991,7 +1006,7 @@ int spi_b200_active_post_step(spi_b200_model* m, float* state, const float* raw_
   A.grav_x = grav_x; A.grav_y = grav_y;
   for (int j = 0; j < 12; j++) A.q_default[j] = q_default[j];
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  activestep::tick_kernel<<<1, 1, 0, st>>>(schedule, counter, ctrl);
+  activestep::tick_kernel<<<1, 1, 0, st>>>(schedule, schedule_rows, counter, ctrl);
   if (int rc = check_launch("tick_kernel")) return rc;
   activestep::active_post_step_kernel<<<Mn, 32 * P1, activestep::smem_bytes(P1, ring_slots > 0), st>>>(A);
   return check_launch("active_post_step_kernel");
@@ -1312,11 +1327,12 @@ int spi_b200_fim_contract(spi_b200_model* m, const float* hist, const unsigned c
   if (P > fimtc::kSlots) return fail(-3, "P must be <= 16");
   if (!hist || (!out_JtJ && !out_trace)) return fail(-3, "NULL buffer");
   if (!(delta != 0.f)) return fail(-3, "delta must be non-zero");
-  static std::atomic<int> attr_done{0};
-  if (!attr_done.load()) {
+  static std::atomic<unsigned long long> attr_done{0};
+  int attr_dev = -1;
+  if (attr_needed_on_current_device(&attr_done, &attr_dev)) {
     CUDA_OK(cudaFuncSetAttribute(fimtc::fim_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  fimtc::kSmemBytes));
-    attr_done.store(1);
+    attr_mark_done(&attr_done, attr_dev);
   }
   fimtc::FimArgs A;
   A.hist = hist; A.live = live; A.T = T; A.M = Mn; A.P = P; A.inv_delta = 1.0f / delta; A.accumulate = accumulate;

@@ -154,6 +154,9 @@ class RolloutEngine:
         if not torch.cuda.is_available():
             raise _lib.SpiB200Error("RolloutEngine needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.index is None:
+            self.device = torch.device(f"cuda:{torch.cuda.current_device()}")
+        self._status_buf = None
         self.model = model or gm.go2_nominal()
         self.blob = gm.build_model_blob(self.model)
         self._handle = C.c_void_p()
@@ -198,9 +201,28 @@ class RolloutEngine:
         ids = _ids(param_names)
         assert ids.size == P, "one name/id per parameter column"
         S, H = segs.num_segments, segs.horizon
+        # raw pointers cross the C-ABI below: a wrong device / dtype / stride must be an error here, not an illegal access there
+        for name, t, dt, shape in (("seg_init", segs.seg_init, torch.float32, (S, 37)),
+                                   ("seg_actions", segs.seg_actions, torch.float32, (S, H, 12)),
+                                   ("seg_target", segs.seg_target, torch.float32, (S, 19)),
+                                   ("seg_gains", segs.seg_gains, torch.float32, (S, 24)),
+                                   ("seg_mask", segs.seg_mask, torch.uint8, (S,)),
+                                   ("out", out, torch.float32, (Cn, 3))):
+            if t is None:
+                if name in ("seg_gains", "seg_mask", "out"):
+                    continue
+                raise ValueError(f"{name} is None")
+            if not (t.is_cuda and t.device == self.device and t.dtype == dt and t.is_contiguous() and tuple(t.shape) == shape):
+                raise ValueError(f"{name}: need a contiguous {dt} tensor of shape {shape} on {self.device}, got "
+                                 f"{t.dtype} {tuple(t.shape)} on {t.device} (contiguous={t.is_contiguous()})")
         cost = out if out is not None else torch.empty((Cn, 3), device=self.device, dtype=torch.float32)
         per = torch.empty((Cn, S, 3), device=self.device, dtype=torch.float32) if return_per_seg else None
-        status = torch.empty((Cn,), device=self.device, dtype=torch.int32)
+        if return_status:
+            status = torch.empty((Cn,), device=self.device, dtype=torch.int32)     # handed to the caller: its own buffer
+        else:                                                                      # scratch: grown once, then reused
+            if self._status_buf is None or self._status_buf.shape[0] < Cn:
+                self._status_buf = torch.empty((Cn,), device=self.device, dtype=torch.int32)
+            status = self._status_buf[:Cn]
         denom = segs.cost_denominator if cost_denominator is None else cost_denominator
         with torch.cuda.device(self.device):
             rc = self.lib.spi_b200_eval_candidates(
@@ -377,7 +399,7 @@ class RolloutEngine:
                 self._handle, _ptr(state), _ptr(raw_actions), _ptr(done), _ptr(main_commands), T, _ptr(commands),
                 _ptr(actions), _ptr(gait), _ptr(clock), _ptr(history), _ptr(obs), _ptr(obs_hi), _ptr(obs_lo),
                 0 if obs_hi is None else int(obs_hi.shape[1]), int(ring_slots), _ptr(hist_index), _ptr(fim_hist),
-                _ptr(fim_live), _ptr(dead_steps), _ptr(schedule), _ptr(counter), _ptr(ctrl), Mn, P1, float(dt),
+                _ptr(fim_live), _ptr(dead_steps), _ptr(schedule), int(schedule.shape[0]), _ptr(counter), _ptr(ctrl), Mn, P1, float(dt),
                 float(action_clip), float(clip_obs), float(grav_xy[0]), float(grav_xy[1]),
                 qd.ctypes.data_as(C.POINTER(C.c_float)), self._stream())
         _lib.check(rc, "spi_b200_active_post_step")

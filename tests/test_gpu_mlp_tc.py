@@ -1,4 +1,4 @@
-"""spi_b200_policy_forward (tcgen05 3xTF32 actor MLP) against an fp64 evaluation of the reference's actor
+"""spi_b200_policy_forward (tcgen05 fp16-pair actor MLP: hi.hi + hi.lo + lo.hi, fp32-grade) against an fp64 evaluation of the reference's actor
 (agents/modules/modules.py:47-63: Linear-ELU x3 + Linear; 900-512-256-128-12 per config/algo/ppo.yaml:32-40) and against
 torch's fp32 evaluation on the GPU.  Tolerance: fp32 grade — the kernel must be as close to fp64 as torch's own fp32
 GEMMs are (a few 1e-6 of the output scale); plain TF32 would sit at ~1e-3."""
