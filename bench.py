@@ -216,8 +216,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus, S) | {"reference_note": "Isaac Gym is closed source and not installable; "
-                                                  "this arm is the CPU restatement (oracle/, fp32) on all host threads"},
+        "config": workload_config(args.gpus, S),
+        "reference_note": "Isaac Gym is closed source and not installable; this arm is the CPU restatement (oracle/, fp32) "
+                          "on all host threads",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -335,9 +336,22 @@ def run_b200(args):
     h2d = host_params.nbytes + init.nbytes + act.nbytes + tgt.nbytes + gains.nbytes + mask.nbytes
     d2h = cost_h.nbytes + status_h.nbytes
 
+    # ---- the other BASELINE configs, bounded (all ranks take part: config 4 strong scaling and config 5 are sharded) ----
+    def max_over_ranks(x):
+        tt = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt[0])
+    extra = None
+    if not args.no_extras:
+        try:
+            extra = run_extras(eng, segs, cfg, S, rank, world, barrier, max_over_ranks)
+        except Exception as exc:            # the headline line must survive a failure of a secondary record
+            extra = {"error": f"{type(exc).__name__}: {exc}"}
+
     if rank != 0:
         if world > 1:
-            dist.barrier()
+            _rank0_done_wait(world)
             dist.destroy_process_group()
         return 0
 
@@ -387,11 +401,167 @@ def run_b200(args):
         "gpu_launches": int(launches), "clocks": clocks,
         "best": {"cost": float(best[-1]), "base_mass_kg": float(best[0])},
     }
+    if extra is not None:
+        line["extra"] = extra
     emit(line)
     if world > 1:
-        dist.barrier()
+        _rank0_done_signal()
         dist.destroy_process_group()
     return 0
+
+
+# Rank 0 times the CPU oracle (cpu_baseline) after the GPU work; the other ranks must not spin in an NCCL barrier meanwhile
+# (a spinning rank costs a host core each and depressed the 8-GPU cpu_baseline by 20 % in round 1): they sleep on the
+# c10d TCP store instead.
+def _rank0_done_signal():
+    import torch.distributed as dist
+    try:
+        dist.distributed_c10d._get_default_store().set("spi_bench_rank0_done", "1")
+    except Exception:
+        pass
+
+
+def _rank0_done_wait(world):
+    import datetime
+
+    import torch.distributed as dist
+    try:
+        dist.distributed_c10d._get_default_store().wait(["spi_bench_rank0_done"], datetime.timedelta(seconds=600))
+    except Exception:
+        pass
+
+
+# ------------------------------------------------------------------------------------------------
+# bounded secondary records of the default run (`extra`): the other BASELINE.json configs, timed the same way
+# ------------------------------------------------------------------------------------------------
+def run_extras(eng, segs, cfg, S, rank, world, barrier, max_over_ranks):
+    """-> dict for the JSON line's `extra` key.  Every record is measured with CUDA events / a synchronised wall clock after
+    its own warm-up, max over ranks, and is small enough that the default run still ends within a minute or two:
+      config4_strong  BASELINE config 4 as written: 16384 candidates IN TOTAL split over the N ranks (strong scaling),
+                      ms per CEM iteration (sample -> rollout -> cost -> all-gather -> select / refit)
+      config2         scripts/mass_landscape.py --config all --horizon 5: the 20-candidate base-mass sweep, ms per sweep (rank 0)
+      config3         scripts/mass_opt.py: the 50-trial TPE study + the final re-evaluation = 51 sequential single-candidate
+                      launches, seconds per study incl. the host-side sampler (rank 0)
+      active          BASELINE config 5: one evaluate_policy of 1024 command trajectories per GPU x 11 envs x 1249 control
+                      steps (3 pipelines), seconds per rollout and env steps/s, plus the kernel times of one un-graphed
+                      control step (actor / physics / post-step) and of the Fisher contraction
+    """
+    import torch
+
+    from spi_active_b200 import active as act, cem, landscape
+    out = {}
+    dev = eng.device
+
+    def timed(fn, n, warm=1):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / n
+
+    # ---- config 4, strong scaling -----------------------------------------------------------------------------------
+    C4 = 16384
+    opt = cem.CemOptimizer(eng, segs, cfg, C4, rank, world)
+    ms = timed(opt.iterate, 3)
+    out["config4_strong"] = {"candidates_total": C4, "candidates_per_gpu": C4 // world, "n_gpus": world,
+                             "ms_per_cem_iteration": ms, "candidate_env_steps_per_s": C4 * S * HORIZON / (ms * 1e-3),
+                             "scaling": "strong"}
+    del opt
+    if rank == 0:
+        # ---- config 2: the 20-point landscape ---------------------------------------------------------------------------
+        scales = np.linspace(landscape.MASS_SCALE_MIN, landscape.MASS_SCALE_MAX, landscape.MASS_SAMPLES)
+        ref_masses = eng.model.body_masses_isaac_order()
+        ms2 = timed(lambda: landscape.mass_sweep(eng, segs, ref_masses, scales), 5, warm=2) if world == 1 else None
+        if world > 1:       # the other ranks are parked at a barrier: no collective inside, plain local timing
+            for _ in range(2):
+                landscape.mass_sweep(eng, segs, ref_masses, scales)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for _ in range(5):
+                landscape.mass_sweep(eng, segs, ref_masses, scales)
+            torch.cuda.synchronize(); ms2 = (time.perf_counter() - t0) / 5 * 1e3
+        out["config2"] = {"candidates": int(landscape.MASS_SAMPLES), "segments": S, "ms_per_sweep": ms2,
+                          "candidate_env_steps_per_s": landscape.MASS_SAMPLES * S * HORIZON / (ms2 * 1e-3),
+                          "note": "includes the D2H of the [20,3] costs, as the CLI does"}
+        # ---- config 3: the TPE study ---------------------------------------------------------------------------------------
+        obj = lambda sc: landscape.evaluate_mass_scale(sc, eng, segs, ref_masses)
+        landscape.optimize_mass(obj, n_trials=5)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        bs, bv, trials = landscape.optimize_mass(obj)
+        landscape.evaluate_mass_scale(bs, eng, segs, ref_masses, return_details=True)      # mass_opt.py:226-228
+        torch.cuda.synchronize(); s3 = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for _ in range(51):
+            obj(1.0)
+        torch.cuda.synchronize(); s3_eval = time.perf_counter() - t0
+        out["config3"] = {"trials": len(trials) + 1, "s_per_study": s3, "s_in_the_51_evaluations": s3_eval,
+                          "best_base_mass_kg": bs * float(ref_masses[0]), "best_cost": bv,
+                          "note": "51 sequential C = 1 launches (55 CTAs each: latency-bound by design of the study); the "
+                                  "rest of the time is the host-side TPE sampler"}
+    barrier()
+    # ---- config 5: active exploration ------------------------------------------------------------------------------------------
+    M, T = 1024, 1250
+    acfg = act.ActiveConfig(exploration_params=list(act.ActiveExploration.PARAM_ORDER), seed=rank)
+    ex = act.PipelinedExploration(eng, act.PolicyMLP.random(dev, seed=0, gain=0.3), M, acfg, n_pipelines=3)
+    rng = np.random.default_rng(rank)
+    r = np.asarray(act.COMMAND_RANGES)
+    vals = rng.uniform(r[act.COMMAND_SAMPLING_IDXS, 0], r[act.COMMAND_SAMPLING_IDXS, 1], (M, 5, 3)).astype(np.float32)
+    cmds = torch.from_numpy(np.stack([act.expand_commands(act.commands_constant(v, 250)) for v in vals]))
+    res = {}
+
+    def rollout():
+        res["out"] = ex.evaluate_policy(cmds, total_steps=T)
+    rollout()
+    barrier(); t0 = time.perf_counter()
+    for _ in range(2):
+        rollout()
+    barrier()
+    s5 = max_over_ranks(time.perf_counter() - t0) / 2
+    rec = {"main_envs_per_gpu": M, "envs_per_gpu": ex.num_envs, "control_steps": int(res["out"]["steps"]), "n_gpus": world,
+           "s_per_rollout": s5, "env_steps_per_s": world * ex.num_envs * res["out"]["steps"] / s5,
+           "reward_mean": float(res["out"]["total_reward"][::ex.param_dim + 1].mean())}
+    # kernel times of one control step of the un-cut population, launched eagerly (no graph, one stream): CUDA events
+    one = act.ActiveExploration(eng, act.PolicyMLP.random(dev, seed=0, gain=0.3), M, acfg)
+    one.reset_all(cmds, total_steps=64)
+    if one.step_impl == "fused" and one.tc_policy is not None and getattr(one, "ring", False):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        acc = np.zeros(3)
+        n_rep = 20
+        for k in range(n_rep + 3):
+            one.step_idx += 1
+            ev[0].record()
+            raw = one.tc_policy.forward_ring(one.obs_hi, one.obs_lo, one.num_envs, one.ctrl[3:4], out=one.raw_actions)
+            ev[1].record()
+            one.backend.env_step(one.state, raw, params=one.params, param_names=one.param_names,
+                                 motor_model=acfg.motor_model, flags=1, zero_action_mask=one.done)
+            ev[2].record()
+            one.backend.active_post_step(one.state, raw, one.done, one.main_commands, one.commands, one.actions,
+                                         one.gait_indices, one.clock, None, None, None, one.hist, one.live_hist,
+                                         one.dead_steps, one.schedule, one.counter, one.ctrl, one.dt, acfg.action_clip,
+                                         act.CLIP_OBSERVATIONS, act.TERMINATION_GRAVITY, one.model.q_default,
+                                         obs_hi=one.obs_hi, obs_lo=one.obs_lo, ring_slots=act.RING_SLOTS)
+            ev[3].record()
+            torch.cuda.synchronize()
+            if k >= 3:
+                acc += [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        one.backend.fim_contract(one.hist, float(acfg.delta_param), live=one.live_hist)
+        e0.record()
+        one.backend.fim_contract(one.hist, float(acfg.delta_param), live=one.live_hist)
+        e1.record(); torch.cuda.synchronize()
+        flops = 2.0 * 3 * one.num_envs * sum(a * b for a, b in zip((928, 512, 256), (512, 256, 128)))
+        rec["step_kernels_ms"] = {"actor_mlp": acc[0] / n_rep, "physics_env_step": acc[1] / n_rep,
+                                  "post_step": acc[2] / n_rep,
+                                  "fim_contract_per_%d_steps" % one.hist.shape[0]: e0.elapsed_time(e1),
+                                  "actor_issued_f16_tflops": flops / (acc[0] / n_rep * 1e-3) / 1e12,
+                                  "note": "eager single-stream launches incl. launch gaps; inside the captured, 3-way pipelined "
+                                          "rollout the kernels overlap"}
+    out["active"] = rec
+    return out
 
 
 class _StdoutGuard:
@@ -484,6 +654,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the bounded `extra` records (other BASELINE configs)")
     ap.add_argument("--workload", default="sysid", choices=["sysid", "active"],
                     help="sysid (default) = the headline metric; active = the config-5 exploration rollout (secondary)")
     args = ap.parse_args()

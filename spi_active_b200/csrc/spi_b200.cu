@@ -401,27 +401,79 @@ __global__ void cem_sample_kernel(const float* mean, const float* stdv, const fl
   if (hi) v = fminf(v, hi[p]);
   out[idx] = v;
 }
-// rank[i] = #{ j : cost_j < cost_i  or (cost_j == cost_i and j < i) }; NaN/inf sort last
-__global__ void cem_rank_kernel(const float* cost, int C, int* rank) {
-  __shared__ float tile[256];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  float ci = (i < C) ? cost[i] : INFINITY;
-  if (!(ci == ci)) ci = INFINITY;
-  int r = 0;
-  for (int base = 0; base < C; base += 256) {
-    const int j = base + threadIdx.x;
-    float cj = (j < C) ? cost[j] : INFINITY;
-    if (!(cj == cj)) cj = INFINITY;
+// Elite selection in O(C): the n_elite smallest candidates in the stable order (cost, index), NaN / inf last — the same set
+// the O(C^2) rank kernel of round 1 produced (1.07e9 compares at 32768 candidates, replicated on every rank: it was the
+// first thing to show in multi-GPU scaling).  One CTA: 4 passes of an 8-bit radix select over order-preserving uint keys
+// find the n_elite-th smallest key K*; every key < K* is elite, ties at K* are admitted in index order until n_elite is
+// reached (block-wide exclusive scan over contiguous index chunks).  Output in the old kernel's vocabulary so that the
+// refit kernel is unchanged: rank[i] = 0 for the best candidate, 1 for the other elites, n_elite for the rest.
+__device__ __forceinline__ unsigned cem_key(float c) {
+  if (!(fabsf(c) <= 3.4028235e38f)) c = INFINITY;    // NaN and +-inf sort last (cem.cem_refit_numpy: non-finite last)
+  const unsigned b = __float_as_uint(c);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+constexpr int kSelThreads = 1024;
+__global__ void __launch_bounds__(kSelThreads) cem_select_kernel(const float* cost, int C, int n_elite, int* rank) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned s_prefix, s_remaining, s_best_key;
+  __shared__ int s_best_idx;
+  __shared__ unsigned scan[kSelThreads];
+  const int t = threadIdx.x;
+  if (t == 0) { s_prefix = 0u; s_remaining = (unsigned)n_elite; s_best_key = 0xFFFFFFFFu; s_best_idx = 0x7FFFFFFF; }
+  __syncthreads();
+  // ---- radix select of the n_elite-th smallest key (1-based position s_remaining among the keys matching s_prefix) ----
+  for (int pass = 0; pass < 4; pass++) {
+    const int shift = 24 - 8 * pass;
+    const unsigned mask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    if (t < 256) hist[t] = 0u;
     __syncthreads();
-    tile[threadIdx.x] = cj;
-    __syncthreads();
-    const int n = min(256, C - base);
-    for (int t = 0; t < n; t++) {
-      const float v = tile[t];
-      r += (v < ci || (v == ci && (base + t) < i)) ? 1 : 0;
+    const unsigned prefix = s_prefix;
+    for (int i = t; i < C; i += kSelThreads) {
+      const unsigned k = cem_key(cost[i]);
+      if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 0xFFu], 1u);
     }
+    __syncthreads();
+    if (t == 0) {
+      unsigned rem = s_remaining, d = 0;
+      for (; d < 256; d++) { if (hist[d] >= rem) break; rem -= hist[d]; }
+      s_prefix = prefix | (d << shift);
+      s_remaining = rem;                               // position among the keys equal to the new prefix
+    }
+    __syncthreads();
   }
-  if (i < C) rank[i] = r;
+  const unsigned kstar = s_prefix;
+  const unsigned ties_admitted = s_remaining;          // how many keys == K* are elite (>= 1)
+  // ---- ties in index order: contiguous chunk per thread, exclusive scan of the per-chunk tie counts ----
+  const int chunk = (C + kSelThreads - 1) / kSelThreads;
+  const int i0 = min(t * chunk, C), i1 = min(i0 + chunk, C);
+  unsigned n_tie = 0;
+  unsigned best_key = 0xFFFFFFFFu; int best_idx = 0x7FFFFFFF;
+  for (int i = i0; i < i1; i++) {
+    const unsigned k = cem_key(cost[i]);
+    n_tie += (k == kstar) ? 1u : 0u;
+    if (k < best_key) { best_key = k; best_idx = i; }  // first index wins within the chunk
+  }
+  scan[t] = n_tie;
+  __syncthreads();
+  for (int o = 1; o < kSelThreads; o <<= 1) {          // Hillis-Steele inclusive scan
+    const unsigned v = (t >= o) ? scan[t - o] : 0u;
+    __syncthreads();
+    scan[t] += v;
+    __syncthreads();
+  }
+  unsigned tie_before = scan[t] - n_tie;
+  // ---- the best candidate: minimum (key, index) ----
+  atomicMin(&s_best_key, best_key);
+  __syncthreads();
+  if (best_key == s_best_key) atomicMin(&s_best_idx, best_idx);
+  __syncthreads();
+  const int best = s_best_idx;
+  for (int i = i0; i < i1; i++) {
+    const unsigned k = cem_key(cost[i]);
+    bool elite = k < kstar;
+    if (k == kstar) { elite = tie_before < ties_admitted; tie_before++; }
+    rank[i] = (i == best) ? 0 : (elite ? 1 : n_elite);
+  }
 }
 // one CTA per parameter: elite mean / std in a fixed summation order, smoothed update; CTA 0 also
 // writes the best candidate (rank 0)
@@ -431,7 +483,7 @@ __global__ void cem_refit_kernel(const float* params, const float* cost, const i
   __shared__ float sh_mean;
   const int p = blockIdx.x, t = threadIdx.x;
   float acc = 0.f;
-  for (int i = t; i < C; i += 256) acc += (rank[i] < n_elite) ? params[(size_t)i * P + p] : 0.f;
+  for (int i = t; i < C; i += 256) acc += (rank[i] < n_elite) ? params[(size_t)i * P + p] : 0.f;   // rank: 0 best, 1 elite, n_elite otherwise
   sh[t] = acc;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) { if (t < o) sh[t] += sh[t + o]; __syncthreads(); }
@@ -685,7 +737,10 @@ int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C
     const unsigned n2 = (unsigned)((n_cta + 1) / 2);
     if (minb == 1) ws::rollout_ws2_kernel<1><<<n2, 2 * ws::kWsThreads, 0, st>>>(A);
     else ws::rollout_ws2_kernel<2><<<n2, 2 * ws::kWsThreads, 0, st>>>(A);
-  } else if (minb == 2) ws::rollout_ws_kernel<false, 2><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
+  } else if (minb == 2 || (minb == 0 && n_cta <= 2LL * m->sm_count))
+    // small grids (a mass_opt trial is 55 CTAs, the 20-point landscape 1100 -> no: only grids that fit 2 CTAs per SM): the
+    // uncapped-register build has the shorter per-CTA latency, and latency is all a sub-wave launch has
+    ws::rollout_ws_kernel<false, 2><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
   else if (minb == 3) ws::rollout_ws_kernel<false, 3><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
   else ws::rollout_ws_kernel<false, 4><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
   if (int rc = check_launch("rollout_ws_kernel")) return rc;
@@ -1369,8 +1424,8 @@ int spi_b200_cem_refit(spi_b200_model* m, const float* params, const float* cost
   if (!params || !cost || !mean || !std) return fail(-3, "NULL buffer");
   if (int rc = ensure(&m->d_rank, &m->rank_cap, (size_t)C)) return rc;
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  cem_rank_kernel<<<(C + 255) / 256, 256, 0, st>>>(cost, C, m->d_rank);
-  if (int rc = check_launch("cem_rank_kernel")) return rc;
+  cem_select_kernel<<<1, kSelThreads, 0, st>>>(cost, C, n_elite, m->d_rank);
+  if (int rc = check_launch("cem_select_kernel")) return rc;
   cem_refit_kernel<<<P, 256, 0, st>>>(params, cost, m->d_rank, C, P, n_elite, alpha, std_floor, mean, std, out_best);
   return check_launch("cem_refit_kernel");
 }

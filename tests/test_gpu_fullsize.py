@@ -85,6 +85,36 @@ def test_full_size_sample_matches_oracle(engine, oracle_lib, blob, full):
     np.testing.assert_allclose(cost[pick], ref, rtol=5e-5, atol=2e-6)
 
 
+@pytest.mark.parametrize("case", ["ties_at_threshold", "mostly_inf", "all_equal", "n_elite_1", "negative_and_nan"])
+def test_elite_selection_edge_cases(engine, case):
+    """spi_b200_cem_refit's O(C) radix select against the host rule (stable order by (cost, index), NaN / inf last) where the
+    old O(C^2) rank kernel and a naive select differ: ties straddling the elite threshold, more diverged candidates than
+    non-elites, all-equal costs, a single elite, negative costs and NaN."""
+    rng = np.random.default_rng(11)
+    C, P = 5000, 4
+    params = rng.standard_normal((C, P)).astype(np.float32)
+    cost = rng.random(C).astype(np.float32)
+    n_elite = 250
+    if case == "ties_at_threshold":
+        cost = np.round(cost * 40).astype(np.float32) / 40            # ~125 candidates per distinct value
+    elif case == "mostly_inf":
+        cost[rng.choice(C, C - 100, replace=False)] = np.inf          # the threshold key is +inf itself
+    elif case == "all_equal":
+        cost[:] = 0.5
+    elif case == "n_elite_1":
+        n_elite = 1
+    elif case == "negative_and_nan":
+        cost = (cost - 0.5).astype(np.float32); cost[::7] = np.nan; cost[3] = -np.inf
+    f = lambda a: torch.tensor(np.asarray(a, np.float32), device=engine.device)
+    mean, std = f(np.zeros(P)), f(np.ones(P))
+    best = engine.cem_refit(f(params), f(cost), n_elite, 0.7, mean, std, f(np.full(P, 1e-6)))
+    m_ref, s_ref, b_ref, c_ref = cem.cem_refit_numpy(params, cost, n_elite, 0.7, np.zeros(P), np.ones(P), np.full(P, 1e-6))
+    np.testing.assert_allclose(mean.cpu().numpy(), m_ref, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(std.cpu().numpy(), s_ref, rtol=2e-4, atol=2e-6)
+    np.testing.assert_array_equal(best.cpu().numpy()[:-1], b_ref)
+    assert float(best[-1]) == c_ref or (np.isnan(c_ref) and np.isnan(float(best[-1])))
+
+
 def test_population_shards_are_slices_of_the_full_population(engine, full):
     S, ds, segs, cfg, pop = full
     f = lambda a: torch.tensor(np.asarray(a, np.float32), device=engine.device)

@@ -27,7 +27,7 @@ def _segs(config, H, device, steps=None):
 
 
 def test_library_loaded(engine):
-    assert engine.lib.spi_b200_version() == 103
+    assert engine.lib.spi_b200_version() == 104
 
 
 @pytest.mark.parametrize("config,H", [("stand", 5), ("sine", 5), ("jump", 3), ("all", 5)])
