@@ -42,6 +42,10 @@ def main() -> None:
     ap.add_argument("--iterations", type=int, default=5)
     ap.add_argument("--rollout-length", type=float, default=25.0)
     ap.add_argument("--horizon-length", type=float, default=5.0)
+    ap.add_argument("--command-sampling-mode", default="constant", choices=["constant", "polynomial", "bezier"],
+                    help="config/algo/active_sysid.yaml:44-50")
+    ap.add_argument("--poly-degree", type=int, default=3)
+    ap.add_argument("--num-bezier-points", type=int, default=4)
     ap.add_argument("--log-dir", type=Path, default=Path("logs/active_sysid"))
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--fim-mode", default="auto", choices=["auto", "step", "tensor"],
@@ -71,7 +75,8 @@ def main() -> None:
               f"{ex.total_steps} steps/rollout, FIM mode {ex.fim_mode}")
     t0 = time.perf_counter()
     res = act.optimize_commands(ex, args.iterations, args.rollout_length, args.horizon_length, args.seed,
-                                rank=rank, world=world)
+                                rank=rank, world=world, mode=args.command_sampling_mode, poly_degree=args.poly_degree,
+                                num_bezier_points=args.num_bezier_points)
     dt = time.perf_counter() - t0
     if world > 1:
         dist.barrier()

@@ -667,26 +667,98 @@ def commands_constant(values: np.ndarray, num_steps_per_update: int) -> np.ndarr
 
 def commands_polynomial(coeffs: np.ndarray, ranges: np.ndarray, num_steps_per_update: int) -> np.ndarray:
     """coeffs[num_updates, dims, degree + 1] in [-2, 2]: per window a polynomial in t in [0, 1], squashed by tanh to
-    [-1, 1] and mapped linearly onto the range (:316-360)."""
+    [-1, 1] and mapped linearly onto the range (:316-360; float32 accumulation like the reference)."""
     t = np.linspace(0.0, 1.0, num_steps_per_update, dtype=np.float32)
-    powers = np.stack([t ** k for k in range(coeffs.shape[2])], axis=1)          # [steps, deg+1]
     out = []
     for u in range(coeffs.shape[0]):
-        y = np.tanh(powers @ coeffs[u].T)                                         # [steps, dims]
-        lo, hi = ranges[:, 0][None], ranges[:, 1][None]
-        out.append(lo + (y + 1.0) * 0.5 * (hi - lo))
+        seg = np.zeros((num_steps_per_update, coeffs.shape[1]), dtype=np.float32)
+        for d in range(coeffs.shape[1]):
+            poly = np.zeros_like(t)
+            for i in range(coeffs.shape[2]):
+                poly += coeffs[u, d, i] * (t ** i)
+            poly = np.tanh(poly)
+            vmin, vmax = ranges[d]
+            seg[:, d] = vmin + (poly + 1.0) * 0.5 * (vmax - vmin)
+        out.append(seg)
     return np.concatenate(out, axis=0).astype(np.float32)
 
 
-def commands_bezier(points: np.ndarray, num_steps: int) -> np.ndarray:
-    """points[num_points, dims] control points (already inside the ranges) -> Bernstein curve over the rollout
-    (:362-400)."""
-    n = points.shape[0] - 1
-    t = np.linspace(0.0, 1.0, num_steps, dtype=np.float64)
-    out = np.zeros((num_steps, points.shape[1]))
-    for i in range(n + 1):
-        out += (math.comb(n, i) * (t ** i) * ((1 - t) ** (n - i)))[:, None] * points[i][None]
-    return out.astype(np.float32)
+def _binomial_coefficient(n: int, k: int) -> int:
+    """active_sysid.py:402-410 (float product truncated to int, like the reference)."""
+    if k > n - k:
+        k = n - k
+    result = 1
+    for i in range(k):
+        result *= (n - i) / (i + 1)
+    return int(result)
+
+
+def commands_bezier(points: np.ndarray, ranges: np.ndarray, num_steps_per_update: int) -> np.ndarray:
+    """points[num_updates, num_points, dims] control points: per update WINDOW a Bernstein curve over t in [0, 1], every sample
+    clipped to the dimension's range (:362-400) -> [num_updates * steps, dims]."""
+    points = np.asarray(points, dtype=np.float32)
+    n = points.shape[1] - 1
+    t = np.linspace(0, 1, num_steps_per_update, dtype=np.float32)
+    out = []
+    for u in range(points.shape[0]):
+        seg = np.zeros((num_steps_per_update, points.shape[2]), dtype=np.float64)
+        for j in range(n + 1):
+            bern = _binomial_coefficient(n, j) * (t ** j) * ((1 - t) ** (n - j))          # float32 powers, like the reference
+            seg += bern.astype(np.float64)[:, None] * points[u, j].astype(np.float64)[None]
+        out.append(np.clip(seg, ranges[:, 0][None], ranges[:, 1][None]).astype(np.float32))
+    return np.concatenate(out, axis=0).astype(np.float32)
+
+
+def sample_commands(suggest, mode: str, command_ranges=COMMAND_RANGES, num_command_updates: int = 5,
+                    num_steps_per_update: int = 250, sampling_idxs=COMMAND_SAMPLING_IDXS, default_command=DEFAULT_COMMAND,
+                    poly_degree: int = 3, num_bezier_points: int = 4) -> np.ndarray:
+    """ActiveSysId.sample_commands (active_sysid.py:259-293) for the three sampling modes.  `suggest(name, low, high)` plays
+    trial.suggest_float: the parameter names and the ORDER of the calls are the reference's, so a study (or a recorded
+    sequence of suggestions) drives both implementations identically.  -> [num_updates * steps, 14]."""
+    ranges = np.asarray(command_ranges, dtype=np.float32)
+    dims = list(sampling_idxs)
+    sub = ranges[dims]
+    if mode == "constant":                                    # :295-314 — dimension-major suggestion order
+        vals = np.zeros((num_command_updates, len(dims)), dtype=np.float32)
+        for d, actual in enumerate(dims):
+            for u in range(num_command_updates):
+                vals[u, d] = suggest(f"dim_{actual}_update_{u}", float(ranges[actual][0]), float(ranges[actual][1]))
+        sampled = commands_constant(vals, num_steps_per_update)
+    elif mode == "polynomial":                                # :316-360 — update-major, coefficients in [-2, 2]
+        coeffs = np.zeros((num_command_updates, len(dims), poly_degree + 1), dtype=np.float64)
+        for u in range(num_command_updates):
+            for d, actual in enumerate(dims):
+                for i in range(poly_degree + 1):
+                    coeffs[u, d, i] = suggest(f"dim_{actual}_update_{u}_coeff_{i}", -2.0, 2.0)
+        sampled = commands_polynomial(coeffs, sub, num_steps_per_update)
+    elif mode == "bezier":                                    # :362-400 — update-major, control points inside the ranges
+        pts = np.zeros((num_command_updates, num_bezier_points, len(dims)), dtype=np.float32)
+        for u in range(num_command_updates):
+            for d, actual in enumerate(dims):
+                for k in range(num_bezier_points):
+                    pts[u, k, d] = suggest(f"dim_{actual}_update_{u}_bezier_{k}", float(ranges[actual][0]), float(ranges[actual][1]))
+        sampled = commands_bezier(pts, sub, num_steps_per_update)
+    else:
+        raise ValueError(f"Unknown command_sampling_mode: {mode}")
+    return expand_commands(sampled, sampling_idxs, default_command)
+
+
+def search_space(mode: str, **kw):
+    """(names, low, high) of the suggestions one trial makes in `mode`, in call order — the box a vector optimiser
+    (CMA-ES here, optuna's CmaEsSampler in the reference) searches."""
+    names, lo, hi = [], [], []
+
+    def rec(name, low, high):
+        names.append(name); lo.append(low); hi.append(high)
+        return 0.5 * (low + high)
+    sample_commands(rec, mode, **kw)
+    return names, np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)
+
+
+def commands_from_vector(x: np.ndarray, mode: str, **kw) -> np.ndarray:
+    """One trial's parameter vector (in search_space order) -> commands [T, 14]."""
+    it = iter(np.asarray(x, dtype=np.float64).tolist())
+    return sample_commands(lambda name, low, high: next(it), mode, **kw)
 
 
 class CmaEs:
@@ -762,26 +834,27 @@ def gather_main_results(main_reward: torch.Tensor, fim: Optional[torch.Tensor], 
 
 def optimize_commands(explorer: ActiveExploration, iterations: int = 5, rollout_length: float = 25.0,
                       horizon_length: float = 5.0, seed: int = 0, total_steps: Optional[int] = None,
-                      rank: int = 0, world: int = 1, group=None):
-    """The study loop of active_sysid.py:165-242 in `constant` sampling mode: M trials per iteration, 3 sampled command
-    dims x (rollout / horizon) update windows each; objective = -total_reward of the main env.
+                      rank: int = 0, world: int = 1, group=None, mode: str = "constant", poly_degree: int = 3,
+                      num_bezier_points: int = 4):
+    """The study loop of active_sysid.py:165-242: M trials per iteration, each trial's commands sampled in `mode`
+    (`constant` | `polynomial` | `bezier`, config/algo/active_sysid.yaml:44-50) over 3 command dims x (rollout / horizon)
+    update windows; objective = -total_reward of the main env.
 
     Multi-GPU (world > 1): the M = world * explorer.num_main_envs trials of an iteration are sharded contiguously over
     the ranks; every rank runs the same seeded sampler, rolls out its own slice and all-gathers the [M_local] rewards
     and [M_local, P, P] Fisher blocks, so `tell` sees the full population on every rank (no broadcast)."""
     dt = explorer.dt
-    n_updates = int(rollout_length // horizon_length)
-    steps_per_update = int(horizon_length / dt)
-    ranges = np.asarray(COMMAND_RANGES, dtype=np.float32)[COMMAND_SAMPLING_IDXS]
-    lo = np.tile(ranges[:, 0], n_updates); hi = np.tile(ranges[:, 1], n_updates)
+    kw = dict(num_command_updates=int(rollout_length // horizon_length), num_steps_per_update=int(horizon_length / dt),
+              poly_degree=poly_degree, num_bezier_points=num_bezier_points)
+    names, lo, hi = search_space(mode, **kw)
     es = CmaEs(lo, hi, seed=seed)
     M_local, P1 = explorer.num_main_envs, explorer.param_dim + 1
     M = M_local * world
     history, best_fim = [], None
     for it in range(iterations):
-        x = es.ask(M)                                                     # [M, n_updates * dims], identical on every rank
+        x = es.ask(M)                                                     # [M, len(names)], identical on every rank
         mine = x[rank * M_local:(rank + 1) * M_local]
-        cmds = np.stack([expand_commands(commands_constant(xi.reshape(n_updates, -1), steps_per_update)) for xi in mine])
+        cmds = np.stack([commands_from_vector(xi, mode, **kw) for xi in mine])
         out = explorer.evaluate_policy(torch.from_numpy(cmds), total_steps=total_steps)
         dev = explorer.device
         local_r = torch.from_numpy(np.ascontiguousarray(out["total_reward"][::P1])).to(dev)
@@ -794,5 +867,5 @@ def optimize_commands(explorer: ActiveExploration, iterations: int = 5, rollout_
             best_fim = fim[int(np.argmax(main_reward))]
         history.append(float(main_reward.max()))
     best_x, best_v = es.best
-    best_commands = expand_commands(commands_constant(best_x.reshape(n_updates, -1), steps_per_update))
-    return {"best_commands": best_commands, "best_value": -best_v, "history": history, "best_fim": best_fim}
+    return {"best_commands": commands_from_vector(best_x, mode, **kw), "best_value": -best_v, "history": history,
+            "best_fim": best_fim, "param_names": names}

@@ -729,10 +729,12 @@ int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C
     if (int rc = timing_events(m, &e0, &e1)) return rc;
     CUDA_OK(cudaEventRecord(e0, st));
   }
-  // Two anti-phased 32-rollout groups per CTA (rollout_ws.cuh) once the grid fills the GPU more than once; below that
-  // the launch is a single partial wave and the one-group CTAs spread over more SMs.  SPI_B200_WS_HALVES = 1 / 2 forces.
+  // SPI_B200_WS_HALVES=2 (experiment, off): two 32-rollout groups per CTA whose leg phases 1 are kept from overlapping by a
+  // token on named barriers (rollout_ws.cuh).  Measured slower than the independent 5-warp CTAs (43.6 vs 41.4 ms at C = 4096;
+  // SPI_B200_WS_TOKEN=0 / 1, i.e. no token / initial stagger only: 42.2 ms) — a leg warp alone issues at ~0.33 IPC, so a
+  // sub-partition needs >= 3 leg warps in phase 1 at once and serialising them starves it (profiles/README.md r2).
   static const int halves_env = [] { const char* e = getenv("SPI_B200_WS_HALVES"); return e ? atoi(e) : 0; }();
-  const bool two = halves_env ? (halves_env == 2) : (n_cta > 4LL * m->sm_count);
+  const bool two = halves_env == 2;
   if (two) {
     const unsigned n2 = (unsigned)((n_cta + 1) / 2);
     if (minb == 1) ws::rollout_ws2_kernel<1><<<n2, 2 * ws::kWsThreads, 0, st>>>(A);

@@ -41,6 +41,9 @@ reference's real, unmodified code object, called with plain torch tensors:
                      LeggedRobotBase(BaseTask) env built by its real instantiate_env on the product's B200Sim plugin (oracle
                      backend; tests/ref_harness.py, tests/test_b1_reference_env.py): recordings + costs for two chunkings
 
+  commands.npz       ActiveSysId.sample_commands / _sample_constant / _sample_polynomial / _sample_bezier
+                     (spigym/agents/sysid/active_sysid.py:259-410) with a stub trial.suggest_float replaying seeded values
+
 What this cannot pin is the rigid-body physics itself: PhysX is not available.
 """
 from __future__ import annotations
@@ -423,8 +426,41 @@ def gen_b1_env():
     print("b1_env.npz", {k: v.tolist() for k, v in out.items() if k.endswith("_costs")})
 
 
+def gen_commands(rng):
+    """The reference's real command samplers; `self` carries what _init_config (active_sysid.py:101-121) would load from
+    config/algo/active_sysid.yaml:23-50."""
+    import yaml
+    from spigym.agents.sysid.active_sysid import ActiveSysId
+    cc = yaml.safe_load((REF / "spigym" / "config" / "algo" / "active_sysid.yaml").read_text())["algo"]["config"]["command"]
+    dt = 0.02
+    out = dict(num_updates=np.int64(cc["rollout_length"] // cc["horizon_length"]),
+               steps_per_update=np.int64(int(cc["horizon_length"] / dt)))
+    for mode in ("constant", "polynomial", "bezier"):
+        self = SimpleNamespace(default_command=np.array(cc["default_command"], dtype=np.float32),
+                               command_sampling_idxs=cc["command_sampling_idxs"], command_sampling_mode=mode,
+                               num_steps_per_update=int(out["steps_per_update"]), poly_degree=cc["poly_degree"],
+                               num_bezier_points=cc["num_bezier_points"])
+        for name in ("_sample_constant", "_sample_polynomial", "_sample_bezier", "_binomial_coefficient"):
+            setattr(self, name, getattr(ActiveSysId, name).__get__(self))
+        names, values, lows, highs = [], [], [], []
+
+        class Trial:
+            def suggest_float(_, name, low, high):
+                v = float(rng.uniform(low, high)) if mode != "bezier" else float(rng.uniform(low - 0.3 * (high - low), high + 0.3 * (high - low)))
+                names.append(name); values.append(v); lows.append(low); highs.append(high)
+                return v
+        ranges = np.array(cc["command_ranges"], dtype=np.float32)
+        cmds = ActiveSysId.sample_commands(self, Trial(), ranges, int(out["num_updates"]))
+        out[f"{mode}_names"], out[f"{mode}_values"] = np.array(names), np.array(values)
+        out[f"{mode}_low"], out[f"{mode}_high"] = np.array(lows), np.array(highs)
+        out[f"{mode}_commands"] = cmds
+        print("commands.npz", mode, cmds.shape, len(names))
+    np.savez(HERE / "commands.npz", **out)
+
+
 def main():
     R = import_reference()
+    gen_commands(np.random.default_rng(11))
     gen_urdf_blob()
     gen_b1_env()
     gen_ppo_actor()

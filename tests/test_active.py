@@ -209,8 +209,34 @@ def test_command_samplers():
     r = np.asarray(act.COMMAND_RANGES, np.float32)[act.COMMAND_SAMPLING_IDXS]
     p = act.commands_polynomial(rng.uniform(-2, 2, (5, 3, 4)), r, 250)
     assert p.shape == (1250, 3) and (p >= r[:, 0] - 1e-6).all() and (p <= r[:, 1] + 1e-6).all()
-    b = act.commands_bezier(np.array([[0.0], [1.0], [1.0], [0.0]]), 101)
-    assert abs(b[0, 0]) < 1e-7 and abs(b[-1, 0]) < 1e-7 and abs(b[50, 0] - 0.75) < 1e-6
+    # bezier: one curve PER update window, clipped to the range (active_sysid.py:362-400)
+    pts = np.array([[[0.0], [1.0], [1.0], [0.0]], [[0.5], [3.0], [3.0], [0.5]]], np.float32)
+    b = act.commands_bezier(pts, np.array([[0.0, 1.0]], np.float32), 101)
+    assert b.shape == (202, 1) and abs(b[0, 0]) < 1e-7 and abs(b[100, 0]) < 1e-7 and abs(b[50, 0] - 0.75) < 1e-6
+    assert abs(b[101, 0] - 0.5) < 1e-7 and b[101:].max() == 1.0                   # second window restarts at t = 0, clipped
+
+
+@pytest.mark.parametrize("mode", ["constant", "polynomial", "bezier"])
+def test_sample_commands_matches_reference(mode):
+    """tests/golden/commands.npz: the reference's real ActiveSysId.sample_commands (active_sysid.py:259-400) driven by a stub
+    `trial.suggest_float` that replays a recorded sequence — same names, same call order, same commands."""
+    from pathlib import Path
+    g = np.load(Path(__file__).resolve().parent / "golden" / "commands.npz", allow_pickle=True)
+    names, values = list(g[f"{mode}_names"]), g[f"{mode}_values"]
+    seen = []
+    it = iter(values.tolist())
+
+    def suggest(name, low, high):
+        seen.append(name)
+        return next(it)
+    kw = dict(num_command_updates=int(g["num_updates"]), num_steps_per_update=int(g["steps_per_update"]))
+    cmds = act.sample_commands(suggest, mode, **kw)
+    assert seen == names
+    np.testing.assert_allclose(cmds, g[f"{mode}_commands"], rtol=0, atol=1e-6)
+    sp_names, lo, hi = act.search_space(mode, **kw)
+    assert sp_names == names
+    np.testing.assert_allclose(lo, g[f"{mode}_low"]); np.testing.assert_allclose(hi, g[f"{mode}_high"])
+    np.testing.assert_allclose(act.commands_from_vector(values, mode, **kw), g[f"{mode}_commands"], rtol=0, atol=1e-6)
 
 
 def _active_gloo_worker(rank, world, port, out_dir):
@@ -224,7 +250,7 @@ def _active_gloo_worker(rank, world, port, out_dir):
     ex = act.ActiveExploration(be, act.PolicyMLP.random("cpu", seed=1), 4 // world,
                                act.ActiveConfig(exploration_params=["mass", "comx"], seed=3, randomize_reset=False))
     res = act.optimize_commands(ex, iterations=2, rollout_length=0.4, horizon_length=0.2, seed=0, total_steps=12,
-                                rank=rank, world=world)
+                                rank=rank, world=world, mode="bezier" if out_dir.endswith("bezier") else "constant")
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), history=res["history"], best=res["best_commands"],
              fim=res["best_fim"])
     dist.destroy_process_group()
@@ -237,7 +263,7 @@ def test_sharded_command_search_over_gloo_matches_single_process(tmp_path):
     import torch.multiprocessing as mp
     outs = {}
     for world in (1, 2):
-        d = tmp_path / f"w{world}"
+        d = tmp_path / f"w{world}_bezier"          # the per-window bezier sampler drives this search (worker reads the suffix)
         d.mkdir()
         with socket.socket() as s:
             s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
