@@ -133,6 +133,18 @@ def roofline_constants():
     return rec
 
 
+def ncu_executed_flops_per_rollout():
+    """FP32 operations the rollout kernel EXECUTES per (candidate, segment) rollout — 2 x FFMA + FMUL + FADD thread-level counts
+    of the committed ncu capture divided by its rollouts (grid x 32) — or None.  The oracle's op count (the `achieved` figure)
+    includes work the kernel never does (zeros of the joint-origin sparsity, the constant calf projection, divisions)."""
+    p = ROOT / "profiles" / "ncu_rollout_summary.json"
+    try:
+        rec = json.loads(p.read_text())
+        return rec["executed_fp32_flop_per_launch"] / (rec["grid_size"] * 32.0 * 1730.0 / (55.0 * 32.0))
+    except Exception:
+        return None
+
+
 def ncu_traffic():
     """Per-launch DRAM bytes of the rollout kernel from the committed `ncu --set full` summary, or None."""
     p = ROOT / "profiles" / "ncu_rollout_summary.json"
@@ -374,6 +386,12 @@ def run_b200(args):
                        "MEASURED_PEAKS.json holds no FP32 figure",
         "kernel_ms_per_launch": kern_ms_per_launch, "kernel_share_of_step": kern_ms_per_launch / ms_per_step,
         "algorithmic_flops_per_launch": alg_flops, "flops_per_rollout": flops_per_rollout,
+        "executed": (lambda fr: None if fr is None else {
+            "flops_per_rollout": fr, "tflops": fr * C_local * S / (kern_ms_per_launch * 1e-3) / 1e12,
+            "frac": fr * C_local * S / (kern_ms_per_launch * 1e-3) / 1e12 / peak_tf,
+            "note": "hardware-style fraction: FP32 operations the kernel executes (ncu thread-level FFMA x 2 + FMUL + FADD, "
+                    "profiles/ncu_rollout_summary.json) over the same FFMA peak; `frac` above counts the oracle's operations"
+        })(ncu_executed_flops_per_rollout()),
         "hbm": {"algorithmic_bytes_per_launch": alg_bytes,
                 "achieved_gbs": alg_bytes / (kern_ms_per_launch * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",

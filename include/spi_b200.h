@@ -235,6 +235,9 @@ int spi_b200_fim_reward(spi_b200_model* model, const float* states, int M, int P
  *   hist_index may be NULL — and the actor runs through spi_b200_policy_forward_ring with the matching head position;
  *   hist_index [840] device ints (short_history gather); fim_hist [K,M,P1,25] + fim_live [K,M] or NULL;
  *   dead_steps [N] or NULL (+= done); schedule [steps,4] device ints (command row, sync flag, FIM slot, ring head),
+ *   fim_jtj [M,P,P] / fim_trace [M] (or NULL): FUSED Fisher accumulation — jtj[m] += live * J J^T of this step, trace[m] += its
+ *   trace, J = (main - aux_p) / fim_delta in R^{P x 25} (active_sysid_openloop.py:402-426), from the rows the kernel already
+ *   holds; the alternative to recording fim_hist / fim_live for spi_b200_fim_contract (pass those as NULL then);
  *   counter [1] / ctrl [4] device ints: ctrl <- schedule[counter++] on the device before the step; schedule has
  *   `schedule_rows` rows of 4 ints — a step past the last row re-reads the last row instead of running off the buffer;
  *   q_default [12] HOST.  1 <= P1 <= 17.                                                                          */
@@ -242,8 +245,8 @@ int spi_b200_active_post_step(spi_b200_model* model, float* state, const float* 
                               const float* main_commands, int T, float* commands, float* actions, float* gait,
                               float* clock, float* history, float* obs, void* obs_hi, void* obs_lo, int obs_stride,
                               int ring_slots, const int* hist_index, float* fim_hist,
-                              unsigned char* fim_live, float* dead_steps, const int* schedule, int schedule_rows,
-                              int* counter, int* ctrl, int M, int P1, float dt, float action_clip, float clip_obs, float grav_x, float grav_y,
+                              unsigned char* fim_live, float* dead_steps, float* fim_jtj, float* fim_trace, float fim_delta,
+                              const int* schedule, int schedule_rows, int* counter, int* ctrl, int M, int P1, float dt, float action_clip, float clip_obs, float grav_x, float grav_y,
                               const float* q_default, void* cuda_stream);
 
 /* The locomotion policy (actor MLP: Linear-ELU x3 + Linear; spigym/agents/modules/modules.py:47-63,

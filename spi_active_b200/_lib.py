@@ -81,9 +81,11 @@ SIGNATURES = {
     "spi_b200_body_states": (C.c_int, [_V, _V, C.c_int, _V, _V]),
     "spi_b200_compute_torques": (C.c_int, [_V, _V, _V, _V, _V, _V, C.c_int, C.c_int, C.c_uint, _V, _V]),
     "spi_b200_fim_reward": (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_float, C.c_int, _V, _V, _V]),
-    "spi_b200_active_post_step": (C.c_int, [_V, _V, _V, _V, _V, C.c_int, _V, _V, _V, _V, _V, _V, _V, _V, C.c_int, C.c_int, _V, _V,
-                                            _V, _V, _V, C.c_int, _V, _V, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
-                                            C.c_float, C.c_float, _F, _V]),
+    "spi_b200_active_post_step": (C.c_int, [_V, _V, _V, _V, _V, C.c_int,                       # model .. main_commands, T
+                                            _V, _V, _V, _V, _V, _V, _V, _V, C.c_int, C.c_int,  # commands .. obs_lo, obs_stride, ring_slots
+                                            _V, _V, _V, _V, _V, _V, C.c_float,                 # hist_index, fim_hist, fim_live, dead_steps, fim_jtj, fim_trace, fim_delta
+                                            _V, C.c_int, _V, _V, C.c_int, C.c_int,             # schedule, schedule_rows, counter, ctrl, M, P1
+                                            C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _F, _V]),
     "spi_b200_policy_create": (C.c_int, [_I, C.POINTER(_F), C.POINTER(_F), C.POINTER(_V)]),
     "spi_b200_policy_destroy": (C.c_int, [_V]),
     "spi_b200_policy_input_layout": (C.c_int, [_V, C.c_int, _I, _I]),

@@ -198,7 +198,8 @@ class ActiveConfig:
     randomize_reset: bool = True          # legged_robot_base.py:737-784 reset distribution
     seed: int = 0
     # "step": J J^T per control step on CUDA cores (spi_b200_fim_reward); "tensor": the states of `fim_chunk` steps are
-    # kept on device and contracted on the tensor cores (spi_b200_fim_contract); "auto": tensor on a CUDA backend
+    # kept on device and contracted on the tensor cores (spi_b200_fim_contract); "fused": accumulated inside the post-step
+    # kernel from the rows it already holds (no state history); "auto": tensor on a CUDA backend
     fim_mode: str = "auto"
     fim_chunk: int = 64
     # "torch": the post-physics bookkeeping of a step as ~130 torch ops (device-agnostic statement, runs on the CPU
@@ -260,13 +261,18 @@ class ActiveExploration:
         mode = c.fim_mode
         if mode == "auto":
             mode = "tensor" if (self.device.type == "cuda" and hasattr(backend, "fim_contract")) else "step"
-        if mode not in ("step", "tensor"):
-            raise ValueError(f"fim_mode must be 'auto', 'step' or 'tensor', not {c.fim_mode!r}")
+        if mode not in ("step", "tensor", "fused"):
+            raise ValueError(f"fim_mode must be 'auto', 'step', 'tensor' or 'fused', not {c.fim_mode!r}")
+        if mode == "fused" and not hasattr(backend, "active_post_step"):
+            raise ValueError("fim_mode='fused' needs a backend with active_post_step")
         if mode == "tensor" and not hasattr(backend, "fim_contract"):
             raise ValueError("fim_mode='tensor' needs a backend with fim_contract")
         if mode == "tensor" and self.param_dim > 16:
             raise ValueError("fim_mode='tensor' supports at most 16 exploration parameters")
         self.fim_mode = mode
+        if mode == "fused":       # J J^T accumulated inside spi_b200_active_post_step: no state history at all
+            self.hist = self.live_hist = None
+            self.trace_acc, self.dead_steps = z(self.num_main_envs), z(N)
         if mode == "tensor":
             K = max(1, int(c.fim_chunk))
             self.hist = z(K, self.num_main_envs, self.param_dim + 1, 25)
@@ -276,11 +282,13 @@ class ActiveExploration:
             self._hist_count = 0
         impl = c.step_impl
         if impl == "auto":
-            impl = "fused" if (mode == "tensor" and hasattr(backend, "active_post_step")) else "torch"
+            impl = "fused" if (mode in ("tensor", "fused") and hasattr(backend, "active_post_step")) else "torch"
         if impl not in ("torch", "fused"):
             raise ValueError(f"step_impl must be 'auto', 'torch' or 'fused', not {c.step_impl!r}")
-        if impl == "fused" and not (mode == "tensor" and hasattr(backend, "active_post_step")):
-            raise ValueError("step_impl='fused' needs fim_mode='tensor' and a backend with active_post_step")
+        if impl == "fused" and not (mode in ("tensor", "fused") and hasattr(backend, "active_post_step")):
+            raise ValueError("step_impl='fused' needs fim_mode='tensor' or 'fused' and a backend with active_post_step")
+        if mode == "fused" and impl != "fused":
+            raise ValueError("fim_mode='fused' needs step_impl='fused'")
         self.step_impl = impl
         if impl == "fused":
             self.hist_index_i32 = self.hist_index.to(torch.int32).contiguous()
@@ -402,7 +410,10 @@ class ActiveExploration:
                                       self.live_hist, self.dead_steps, self.schedule,
                                       self.counter, self.ctrl, self.dt, c.action_clip, CLIP_OBSERVATIONS,
                                       TERMINATION_GRAVITY, self.model.q_default, obs_hi=self.obs_hi, obs_lo=self.obs_lo,
-                                      ring_slots=RING_SLOTS if ring else 0)
+                                      ring_slots=RING_SLOTS if ring else 0,
+                                      fim_jtj=self.jtj if self.fim_mode == "fused" else None,
+                                      fim_trace=self.trace_acc if self.fim_mode == "fused" else None,
+                                      fim_delta=float(c.delta_param))
 
     # ---- ring mode: the plain observation / history exist only on request ------------------------------------------------
     def materialize_observation(self):
@@ -441,7 +452,7 @@ class ActiveExploration:
     def _build_schedule(self, n_calls: int, T: int):
         """Row i = the host inputs of the (i + 1)-th env step after a reset: (command row, k-sync flag, FIM ring slot)
         — what _advance_inputs computes step by step, uploaded once."""
-        k, K = self.cfg.ksync_steps, self.hist.shape[0]
+        k, K = self.cfg.ksync_steps, (self.hist.shape[0] if self.hist is not None else 1)
         n_rows = n_calls + 4              # + the rows the graph warm-up / capture steps read past the end
         rows = np.zeros((n_rows, 4), dtype=np.int32)
         for i in range(n_rows):
@@ -536,9 +547,9 @@ class ActiveExploration:
         assert commands.shape[0] == self.num_main_envs and commands.shape[2] == 14
         self.reset_all(commands, total_steps, initial_main_states)
         self.total_reward.zero_(); self.jtj.zero_()
-        if self.fim_mode == "tensor":
+        if self.fim_mode in ("tensor", "fused"):      # the reset step's record / contribution is dropped, like its reward (:545-548)
             self.trace_acc.zero_(); self.dead_steps.zero_()
-            self._hist_count = 0                      # the reset step's record is dropped, like its reward (:545-548)
+            self._hist_count = 0
         self._graph_ok = self.device.type == "cuda" if use_cuda_graph is None else use_cuda_graph
         self._steps_done = 1
         self._steps_scheduled = total_steps
@@ -566,8 +577,9 @@ class ActiveExploration:
     @torch.no_grad()
     def finish_rollout(self):
         step = self._steps_done
-        if self.fim_mode == "tensor":
-            self._flush_fim()
+        if self.fim_mode in ("tensor", "fused"):
+            if self.fim_mode == "tensor":
+                self._flush_fim()
             self.total_reward.copy_(self.trace_acc.repeat_interleave(self.param_dim + 1)
                                     + self.cfg.termination_rew * self.dead_steps)
         return {"total_reward": (self.total_reward / step).cpu().numpy(), "fim": (self.jtj / step).cpu().numpy(),
@@ -579,6 +591,8 @@ class ActiveExploration:
                 self.total_reward, self.jtj, self.step_reward]
         if self.fim_mode == "tensor":
             live += [self.dead_steps]                 # hist / live_hist slots are rewritten before they are read
+        if self.fim_mode == "fused":
+            live += [self.dead_steps, self.trace_acc]
         if self.step_impl == "fused":
             live += [self.counter, self.ctrl]         # the warm-up / capture steps must not consume schedule rows
             if self.tc_policy is not None:

@@ -53,6 +53,12 @@ struct Args {
   float* fim_hist;                 // [K,M,P1,25] or null
   unsigned char* fim_live;         // [K,M] or null
   float* dead_steps;               // [N] or null
+  // fused Fisher accumulation (alternative to fim_hist + spi_b200_fim_contract): jtj[m] += live * J J^T of THIS step, trace[m] +=
+  // its trace, with J = (main - aux_p) * inv_delta in R^{P x 25} (active_sysid_openloop.py:402-426) formed from the state rows
+  // the kernel already holds in shared memory — no [T, M, P1, 25] history is written or read back
+  float* fim_jtj;                  // [M,P,P] or null
+  float* fim_trace;                // [M] or null
+  float fim_inv_delta;
   const int* ctrl;                 // device: [0] command row t, [1] k-sync flag, [2] FIM ring slot, [3] observation ring head
                                    // (written by tick_kernel)
   int M, P1, T;
@@ -137,7 +143,33 @@ __global__ void __launch_bounds__(32 * kMaxGroup) active_post_step_kernel(const 
   if (A.fim_hist) {
     if (lane < kFimDim) A.fim_hist[(((size_t)slot * A.M + m) * A.P1 + w) * kFimDim + lane] = s[lane];
     if (w == 0 && lane == 0) A.fim_live[(size_t)slot * A.M + m] = group_done ? 0 : 1;
-    if (lane == 0 && A.dead_steps) A.dead_steps[env] += group_done ? 1.0f : 0.0f;
+  }
+  if ((A.fim_hist || A.fim_jtj) && lane == 0 && A.dead_steps) A.dead_steps[env] += group_done ? 1.0f : 0.0f;
+  if (A.fim_jtj && !group_done) {
+    // one (p, q) entry per thread: 25-term dot product of two difference rows (the rows sit in shared memory: sm.st(i)[0 .. 25))
+    const int P = A.P1 - 1;
+    const float* main_row = sm.st(0);
+    for (int idx = threadIdx.x; idx < P * P; idx += blockDim.x) {
+      const int p = idx / P, q = idx - p * P;
+      const float* ap = sm.st(p + 1);
+      const float* aq = sm.st(q + 1);
+      float acc = 0.f;
+#pragma unroll 5
+      for (int d = 0; d < kFimDim; d++)
+        acc = fmaf((main_row[d] - ap[d]) * A.fim_inv_delta, (main_row[d] - aq[d]) * A.fim_inv_delta, acc);
+      A.fim_jtj[((size_t)m * P + p) * P + q] += acc;
+    }
+    if (w == 0 && A.fim_trace) {             // trace = ||J||_F^2, summed in a fixed order (lane p, then a shuffle tree)
+      float t = 0.f;
+      if (lane < P) {
+        const float* ap = sm.st(lane + 1);
+#pragma unroll 5
+        for (int d = 0; d < kFimDim; d++) { const float j = (main_row[d] - ap[d]) * A.fim_inv_delta; t = fmaf(j, j, t); }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) A.fim_trace[m] += t;
+    }
   }
 
   // ---- the 60 scaled observation terms ---------------------------------------------------------------------------------

@@ -1030,8 +1030,8 @@ int spi_b200_active_post_step(spi_b200_model* m, float* state, const float* raw_
                               const float* main_commands, int T, float* commands, float* actions, float* gait,
                               float* clock, float* history, float* obs, void* obs_hi, void* obs_lo, int obs_stride,
                               int ring_slots, const int* hist_index, float* fim_hist,
-                              unsigned char* fim_live, float* dead_steps, const int* schedule, int schedule_rows,
-                              int* counter, int* ctrl,
+                              unsigned char* fim_live, float* dead_steps, float* fim_jtj, float* fim_trace, float fim_delta,
+                              const int* schedule, int schedule_rows, int* counter, int* ctrl,
                               int Mn, int P1, float dt, float action_clip, float clip_obs, float grav_x, float grav_y,
                               const float* q_default, void* cuda_stream) {
   if (!m) return fail(-1, "model handle is NULL");
@@ -1045,6 +1045,7 @@ int spi_b200_active_post_step(spi_b200_model* m, float* state, const float* raw_
     return fail(-3, "ring mode needs obs_hi / obs_lo with obs_stride >= 900");
   if (ring_slots == 0 && (!history || !obs || !hist_index)) return fail(-3, "NULL buffer");
   if (fim_hist && !fim_live) return fail(-3, "fim_live is NULL");
+  if (fim_jtj && !(fim_delta != 0.f)) return fail(-3, "fim_delta must be non-zero with fim_jtj");
   if (obs_hi && (!obs_lo || obs_stride < activestep::kObs)) return fail(-3, "obs_lo is NULL or obs_stride < 900");
   static std::atomic<unsigned long long> attr_done{0};
   int attr_dev = -1;
@@ -1059,6 +1060,7 @@ int spi_b200_active_post_step(spi_b200_model* m, float* state, const float* raw_
   A.obs_hi = static_cast<__half*>(obs_hi); A.obs_lo = static_cast<__half*>(obs_lo); A.obs_stride = obs_stride;
   A.obs_scale = mlptc::kActScale; A.ring_slots = ring_slots;
   A.fim_hist = fim_hist; A.fim_live = fim_live; A.dead_steps = dead_steps; A.ctrl = ctrl;
+  A.fim_jtj = fim_jtj; A.fim_trace = fim_trace; A.fim_inv_delta = fim_delta != 0.f ? 1.0f / fim_delta : 0.f;
   A.M = Mn; A.P1 = P1; A.T = T; A.dt = dt; A.action_clip = action_clip; A.clip_obs = clip_obs;
   A.grav_x = grav_x; A.grav_y = grav_y;
   for (int j = 0; j < 12; j++) A.q_default[j] = q_default[j];

@@ -381,10 +381,14 @@ class RolloutEngine:
     def active_post_step(self, state, raw_actions, done, main_commands, commands, actions, gait, clock, history, obs,
                          hist_index, fim_hist, fim_live, dead_steps, schedule, counter, ctrl, dt: float,
                          action_clip: float, clip_obs: float, grav_xy, q_default, obs_hi=None, obs_lo=None,
-                         ring_slots: int = 0):
+                         ring_slots: int = 0, fim_jtj=None, fim_trace=None, fim_delta: float = 0.0):
         """The fused post-physics step of the active-exploration rollout (spi_b200_active_post_step); every tensor is
         updated in place.  state[N,37], main_commands[M,T,14], N = M * P1.  ring_slots = 15: obs_hi / obs_lo are the ring
-        of frames the actor reads (history / obs / hist_index unused, may be None)."""
+        of frames the actor reads (history / obs / hist_index unused, may be None).  fim_jtj [M,P,P] / fim_trace [M]: fused
+        Fisher accumulation inside the kernel (fim_hist / fim_live then None)."""
+        if fim_jtj is not None:
+            assert fim_jtj.is_cuda and fim_jtj.is_contiguous() and fim_jtj.dtype == torch.float32 and fim_delta != 0.0
+            assert fim_trace is None or (fim_trace.is_cuda and fim_trace.is_contiguous() and fim_trace.dtype == torch.float32)
         Mn, T = int(main_commands.shape[0]), int(main_commands.shape[1])
         N = int(state.shape[0])
         P1 = N // Mn
@@ -399,7 +403,8 @@ class RolloutEngine:
                 self._handle, _ptr(state), _ptr(raw_actions), _ptr(done), _ptr(main_commands), T, _ptr(commands),
                 _ptr(actions), _ptr(gait), _ptr(clock), _ptr(history), _ptr(obs), _ptr(obs_hi), _ptr(obs_lo),
                 0 if obs_hi is None else int(obs_hi.shape[1]), int(ring_slots), _ptr(hist_index), _ptr(fim_hist),
-                _ptr(fim_live), _ptr(dead_steps), _ptr(schedule), int(schedule.shape[0]), _ptr(counter), _ptr(ctrl), Mn, P1, float(dt),
+                _ptr(fim_live), _ptr(dead_steps), _ptr(fim_jtj), _ptr(fim_trace), float(fim_delta), _ptr(schedule),
+                int(schedule.shape[0]), _ptr(counter), _ptr(ctrl), Mn, P1, float(dt),
                 float(action_clip), float(clip_obs), float(grav_xy[0]), float(grav_xy[1]),
                 qd.ctypes.data_as(C.POINTER(C.c_float)), self._stream())
         _lib.check(rc, "spi_b200_active_post_step")

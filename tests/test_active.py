@@ -433,6 +433,36 @@ def test_evaluate_policy_fused_matches_torch_path(engine):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("graph", [False, True])
+def test_fused_fisher_accumulation_matches_tensor_core_contraction(engine, graph):
+    """fim_mode='fused' (J J^T accumulated inside spi_b200_active_post_step from the rows it already holds, no state history)
+    against fim_mode='tensor' (history + tcgen05 spi_b200_fim_contract): same physics, same actor, so rewards and Fisher
+    blocks agree to fp32 summation order — incl. a group that terminates mid-rollout (its later steps score 0) and P = 10."""
+    import dataclasses
+    base = act.ActiveConfig(exploration_params=list(act.ActiveExploration.PARAM_ORDER), ksync_steps=5, seed=3, fim_chunk=8)
+    cmds = _commands(9, 60, seed=4)
+    res = {}
+    for mode in ("tensor", "fused"):
+        ex = act.ActiveExploration(engine, act.PolicyMLP.random(engine.device, seed=1), 9, dataclasses.replace(base, fim_mode=mode))
+        assert ex.fim_mode == mode and ex.step_impl == "fused" and (mode == "tensor") == (ex.hist is not None)
+        n = ex.begin_rollout(cmds, 40, graph)
+        for k in range(n):
+            if k == 11:
+                ex.state[3 * 11, 3:7] = torch.tensor([0.70710678, 0.0, 0.0, 0.70710678], device=engine.device)   # tip group 3
+            ex.advance_rollout()
+        res[mode] = ex.finish_rollout()
+        if graph:      # a second rollout through the captured step restarts cleanly
+            again = ex.evaluate_policy(cmds, total_steps=40, use_cuda_graph=True)
+            first = ex.evaluate_policy(cmds, total_steps=40, use_cuda_graph=True)
+            np.testing.assert_array_equal(again["total_reward"], first["total_reward"])
+    a, b = res["tensor"], res["fused"]
+    assert a["steps"] == b["steps"]
+    np.testing.assert_allclose(b["total_reward"], a["total_reward"], rtol=2e-5)
+    np.testing.assert_allclose(b["fim"], a["fim"], rtol=1e-4, atol=2e-6 * np.abs(a["fim"]).max())
+    assert b["total_reward"][3 * 11] != b["total_reward"][0]
+
+
+@pytest.mark.gpu
 def test_pipelined_exploration_matches_single_explorer_gpu(engine):
     """Two independent explorers replaying their captured steps on two streams give the same rewards / Fisher blocks as one
     explorer on the whole population (every kernel is deterministic per row; only the FIM chunking of the tensor-core

@@ -68,6 +68,17 @@ def main():
         if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") and "not_issued" not in h:
             stalls[h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]] = float(v)
     out["dram_bytes_per_launch"] = out.get("dram_bytes_read", 0.0) + out.get("dram_bytes_write", 0.0)
+    # FP32 operations the kernel actually EXECUTED (thread level, predicated-on): 2 x FFMA + FMUL + FADD per elapsed cycle x cycles
+    per_cycle = {}
+    for op in ("ffma", "fmul", "fadd"):
+        key = f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed"
+        if key in hdr:
+            per_cycle[op] = float(vals[hdr.index(key)].replace(",", ""))
+    if len(per_cycle) == 3 and "duration" in out and "sm_clock" in out:
+        cycles = out["duration"] * out["sm_clock"] * 1e9
+        out["executed_fp32"] = {"thread_ops_per_cycle": per_cycle,
+                                "flop_per_launch": (2 * per_cycle["ffma"] + per_cycle["fmul"] + per_cycle["fadd"]) * cycles,
+                                "note": "2 x FFMA + FMUL + FADD (MUFU / FMNMX not counted)"}
     out["stall_cycles_per_issued_instruction"] = dict(sorted(stalls.items(), key=lambda kv: -kv[1]))
     if a.launches:
         lr = [r for r in csv.reader(open(a.launches)) if len(r) > 10]
@@ -86,6 +97,7 @@ def main():
         (ROOT / "profiles" / "ncu_rollout_summary.json").write_text(json.dumps(
             {"source": dst.name, "kernel": out["kernel"], "grid_size": out.get("grid_size"),
              "dram_bytes_per_launch": out["dram_bytes_per_launch"],
+             "executed_fp32_flop_per_launch": out.get("executed_fp32", {}).get("flop_per_launch"),
              "note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the rollout kernel at the grid "
                      "size above (ncu --set full); the dataset and candidate rows are L2-resident, so DRAM traffic "
                      "does not grow with the candidate count"}, indent=1) + "\n")
