@@ -185,6 +185,16 @@ int spi_b200_sim_step(spi_b200_model* model,
                       float* state, const float* torques, int N, int n_steps,
                       float* out_foot_force, void* cuda_stream);
 
+/* The same step with external wrenches (IsaacGym.apply_rigid_body_force_at_pos_tensor,
+ * spigym/simulator/isaacgym/isaacgym.py:609-613): ext_wrench [N,13,6] or NULL = [torque; force] on each of the 13 moving
+ * bodies (base, then hip / thigh / calf of FL, FR, RL, RR; forces on feet / head links belong to the calf / base they are
+ * fixed to) expressed in the body's own link frame about its link origin, held constant over the n_steps physics steps.
+ * spi_active_b200.simulator.B200Sim converts the reference's world-frame (force, position) pairs of the 19 Isaac Gym bodies. */
+int spi_b200_sim_step_ext(spi_b200_model* model,
+                          const float* params, int P, const int* param_ids, unsigned flags,
+                          float* state, const float* torques, const float* ext_wrench, int N, int n_steps,
+                          float* out_foot_force, void* cuda_stream);
+
 /* Rigid-body state tensor of the 19 Isaac Gym bodies (spigym/simulator/isaacgym/isaacgym.py:541-577
  * `_rigid_body_pos / _rot / _vel / _ang_vel`; body order of spigym/config/robot/go2/go2.yaml:44: base, FL hip / thigh /
  * calf / foot, FR ..., Head_upper, Head_lower, RL ..., RR ...) by forward kinematics of the engine state.

@@ -86,8 +86,10 @@ def rollout_states(blob, params, param_ids, seg_init, seg_actions, seg_gains=Non
     return out
 
 
-def sim_step(blob, state, torques, n_steps=1, params=None, param_ids=None, flags=0, return_foot_force=False):
-    """state[N,37] float64 (copied), torques[N,12] -> new state (, foot_force[N,4,3])"""
+def sim_step(blob, state, torques, n_steps=1, params=None, param_ids=None, flags=0, return_foot_force=False,
+             ext_wrench=None):
+    """state[N,37] float64 (copied), torques[N,12] -> new state (, foot_force[N,4,3]).  ext_wrench[N,13,6]: external
+    [torque; force] on the 13 moving bodies (base, then hip / thigh / calf per leg) in their link frames, held for the call."""
     blob = _f32(blob)
     state = np.array(state, dtype=np.float64, order="C").reshape(-1, 37)
     torques = np.ascontiguousarray(torques, dtype=np.float64).reshape(-1, 12)
@@ -99,9 +101,10 @@ def sim_step(blob, state, torques, n_steps=1, params=None, param_ids=None, flags
         P = params.shape[1]
         ids = np.ascontiguousarray(param_ids, dtype=np.int32)
     ff = np.zeros((N, 4, 3), dtype=np.float64)
-    rc = lib().spi_oracle_sim_step(_ptr(blob), C.c_int(blob.size), _ptr(params), C.c_int(P), _ptr(ids, C.c_int),
-                                   C.c_uint(flags), _ptr(state, C.c_double), _ptr(torques, C.c_double),
-                                   C.c_int(N), C.c_int(n_steps), _ptr(ff, C.c_double))
+    ext = None if ext_wrench is None else np.ascontiguousarray(ext_wrench, dtype=np.float64).reshape(N, 13, 6)
+    rc = lib().spi_oracle_sim_step_ext(_ptr(blob), C.c_int(blob.size), _ptr(params), C.c_int(P), _ptr(ids, C.c_int),
+                                       C.c_uint(flags), _ptr(state, C.c_double), _ptr(torques, C.c_double),
+                                       C.c_int(N), C.c_int(n_steps), _ptr(ff, C.c_double), _ptr(ext, C.c_double))
     if rc != 0:
         raise RuntimeError(f"spi_oracle_sim_step failed: {rc}")
     return (state, ff) if return_foot_force else state

@@ -131,9 +131,17 @@ int spi_oracle_rollout_states(int precision, const float* blob, int n_floats, co
 }
 
 // stepwise simulator: N envs, n_steps physics steps under constant torques (double precision)
+int spi_oracle_sim_step_ext(const float* blob, int n_floats, const float* params, int P, const int* ids, unsigned flags,
+                            double* state, const double* torques, int N, int n_steps, double* out_foot_force,
+                            const double* ext_wrench /*[N,13,6] body-frame [torque; force] per moving body, or null*/);
 int spi_oracle_sim_step(const float* blob, int n_floats, const float* params, int P, const int* ids, unsigned flags,
                         double* state /*[N,37] in/out*/, const double* torques /*[N,12]*/, int N, int n_steps,
                         double* out_foot_force /*[N,4,3] or null*/) {
+  return spi_oracle_sim_step_ext(blob, n_floats, params, P, ids, flags, state, torques, N, n_steps, out_foot_force, nullptr);
+}
+int spi_oracle_sim_step_ext(const float* blob, int n_floats, const float* params, int P, const int* ids, unsigned flags,
+                            double* state, const double* torques, int N, int n_steps, double* out_foot_force,
+                            const double* ext_wrench) {
   Model<double> M;
   if (!M.load(blob, n_floats)) return -1;
   parallel_for(N, 0, 16, [&](long long e) {
@@ -147,7 +155,13 @@ int spi_oracle_sim_step(const float* blob, int n_floats, const float* params, in
     st.w = V3<double>(sp[10], sp[11], sp[12]);
     for (int j = 0; j < 12; j++) { st.q[j] = sp[13 + j]; st.qd[j] = sp[25 + j]; }
     V3<double> ff[4];
-    for (int k = 0; k < n_steps; k++) physics_step(M, Ib, st, torques + (size_t)e * 12, ff);
+    SV<double> ext[13];
+    if (ext_wrench)
+      for (int b = 0; b < 13; b++) {
+        const double* w = ext_wrench + ((size_t)e * 13 + b) * 6;
+        ext[b].a = V3<double>(w[0], w[1], w[2]); ext[b].l = V3<double>(w[3], w[4], w[5]);
+      }
+    for (int k = 0; k < n_steps; k++) physics_step(M, Ib, st, torques + (size_t)e * 12, ff, ext_wrench ? ext : nullptr);
     st.to(sp);
     if (out_foot_force)
       for (int l = 0; l < 4; l++) {

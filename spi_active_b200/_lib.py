@@ -78,6 +78,7 @@ SIGNATURES = {
                                           C.c_int, C.c_uint, _V, _V]),
     "spi_b200_env_step": (C.c_int, [_V, _V, C.c_int, _I, _V, _V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_uint, _V]),
     "spi_b200_sim_step": (C.c_int, [_V, _V, C.c_int, _I, C.c_uint, _V, _V, C.c_int, C.c_int, _V, _V]),
+    "spi_b200_sim_step_ext": (C.c_int, [_V, _V, C.c_int, _I, C.c_uint, _V, _V, _V, C.c_int, C.c_int, _V, _V]),
     "spi_b200_body_states": (C.c_int, [_V, _V, C.c_int, _V, _V]),
     "spi_b200_compute_torques": (C.c_int, [_V, _V, _V, _V, _V, _V, C.c_int, C.c_int, C.c_uint, _V, _V]),
     "spi_b200_fim_reward": (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_float, C.c_int, _V, _V, _V]),

@@ -319,8 +319,10 @@ SPI_DEV float group_sum(float x) {
 
 // ---- one integrator sub-step of length h under joint torques tau[3] (this lane's leg) --------------
 // foot_force (optional): world-frame contact force on this lane's foot.
+// ext (optional): external [torque; force] on this lane's three leg bodies (ext[0..18)) and on the base (ext_base[6]), each in
+// the body's link frame about its origin — spi_b200_sim_step_ext.
 SPI_DEV void substep(const SimConst& S, const LegConst& L, const BaseInertia& B, LaneState& s, const float* tau,
-                     float h, float* foot_force) {
+                     float h, float* foot_force, const float* ext = nullptr, const float* ext_base = nullptr) {
   // base rotation (body -> world) and body-frame velocities
   float R[9];
   {
@@ -388,6 +390,14 @@ SPI_DEV void substep(const SimConst& S, const LegConst& L, const BaseInertia& B,
     }
     if (foot_force) { foot_force[0] = F[0]; foot_force[1] = F[1]; foot_force[2] = F[2]; }
   }
+  if (ext) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      p1.a[i] -= ext[i]; p1.l[i] -= ext[3 + i];
+      p2.a[i] -= ext[6 + i]; p2.l[i] -= ext[9 + i];
+      p3.a[i] -= ext[12 + i]; p3.l[i] -= ext[15 + i];
+    }
+  }
   // inward pass up the leg
   ABInertia A3, A2, A1, A0;
   abi_from_rigid(L.m[2], L.h[2], L.Io[2], A3);
@@ -429,6 +439,10 @@ SPI_DEV void substep(const SimConst& S, const LegConst& L, const BaseInertia& B,
     cross3(v0.a, f, t3);
 #pragma unroll
     for (int i = 0; i < 3; i++) { p0.a[i] += t1[i] + t2[i]; p0.l[i] += t3[i]; }
+  }
+  if (ext_base) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) { p0.a[i] -= ext_base[i]; p0.l[i] -= ext_base[3 + i]; }
   }
   Spatial6 a0;
   solve_base(A0, p0, a0);

@@ -199,6 +199,7 @@ struct StepArgs {
   const float* params; int P; ParamIds ids; unsigned flags;
   float* state; const float* torques; int N, n_steps;
   float* foot_force;
+  const float* ext_wrench;   // [N,13,6] or null
 };
 __global__ void __launch_bounds__(kThreads) sim_step_kernel(const StepArgs A) {
   const DeviceModel& M = *A.model;
@@ -218,8 +219,17 @@ __global__ void __launch_bounds__(kThreads) sim_step_kernel(const StepArgs A) {
 #pragma unroll
   for (int j = 0; j < 3; j++) tau[j] = A.torques[(size_t)env * 12 + 3 * leg + j];
   const float h = S.dt / (float)S.nsub;
+  float ext[18], ext_base[6];
+  if (A.ext_wrench) {
+    const float* w = A.ext_wrench + (size_t)env * 13 * 6;
+#pragma unroll
+    for (int i = 0; i < 6; i++) ext_base[i] = w[i];
+#pragma unroll
+    for (int i = 0; i < 18; i++) ext[i] = w[6 + 18 * leg + i];
+  }
   for (int k = 0; k < A.n_steps; k++)
-    for (int n = 0; n < S.nsub; n++) substep(S, L, B, s, tau, h, ff);
+    for (int n = 0; n < S.nsub; n++)
+      substep(S, L, B, s, tau, h, ff, A.ext_wrench ? ext : nullptr, A.ext_wrench ? ext_base : nullptr);
   if (active) {
     store_lane_state(A.state + (size_t)env * SPI_STATE_DIM, leg, s);
     if (A.foot_force) {
@@ -980,6 +990,12 @@ int spi_b200_env_step(spi_b200_model* m, const float* params, int P, const int* 
 
 int spi_b200_sim_step(spi_b200_model* m, const float* params, int P, const int* param_ids, unsigned flags, float* state,
                       const float* torques, int N, int n_steps, float* out_foot_force, void* cuda_stream) {
+  return spi_b200_sim_step_ext(m, params, P, param_ids, flags, state, torques, nullptr, N, n_steps, out_foot_force, cuda_stream);
+}
+
+int spi_b200_sim_step_ext(spi_b200_model* m, const float* params, int P, const int* param_ids, unsigned flags, float* state,
+                          const float* torques, const float* ext_wrench, int N, int n_steps, float* out_foot_force,
+                          void* cuda_stream) {
   if (!m) return fail(-1, "model handle is NULL");
   if (N <= 0 || n_steps < 0) return fail(-3, "N must be positive, n_steps non-negative");
   if (!state || !torques) return fail(-3, "state / torques is NULL");
@@ -988,6 +1004,7 @@ int spi_b200_sim_step(spi_b200_model* m, const float* params, int P, const int* 
   if (int rc = make_ids(params ? P : 0, param_ids, &A.ids)) return rc;
   A.model = m->d_model; A.params = params; A.P = P; A.flags = flags;
   A.state = state; A.torques = torques; A.N = N; A.n_steps = n_steps; A.foot_force = out_foot_force;
+  A.ext_wrench = ext_wrench;
   const int n_cta = (N + kRolloutsPerCta - 1) / kRolloutsPerCta;
   sim_step_kernel<<<n_cta, kThreads, 0, (cudaStream_t)cuda_stream>>>(A);
   return check_launch("sim_step_kernel");

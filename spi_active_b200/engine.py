@@ -289,8 +289,10 @@ class RolloutEngine:
 
     # ---- stepwise boundary ------------------------------------------------------------------
     def sim_step(self, state: torch.Tensor, torques: torch.Tensor, n_steps: int = 1, params=None, param_names=(),
-                 flags: int = 0, foot_force: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Advance state[N,37] IN PLACE by n_steps physics steps under constant torques[N,12]."""
+                 flags: int = 0, foot_force: Optional[torch.Tensor] = None,
+                 ext_wrench: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Advance state[N,37] IN PLACE by n_steps physics steps under constant torques[N,12].  ext_wrench[N,13,6]: external
+        [torque; force] on the 13 moving bodies in their link frames (spi_b200_sim_step_ext)."""
         assert state.is_cuda and state.dtype == torch.float32 and state.is_contiguous()
         torques = self._f32(torques)
         N = state.shape[0]
@@ -301,10 +303,12 @@ class RolloutEngine:
             P = params.shape[1]
             ids = _ids(param_names)
         with torch.cuda.device(self.device):
-            rc = self.lib.spi_b200_sim_step(self._handle, _ptr(params), P, ids.ctypes.data_as(C.POINTER(C.c_int)),
-                                            int(flags), _ptr(state), _ptr(torques), N, int(n_steps), _ptr(foot_force),
-                                            self._stream())
-        _lib.check(rc, "spi_b200_sim_step")
+            if ext_wrench is not None:
+                ext_wrench = self._f32(ext_wrench).reshape(N, 13, 6).contiguous()
+            rc = self.lib.spi_b200_sim_step_ext(self._handle, _ptr(params), P, ids.ctypes.data_as(C.POINTER(C.c_int)),
+                                                int(flags), _ptr(state), _ptr(torques), _ptr(ext_wrench), N, int(n_steps),
+                                                _ptr(foot_force), self._stream())
+        _lib.check(rc, "spi_b200_sim_step_ext")
         return state
 
     def body_states(self, state: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

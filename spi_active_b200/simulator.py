@@ -62,6 +62,12 @@ PARAMS_DICT_KEYS = {"mass": "mass", "comx": "comx", "comy": "comy", "comz": "com
                     "inertiay": "inertiay", "inertiaiy": "inertiay", "inertiaz": "inertiaz"}
 
 
+# the 19 Isaac Gym bodies (gm.BODY_NAMES order) -> the 13 moving bodies of the engine (base, then hip / thigh / calf of FL,
+# FR, RL, RR): feet are rigidly attached to their calf, Head_upper / Head_lower to the base
+MOVING_BODY_OF_ISAAC_BODY = [0, 1, 2, 3, 3, 4, 5, 6, 6, 0, 0, 7, 8, 9, 9, 10, 11, 12, 12]
+ISAAC_BODY_OF_MOVING_BODY = [0, 1, 2, 3, 5, 6, 7, 11, 12, 13, 15, 16, 17]
+
+
 class _RigidBodyProps:
     """The fields of gymapi.RigidBodyProperties the reference touches (mass, com, inertia)."""
 
@@ -136,6 +142,15 @@ class B200Sim(BaseSimulator):
         self.simulator_config = _get(config, "simulator.config")
         self.robot_config = _get(config, "robot")
         self.model = model or gm.go2_nominal()
+        # config/simulator/b200.yaml `b200.contact`: the engine's compliant foot-contact constants; they are part of the model
+        # blob the engine is created with (setup()), so they must be applied before that
+        contact_cfg = _get(config, "simulator.config.b200.contact")
+        if contact_cfg is not None:
+            cp = self.model.contact
+            for key, cast in (("kn", float), ("cn", float), ("mu", float), ("dt", float), ("veps", float), ("nsub", int)):
+                v = _get(contact_cfg, key)
+                if v is not None:
+                    setattr(cp, key, cast(v))
         self._backend = backend
         self.inertia_keep = bool(_get(config, "simulator.config.b200.inertia_keep", False))
         self.strict_inertiay = bool(_get(config, "simulator.config.b200.strict_inertiay", False))
@@ -238,6 +253,7 @@ class B200Sim(BaseSimulator):
             self._state[:, 6] = 1.0
         self._state[:, 13:25] = torch.tensor(self.model.q_default, dtype=torch.float32, device=dev)
         self._torques = z(N, 12)
+        self._ext_wrench = None
         self._foot_force = z(N, 4, 3)
         self.all_root_states = z(N, 13)
         self.robot_root_states = self.all_root_states            # one actor per env (isaacgym.py:567-571)
@@ -292,7 +308,31 @@ class B200Sim(BaseSimulator):
             self.dof_state.view(self.num_envs, 12, 2)[ids] = ds[ids].to(torch.float32)
 
     def apply_rigid_body_force_at_pos_tensor(self, force_tensor, pos_tensor):
-        raise NotImplementedError("external pushes are domain randomisation (out of scope of the replay path)")
+        """isaacgym.py:609-613: forces [N,19,3] on the 19 Isaac Gym bodies at positions [N,19,3] in ENV_SPACE (world axes,
+        relative to the env origin), consumed by the NEXT physics step.  Converted here to one [torque; force] wrench per
+        moving body in its own link frame (feet act on their calf, the head links on the base) for spi_b200_sim_step_ext."""
+        N, dev = self.num_envs, self._state.device
+        f = torch.as_tensor(force_tensor, dtype=torch.float32, device=dev).reshape(N, 19, 3)
+        p = torch.as_tensor(pos_tensor, dtype=torch.float32, device=dev).reshape(N, 19, 3)
+        if self.env_origins is not None:
+            p = p + torch.as_tensor(self.env_origins, dtype=torch.float32, device=dev).reshape(N, 1, 3)
+        if hasattr(self._backend, "body_states"):
+            self._backend.body_states(self._state, out=self._rigid_body_state)       # poses of the CURRENT state
+        else:
+            raise NotImplementedError("external forces need a backend with body_states")
+        mb = torch.tensor(MOVING_BODY_OF_ISAAC_BODY, device=dev)
+        own = torch.tensor(ISAAC_BODY_OF_MOVING_BODY, device=dev)
+        origin = self._rigid_body_state[:, own, 0:3]                                  # [N,13,3]
+        quat = self._rigid_body_state[:, own, 3:7]                                    # [N,13,4] xyzw, body -> world
+        torque_w = torch.cross(p - origin[:, mb], f, dim=-1)                          # about the moving body's link origin
+        fw = torch.zeros(N, 13, 3, device=dev).index_add_(1, mb, f)
+        tw = torch.zeros(N, 13, 3, device=dev).index_add_(1, mb, torque_w)
+
+        def to_body(v):                                                               # R^T v for unit quaternions
+            u, w = quat[..., :3], quat[..., 3:4]
+            t = 2.0 * torch.cross(u, v, dim=-1)
+            return v - w * t + torch.cross(u, t, dim=-1)
+        self._ext_wrench = torch.cat([to_body(tw), to_body(fw)], dim=-1).contiguous()
 
     def simulate_at_each_physics_step(self):
         """Advance ONE physics step (sim_dt) under the applied torques, refresh dof_state only
@@ -300,8 +340,11 @@ class B200Sim(BaseSimulator):
         if self._params_dirty:
             self._upload_params()
         flags = gm.FLAG_INERTIA_KEEP   # the per-env rows already carry the final inertia tensor: never rescale it
+        kw = {}
+        if self._ext_wrench is not None:          # consumed by this step only, like Isaac Gym's force tensors
+            kw["ext_wrench"], self._ext_wrench = self._ext_wrench, None
         self._backend.sim_step(self._state, self._torques, 1, params=self._params, param_names=self.PARAM_NAMES,
-                               flags=flags, foot_force=self._foot_force)
+                               flags=flags, foot_force=self._foot_force, **kw)
         self._refresh_dof()
 
     # ----- viewer ---------------------------------------------------------------------------------------------------

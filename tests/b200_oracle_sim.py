@@ -11,12 +11,12 @@ class OracleBackend:
     def __init__(self, blob):
         self.blob = blob
 
-    def sim_step(self, state, torques, n_steps=1, params=None, param_names=(), flags=0, foot_force=None):
+    def sim_step(self, state, torques, n_steps=1, params=None, param_names=(), flags=0, foot_force=None, ext_wrench=None):
         from oracle import oracle as orc
         ids = [gm.PARAM_IDS[n] for n in param_names]
         new, ff = orc.sim_step(self.blob, state.numpy().astype(np.float64), torques.numpy().astype(np.float64), n_steps,
                                params=None if params is None else params.numpy(), param_ids=ids, flags=flags,
-                               return_foot_force=True)
+                               return_foot_force=True, ext_wrench=None if ext_wrench is None else ext_wrench.numpy())
         state.copy_(torch.from_numpy(new.astype(np.float32)))
         if foot_force is not None:
             foot_force.copy_(torch.from_numpy(ff.astype(np.float32)))

@@ -20,12 +20,12 @@ class OracleBackend:
     def __init__(self, blob):
         self.blob = blob
 
-    def sim_step(self, state, torques, n_steps=1, params=None, param_names=(), flags=0, foot_force=None):
+    def sim_step(self, state, torques, n_steps=1, params=None, param_names=(), flags=0, foot_force=None, ext_wrench=None):
         from oracle import oracle as orc
         ids = [gm.PARAM_IDS[n] for n in param_names]
         new, ff = orc.sim_step(self.blob, state.numpy().astype(np.float64), torques.numpy().astype(np.float64), n_steps,
                                params=None if params is None else params.numpy(), param_ids=ids, flags=flags,
-                               return_foot_force=True)
+                               return_foot_force=True, ext_wrench=None if ext_wrench is None else ext_wrench.numpy())
         state.copy_(torch.from_numpy(new.astype(np.float32)))
         if foot_force is not None:
             foot_force.copy_(torch.from_numpy(ff.astype(np.float32)))
@@ -129,6 +129,23 @@ def test_plugin_surface_and_limits(blob, nominal_model):
         bad = B200Sim(config=_config(1), device="cpu", backend=OracleBackend(blob)); bad.robot_config.dof_names[0] = "x"; bad.load_assets()
 
 
+def test_contact_block_of_the_yaml_reaches_the_model(blob):
+    """config/simulator/b200.yaml `b200.contact.*` -> ContactParams of the model the engine is built from."""
+    cfg = _config(2)
+    cfg.simulator.config.b200 = SimpleNamespace(inertia_keep=True, strict_inertiay=False,
+                                                contact=SimpleNamespace(kn=12345.0, cn=0.25, mu=0.8, dt=20.0, nsub=4))
+    sim = B200Sim(config=cfg, device="cpu", backend=OracleBackend(blob))
+    c = sim.model.contact
+    assert (c.kn, c.cn, c.mu, c.dt, c.nsub) == (12345.0, 0.25, 0.8, 20.0, 4) and sim.inertia_keep
+    b = gm.build_model_blob(sim.model)
+    assert b[gm.BLOB["CONTACT_KN"]] == np.float32(12345.0) and b[gm.BLOB["NSUB"]] == 4.0
+    import yaml
+    from pathlib import Path
+    y = yaml.safe_load((Path(__file__).resolve().parent.parent / "config" / "simulator" / "b200.yaml").read_text())
+    d = gm.ContactParams()                      # the shipped yaml states the defaults
+    assert y["simulator"]["config"]["b200"]["contact"] == dict(kn=d.kn, cn=d.cn, mu=d.mu, dt=d.dt, nsub=d.nsub)
+
+
 def test_params_dict_overrides(blob):
     """isaacgym_active_sysid.py:39-94: per-env values; `inertiaiy` (sic) accepted; strict flag drops inertiay."""
     pd = {"mass": {"body_name": "base", "value": [9.39, 9.49]}, "comx": {"body_name": "base", "value": [0.0, 0.1]},
@@ -227,3 +244,84 @@ def test_body_states_kernel_matches_oracle(engine, oracle_lib, blob, nominal_mod
     assert (sign > 0).all()                                         # same hemisphere: composed, not re-extracted
     np.testing.assert_allclose(out[..., 3:7], ref[..., 3:7], atol=2e-6)
     np.testing.assert_allclose(out[..., 7:13], ref[..., 7:13], atol=2e-5)
+
+
+# ---- external forces: IsaacGym.apply_rigid_body_force_at_pos_tensor (isaacgym.py:609-613) ----------------------------------
+def _free_flight_sim(num_envs, device, backend, seed=3, vel_scale=1.0):
+    from test_oracle_physics import _rand_state
+    sim, _ = _make_sim(num_envs, device, backend)
+    rng = np.random.default_rng(seed)
+    m = gm.go2_nominal()
+    st = np.stack([_rand_state(rng, m, height=5.0) for _ in range(num_envs)]).astype(np.float32)
+    st[:, 7:13] *= vel_scale; st[:, 25:37] *= vel_scale
+    sim._state.copy_(torch.from_numpy(st).to(sim._state.device))
+    sim.refresh_sim_tensors()
+    return sim, st
+
+
+def test_external_force_changes_momentum_by_the_impulse(blob, nominal_model):
+    """A world-frame force F at a world point p on any of the 19 Isaac bodies, for one physics step: total linear momentum
+    changes by F dt and angular momentum about the world origin by (p x F) dt relative to the unforced step (free flight, zero
+    joint torques) — independent of which body carries it, which the [torque; force]-per-moving-body conversion must preserve."""
+    from test_oracle_physics import _momentum
+    dt = nominal_model.dt
+    cases = [("base", [30.0, -20.0, 50.0]), ("RL_thigh", [0.0, 40.0, 10.0]), ("FR_foot", [15.0, 5.0, 60.0]),
+             ("Head_lower", [-25.0, 0.0, 5.0]), ("FL_calf", [10.0, -30.0, 0.0])]
+    N = len(cases)
+    # slow states: the wrench is held in the BODY frame over the step's two sub-steps, so a body turning at w rad/s sees the
+    # force direction drift by w * dt / 2 (1 - 2 % for a swinging calf); at 0.1x the rates the mapping itself is checked tightly
+    ref, st0 = _free_flight_sim(N, "cpu", OracleBackend(blob), vel_scale=0.1)
+    ref.apply_torques_at_dof(torch.zeros(N, 12)); ref.simulate_at_each_physics_step()
+    sim, _ = _free_flight_sim(N, "cpu", OracleBackend(blob), vel_scale=0.1)
+    force, pos = torch.zeros(N, 19, 3), torch.zeros(N, 19, 3)
+    for e, (name, F) in enumerate(cases):
+        b = sim.find_rigid_body_indice(name)
+        force[e, b] = torch.tensor(F)
+        pos[e, b] = sim._rigid_body_pos[e, b] + torch.tensor([0.03, -0.02, 0.05])      # off the link origin: a torque arm
+    sim.apply_torques_at_dof(torch.zeros(N, 12))
+    sim.apply_rigid_body_force_at_pos_tensor(force, pos)
+    sim.simulate_at_each_physics_step()
+    for e, (name, F) in enumerate(cases):
+        b = sim.find_rigid_body_indice(name)
+        P1, L1, _ = _momentum(nominal_model, sim._state[e].numpy().astype(np.float64))
+        P0, L0, _ = _momentum(nominal_model, ref._state[e].numpy().astype(np.float64))
+        F = np.asarray(F, np.float64)
+        # (a 60 N push on a free 0.2 kg calf spins it up to ~8 rad/s within the first sub-step, so even from rest the held
+        # body-frame direction drifts by ~1 % in the second one: tolerance 2 % of the impulse)
+        np.testing.assert_allclose(P1 - P0, F * dt, rtol=2e-2, atol=5e-3, err_msg=name)
+        np.testing.assert_allclose(L1 - L0, np.cross(pos[e, b].numpy().astype(np.float64), F) * dt, rtol=2e-2, atol=2e-2,
+                                   err_msg=name)
+    # the force is consumed by that step: the next one is unforced again
+    a = sim._state.clone(); sim.simulate_at_each_physics_step()
+    r = ref._state.clone(); ref._state.copy_(a); ref.simulate_at_each_physics_step()
+    np.testing.assert_allclose(sim._state.numpy(), ref._state.numpy(), atol=1e-6)
+    assert not np.allclose(a.numpy(), r.numpy(), atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_external_force_kernel_matches_oracle(engine, oracle_lib, blob, nominal_model):
+    """spi_b200_sim_step_ext against the oracle for random wrenches on all 13 moving bodies, and the plugin's conversion of
+    world (force, position) pairs on the GPU against the same plugin on the oracle backend."""
+    N = 33
+    rng = np.random.default_rng(8)
+    cpu, st0 = _free_flight_sim(N, "cpu", OracleBackend(blob), seed=5)
+    gpu, _ = _free_flight_sim(N, str(engine.device), None, seed=5)
+    ext = (rng.standard_normal((N, 13, 6)) * np.array([2, 2, 2, 30, 30, 30])).astype(np.float32)
+    tau = rng.uniform(-5, 5, (N, 12)).astype(np.float32)
+    s = torch.from_numpy(st0.copy()).to(engine.device)
+    engine.sim_step(s, torch.from_numpy(tau), 3, ext_wrench=torch.from_numpy(ext))
+    ref = oracle_lib.sim_step(blob, st0.astype(np.float64), tau.astype(np.float64), 3, ext_wrench=ext)
+    np.testing.assert_allclose(s.cpu().numpy()[:, :7], ref[:, :7], atol=2e-5)
+    np.testing.assert_allclose(s.cpu().numpy()[:, 13:25], ref[:, 13:25], atol=2e-5)
+    np.testing.assert_allclose(s.cpu().numpy()[:, 7:13], ref[:, 7:13], atol=1e-3)
+    np.testing.assert_allclose(s.cpu().numpy()[:, 25:37], ref[:, 25:37], atol=5e-3)
+    force = torch.from_numpy(rng.standard_normal((N, 19, 3)).astype(np.float32) * 20)
+    pos = cpu._rigid_body_pos.clone() + 0.05 * torch.from_numpy(rng.standard_normal((N, 19, 3)).astype(np.float32))
+    for sim in (cpu, gpu):
+        dev = sim._state.device
+        sim.apply_torques_at_dof(torch.from_numpy(tau).to(dev))
+        sim.apply_rigid_body_force_at_pos_tensor(force.to(dev), pos.to(dev))
+        sim.simulate_at_each_physics_step()
+    np.testing.assert_allclose(gpu._state.cpu().numpy()[:, :7], cpu._state.numpy()[:, :7], atol=2e-5)
+    np.testing.assert_allclose(gpu._state.cpu().numpy()[:, 13:25], cpu._state.numpy()[:, 13:25], atol=2e-5)
+    np.testing.assert_allclose(gpu._state.cpu().numpy()[:, 7:13], cpu._state.numpy()[:, 7:13], atol=1e-3)

@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_r2_n2.json 2> gpurun_out/bench_r2_n2.err; echo rc=$?
+cat gpurun_out/bench_r2_n2.json; tail -5 gpurun_out/bench_r2_n2.err
