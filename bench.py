@@ -561,20 +561,31 @@ def run_extras(eng, segs, cfg, S, rank, world, barrier, max_over_ranks):
                                          one.gait_indices, one.clock, None, None, None, one.hist, one.live_hist,
                                          one.dead_steps, one.schedule, one.counter, one.ctrl, one.dt, acfg.action_clip,
                                          act.CLIP_OBSERVATIONS, act.TERMINATION_GRAVITY, one.model.q_default,
-                                         obs_hi=one.obs_hi, obs_lo=one.obs_lo, ring_slots=act.RING_SLOTS)
+                                         obs_hi=one.obs_hi, obs_lo=one.obs_lo, ring_slots=act.RING_SLOTS,
+                                         fim_jtj=one.jtj if one.fim_mode == "fused" else None,
+                                         fim_trace=one.trace_acc if one.fim_mode == "fused" else None,
+                                         fim_delta=float(acfg.delta_param))
             ev[3].record()
             torch.cuda.synchronize()
             if k >= 3:
                 acc += [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+        # the alternative Fisher path (fim_mode="tensor"): tcgen05 contraction of a 64-step history of the same shape
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        one.backend.fim_contract(one.hist, float(acfg.delta_param), live=one.live_hist)
+        hist64 = torch.randn(64, M, one.param_dim + 1, 25, device=dev)
+        live64 = torch.ones(64, M, dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            one.backend.fim_contract(hist64, float(acfg.delta_param), live=live64)
         e0.record()
-        one.backend.fim_contract(one.hist, float(acfg.delta_param), live=one.live_hist)
+        for _ in range(10):
+            one.backend.fim_contract(hist64, float(acfg.delta_param), live=live64)
         e1.record(); torch.cuda.synchronize()
+        fim_ms = e0.elapsed_time(e1) / 10
         flops = 2.0 * 3 * one.num_envs * sum(a * b for a, b in zip((928, 512, 256), (512, 256, 128)))
         rec["step_kernels_ms"] = {"actor_mlp": acc[0] / n_rep, "physics_env_step": acc[1] / n_rep,
                                   "post_step": acc[2] / n_rep,
-                                  "fim_contract_per_%d_steps" % one.hist.shape[0]: e0.elapsed_time(e1),
+                                  "fisher": "fused into post_step (fim_mode=%s)" % one.fim_mode,
+                                  "fim_contract_tcgen05_per_64_steps": fim_ms,
+                                  "fim_contract_tcgen05_gbs": hist64.numel() * 4 / (fim_ms * 1e-3) / 1e9,
                                   "actor_issued_f16_tflops": flops / (acc[0] / n_rep * 1e-3) / 1e12,
                                   "note": "eager single-stream launches incl. launch gaps; inside the captured, 3-way pipelined "
                                           "rollout the kernels overlap"}

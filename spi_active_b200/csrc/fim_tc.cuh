@@ -11,7 +11,7 @@
 // Mapping (sm_100a): one CTA = 8 consecutive main envs x 16 parameter slots = 128 rows (UMMA M = N = 128).
 //   * producer (all 128 threads, thread = row): load the recorded states of 2 control steps, form the finite
 //     differences, split every fp32 value into tf32 hi + lo (3xTF32: fp32-accurate products) and store both tiles
-//     in shared memory in the canonical K-major no-swizzle UMMA layout (8 x 16 B core matrices);
+//     in shared memory in the K-major SWIZZLE_128B UMMA layout (a row = 32 tf32 = one 128-byte swizzle atom);
 //   * one elected thread issues tcgen05.mma.kind::tf32 (hi*hi, hi*lo, lo*hi) accumulating the 128 x 128 fp32 tile
 //     in tensor memory; the same shared-memory tile is both the A and the B operand;  tcgen05.commit -> mbarrier
 //     releases the stage back to the producers (2 stages: production of block k+1 overlaps the MMAs of block k);
@@ -20,8 +20,10 @@
 //     its diagonal 16 x 16 blocks (the only env-diagonal part of A A^T) are read back with tcgen05.ld and added to a
 //     running sum in fp32 registers with round-to-nearest (the "promotion" trick of FP8 GEMMs);
 //   * epilogue: running sums -> out_JtJ, trace by shuffles.
-// The off-diagonal env blocks of the 128 x 128 tile are computed and dropped: UMMA has no M = 16 shape, and the
-// whole contraction is ~1 ms against a ~1 s rollout, so the tile is sized for simplicity, not utilisation.
+// The off-diagonal env blocks of the 128 x 128 tile are computed and dropped: UMMA has no M = 16 shape; the kernel is bound by
+// the producer (global loads + difference / split / tile stores), not by the tensor pipe.
+// r2 (profiles/README.md): one step per stage (64 KB of tiles -> 2 CTAs per SM), the steps cut into gridDim.y slices so that a
+// 64-step chunk still fills the GPU, coalesced cooperative loads through a staging buffer with a one-step register prefetch.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -33,27 +35,36 @@ constexpr int kEnvsPerCta = 8;
 constexpr int kSlots = 16;            // parameter slots per env (P <= 16)
 constexpr int kStateDim = 25;         // root13 + q12
 constexpr int kKPerStep = 32;         // 25 padded to a multiple of the tf32 UMMA K (8)
-constexpr int kStepsPerStage = 2;
-constexpr int kKPerStage = kKPerStep * kStepsPerStage;      // 64 floats per row per stage
-constexpr int kChunksPerStage = kKPerStage / 4;             // 16-byte chunks along K
-constexpr int kChunkStride = (kRows / 8) * 128;             // bytes between K-adjacent core matrices (LBO) = 2048
-constexpr int kGroupStride = 128;                           // bytes between 8-row groups (SBO)
-constexpr int kTileBytes = kChunksPerStage * kChunkStride;  // 32 KB
+constexpr int kStepsPerStage = 1;     // r2: one control step per stage -> 2 x 2 x 16 KB of tiles per CTA -> 2 CTAs per SM (TMEM-limited)
+constexpr int kKPerStage = kKPerStep * kStepsPerStage;      // 32 floats = 128 bytes per row per stage = ONE 128-byte swizzle atom
+constexpr int kChunksPerStage = kKPerStage / 4;             // 16-byte chunks along K (8)
+constexpr int kGroupStride = 1024;                          // bytes between 8-row groups (SBO): 8 rows x 128 bytes
+constexpr int kTileBytes = kRows * kKPerStage * 4;          // 16 KB
+static_assert(kKPerStage * 4 == 128, "a tile row must be exactly one 128-byte swizzle atom");
 constexpr int kStages = 2;
-constexpr int kSmemBytes = kStages * 2 * kTileBytes + 64;   // hi + lo per stage, + barriers / tmem slot
+constexpr int kRawStride = (kSlots + 1) * kStateDim + 3;    // floats per env of the raw staging buffer (odd stride: the 16
+                                                            // lanes of an env and the 2 envs of a warp spread over the banks)
+constexpr int kRawBytes = kEnvsPerCta * kRawStride * 4;
+constexpr int kMaxLoads = ((kSlots + 1) * kStateDim + 15) / 16;   // global loads per thread and step (27 at P = 16, 18 at P = 10)
+constexpr int kSmemBytes = kStages * 2 * kTileBytes + kRawBytes + 64;   // hi + lo per stage, raw rows, barriers / tmem slot
 constexpr int kTmemCols = 2 * kRows;   // one 128-column fp32 accumulator per stage
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (between K-adjacent core matrices)
-//   [32,46) stride byte offset >> 4 (between 8-row groups) | [46,48) version = 1 | [61,64) layout type = 0
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout; same layout as mlp_tc.cuh):
+//   [0,14) start address >> 4 | [16,30) leading byte offset field = 1 (unused: one swizzle atom spans the tile's K extent)
+//   [32,46) stride byte offset >> 4 = 1024 >> 4 between 8-row groups | [46,48) version = 1 | [61,64) layout type = 2
+// A row is 128 bytes (32 tf32 of K); the 16-byte chunk c of row r sits at chunk position c ^ (r & 7); a k-step of 8 tf32
+// advances the start address by 32 bytes inside the atom.  r1 used the SWIZZLE_NONE canonical layout, whose 128 x 128 x 8 MMA
+// takes ~256 cycles instead of ~65 (measured on the actor MLP, profiles/README.md r1_c) — 12 such MMAs per control step
+// (~3 000 cycles) were what bounded this kernel, not its loads.
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
   uint64_t d = 0;
   d |= (uint64_t)((addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((kChunkStride >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)1 << 16;
   d |= (uint64_t)((kGroupStride >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
   return d;
 }
 
@@ -106,12 +117,18 @@ struct FimArgs {
   int accumulate;
   float* out_JtJ;               // [M][P][P] or null
   float* out_trace;             // [M] or null
+  // r2: the T control steps are cut into gridDim.y slices so that a 64-step chunk of 1 024 envs (128 env tiles) still fills
+  // 148 SMs x 2 CTAs.  n_split > 1: slice y writes its partial sums to part_JtJ [n_split][M][P][P] / part_trace [n_split][M]
+  // and fim_reduce_kernel adds the slices in a fixed order (deterministic) into out_*.
+  int n_split;
+  float* part_JtJ; float* part_trace;
 };
 
-__global__ void __launch_bounds__(kRows, 1) fim_contract_kernel(const FimArgs A) {
+__global__ void __launch_bounds__(kRows, 2) fim_contract_kernel(const FimArgs A) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* tiles = smem;                                         // [stage][hi, lo][kTileBytes]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * 2 * kTileBytes);   // [kStages]
+  float* raw = reinterpret_cast<float*>(smem + kStages * 2 * kTileBytes);          // [8 envs][kRawStride] rows of one step
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * 2 * kTileBytes + kRawBytes);   // [kStages]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kStages);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -132,10 +149,16 @@ __global__ void __launch_bounds__(kRows, 1) fim_contract_kernel(const FimArgs A)
   const int e = tid >> 4, p = tid & 15;
   const int m = blockIdx.x * kEnvsPerCta + e;
   const bool row_valid = (m < A.M) && (p < A.P);
-  const size_t step_stride = (size_t)A.M * (A.P + 1) * kStateDim;
-  const float* env_base = A.hist + (size_t)(m < A.M ? m : 0) * (A.P + 1) * kStateDim;
-  // byte offset of this row inside a 16-byte K chunk column of a tile
-  const uint32_t row_off = (uint32_t)(tid >> 3) * kGroupStride + (uint32_t)(tid & 7) * 16;
+  const int env_floats = (A.P + 1) * kStateDim;                        // contiguous floats of one env and step
+  const size_t step_stride = (size_t)A.M * env_floats;
+  const float* env_base = A.hist + (size_t)(m < A.M ? m : 0) * env_floats;
+  float* raw_env = raw + e * kRawStride;
+  // byte offset of this row in a tile, and its swizzle phase: chunk c of the row goes to chunk position c ^ (row & 7)
+  const uint32_t row_off = (uint32_t)(tid >> 3) * kGroupStride + (uint32_t)(tid & 7) * 128;
+  const uint32_t row_xor = (uint32_t)(tid & 7);
+  // this CTA's slice of the control steps
+  const int per = (A.T + A.n_split - 1) / A.n_split;
+  const int t_begin = blockIdx.y * per, t_end = min(A.T, t_begin + per);
 
   // running fp32 sums of this thread's row: columns 32 * warp .. 32 * warp + 31 of the 128 x 128 tile
   float acc[32];
@@ -162,40 +185,61 @@ __global__ void __launch_bounds__(kRows, 1) fim_contract_kernel(const FimArgs A)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // the loads precede the MMAs that recycle the accumulator
   };
 
-  const int n_blocks = (A.T + kStepsPerStage - 1) / kStepsPerStage;
+  // Producer, r2: the (P + 1) x 25 floats of an env and step are CONTIGUOUS in the history, so the 16 threads of an env fetch
+  // them as coalesced 64-byte segments (18 loads per thread at P = 10 instead of 50 scalar loads of two 100-byte rows each),
+  // one step ahead of their use (software prefetch into registers), park them in shared memory and form the differences
+  // from there.  The 16 threads of an env sit in one warp: __syncwarp orders the staging buffer.
+  float pre[kMaxLoads];
+  unsigned char pre_live = 1;
+  auto prefetch = [&](int t) {
+    const bool on = (m < A.M) && (t < t_end);
+    pre_live = (on && A.live) ? A.live[(size_t)t * A.M + m] : (unsigned char)1;
+    const float* src = env_base + (size_t)t * step_stride;
+#pragma unroll
+    for (int k = 0; k < kMaxLoads; k++) {
+      const int idx = p + 16 * k;
+      pre[k] = (on && idx < env_floats) ? __ldg(src + idx) : 0.f;
+    }
+  };
+  prefetch(t_begin);
+  const int n_blocks = t_end - t_begin;
   for (int kb = 0; kb < n_blocks; kb++) {
     const int s = kb & 1;
-    if (kb >= kStages) flush(kb - kStages);   // also guarantees the MMAs that read this stage's tiles are done
+    const int t = t_begin + kb;
+    __syncwarp();                                  // the previous step's reads of the staging rows are done
+#pragma unroll
+    for (int k = 0; k < kMaxLoads; k++) {
+      const int idx = p + 16 * k;
+      if (idx < env_floats) raw_env[idx] = pre[k];
+    }
+    const bool live_now = pre_live != 0;           // fetched one step ahead too: a dependent global load per step was exposed
+    prefetch(t + 1);                               // in flight during the conversion below
+    __syncwarp();
+    if (kb >= kStages) flush(kb - kStages);        // also guarantees the MMAs that read this stage's tiles are done
     unsigned char* hi_tile = tiles + (size_t)(s * 2) * kTileBytes;
     unsigned char* lo_tile = hi_tile + kTileBytes;
+    const bool on = row_valid && live_now;
+    float j[kKPerStep];
+    if (on) {
+      const float* auxp = raw_env + (p + 1) * kStateDim;
 #pragma unroll
-    for (int ts = 0; ts < kStepsPerStage; ts++) {
-      const int t = kb * kStepsPerStage + ts;
-      bool on = row_valid && (t < A.T);
-      if (on && A.live) on = A.live[(size_t)t * A.M + m] != 0;
-      float j[kKPerStep];
-      if (on) {
-        const float* mainp = env_base + (size_t)t * step_stride;
-        const float* auxp = mainp + (size_t)(p + 1) * kStateDim;
+      for (int d = 0; d < kStateDim; d++) j[d] = (raw_env[d] - auxp[d]) * A.inv_delta;
+    } else {
 #pragma unroll
-        for (int d = 0; d < kStateDim; d++) j[d] = (__ldg(mainp + d) - __ldg(auxp + d)) * A.inv_delta;
-      } else {
+      for (int d = 0; d < kStateDim; d++) j[d] = 0.f;
+    }
 #pragma unroll
-        for (int d = 0; d < kStateDim; d++) j[d] = 0.f;
-      }
+    for (int d = kStateDim; d < kKPerStep; d++) j[d] = 0.f;
 #pragma unroll
-      for (int d = kStateDim; d < kKPerStep; d++) j[d] = 0.f;
-#pragma unroll
-      for (int c = 0; c < kKPerStep / 4; c++) {
-        float4 h, l;
-        h.x = tf32_round(j[4 * c + 0]); l.x = j[4 * c + 0] - h.x;
-        h.y = tf32_round(j[4 * c + 1]); l.y = j[4 * c + 1] - h.y;
-        h.z = tf32_round(j[4 * c + 2]); l.z = j[4 * c + 2] - h.z;
-        h.w = tf32_round(j[4 * c + 3]); l.w = j[4 * c + 3] - h.w;
-        const uint32_t off = (uint32_t)(ts * (kKPerStep / 4) + c) * kChunkStride + row_off;
-        *reinterpret_cast<float4*>(hi_tile + off) = h;
-        *reinterpret_cast<float4*>(lo_tile + off) = l;
-      }
+    for (int c = 0; c < kKPerStep / 4; c++) {
+      float4 h, l;
+      h.x = tf32_round(j[4 * c + 0]); l.x = j[4 * c + 0] - h.x;
+      h.y = tf32_round(j[4 * c + 1]); l.y = j[4 * c + 1] - h.y;
+      h.z = tf32_round(j[4 * c + 2]); l.z = j[4 * c + 2] - h.z;
+      h.w = tf32_round(j[4 * c + 3]); l.w = j[4 * c + 3] - h.w;
+      const uint32_t off = row_off + (((uint32_t)c ^ row_xor) << 4);
+      *reinterpret_cast<float4*>(hi_tile + off) = h;
+      *reinterpret_cast<float4*>(lo_tile + off) = l;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the UMMA reads
     __syncthreads();
@@ -205,15 +249,15 @@ __global__ void __launch_bounds__(kRows, 1) fim_contract_kernel(const FimArgs A)
       const uint32_t tacc = tmem_d + (uint32_t)(s * kRows);
       // small cross terms first, then the hi * hi products: fewer truncated additions at full magnitude
 #pragma unroll
-      for (int k = 0; k < kKPerStage / 8; k++) {
-        const uint64_t dh = make_desc(hi_addr + (uint32_t)k * 2 * kChunkStride);
-        const uint64_t dl = make_desc(lo_addr + (uint32_t)k * 2 * kChunkStride);
+      for (int k = 0; k < kKPerStage / 8; k++) {     // a k-step of 8 tf32 = 32 bytes inside the swizzle atom
+        const uint64_t dh = make_desc(hi_addr + (uint32_t)k * 32);
+        const uint64_t dl = make_desc(lo_addr + (uint32_t)k * 32);
         mma_tf32(tacc, dh, dl, k > 0 ? 1u : 0u);
         mma_tf32(tacc, dl, dh, 1u);
       }
 #pragma unroll
       for (int k = 0; k < kKPerStage / 8; k++) {
-        const uint64_t dh = make_desc(hi_addr + (uint32_t)k * 2 * kChunkStride);
+        const uint64_t dh = make_desc(hi_addr + (uint32_t)k * 32);
         mma_tf32(tacc, dh, dh, 1u);
       }
       umma_commit(smem_u32(bars + s));
@@ -222,24 +266,37 @@ __global__ void __launch_bounds__(kRows, 1) fim_contract_kernel(const FimArgs A)
   for (int kb2 = (n_blocks > kStages ? n_blocks - kStages : 0); kb2 < n_blocks; kb2++) flush(kb2);
 
   const bool upper = (lane >> 4) != 0;
+  const bool split = A.n_split > 1;
+  float* dst_jtj = split ? A.part_JtJ + (size_t)blockIdx.y * A.M * A.P * A.P : A.out_JtJ;
+  float* dst_trace = split ? A.part_trace + (size_t)blockIdx.y * A.M : A.out_trace;
+  const bool accumulate = !split && A.accumulate;
   float diag = 0.f;
 #pragma unroll
   for (int q = 0; q < kSlots; q++) {
     const float v = upper ? acc[16 + q] : acc[q];
     if (q == p) diag = v;
-    if (row_valid && q < A.P && A.out_JtJ) {
-      float* o = A.out_JtJ + ((size_t)m * A.P + p) * A.P + q;
-      *o = A.accumulate ? (*o + v) : v;
+    if (row_valid && q < A.P && dst_jtj) {
+      float* o = dst_jtj + ((size_t)m * A.P + p) * A.P + q;
+      *o = accumulate ? (*o + v) : v;
     }
   }
   if (!row_valid) diag = 0.f;
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) diag += __shfl_xor_sync(0xffffffffu, diag, o);   // sum over the env's 16 slots
-  if (p == 0 && m < A.M && A.out_trace) A.out_trace[m] = A.accumulate ? (A.out_trace[m] + diag) : diag;
+  if (p == 0 && m < A.M && dst_trace) dst_trace[m] = accumulate ? (dst_trace[m] + diag) : diag;
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+}
+
+// slices of the control steps -> out (fixed order: deterministic), n = M P P (JtJ) or M (trace)
+__global__ void fim_reduce_kernel(const float* part, int n_split, size_t n, int accumulate, float* out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = accumulate ? out[i] : 0.f;
+  for (int s = 0; s < n_split; s++) v += part[(size_t)s * n + i];
+  out[i] = v;
 }
 
 }  // namespace fimtc

@@ -9,6 +9,8 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "aba_leg.cuh"
@@ -556,6 +558,11 @@ struct spi_b200_model {
   float* d_partial = nullptr; size_t partial_cap = 0;
   int* d_bad = nullptr; size_t bad_cap = 0;
   int* d_rank = nullptr; size_t rank_cap = 0;
+  // partial sums of the step slices of spi_b200_fim_contract, one buffer PER STREAM: pipelined explorers contract on their own
+  // streams through the same handle, and a shared buffer would race
+  struct FimPart { float* ptr = nullptr; size_t cap = 0; };
+  std::map<cudaStream_t, FimPart> fim_part;
+  std::mutex fim_part_mu;
   // staging for the *_host entry point
   char* d_stage = nullptr; size_t d_stage_cap = 0;
   char* h_stage = nullptr; size_t h_stage_cap = 0;
@@ -872,6 +879,7 @@ int spi_b200_model_destroy(spi_b200_model* m) {
   if (m->d_partial) cudaFree(m->d_partial);
   if (m->d_bad) cudaFree(m->d_bad);
   if (m->d_rank) cudaFree(m->d_rank);
+  for (auto& kv : m->fim_part) if (kv.second.ptr) cudaFree(kv.second.ptr);
   if (m->d_stage) cudaFree(m->d_stage);
   if (m->h_stage) cudaFreeHost(m->h_stage);
   for (auto e : m->ev_pool) cudaEventDestroy(e);
@@ -1414,8 +1422,28 @@ int spi_b200_fim_contract(spi_b200_model* m, const float* hist, const unsigned c
   A.hist = hist; A.live = live; A.T = T; A.M = Mn; A.P = P; A.inv_delta = 1.0f / delta; A.accumulate = accumulate;
   A.out_JtJ = out_JtJ; A.out_trace = out_trace;
   const int n_cta = (Mn + fimtc::kEnvsPerCta - 1) / fimtc::kEnvsPerCta;
-  fimtc::fim_contract_kernel<<<n_cta, fimtc::kRows, fimtc::kSmemBytes, (cudaStream_t)cuda_stream>>>(A);
-  return check_launch("fim_contract_kernel");
+  // slices of the control steps: ONE wave of 2 CTAs per SM (measured at 128 env tiles, T = 1 248: 2 slices 1.00 ms, 3 slices
+  // 1.30 ms, 5 slices 1.18 ms, 8 slices 1.01 ms — a second, partial wave costs more than the finer slices win), >= 4 steps each
+  static const int split_env = [] { const char* e = getenv("SPI_B200_FIM_SPLIT"); return e ? atoi(e) : 0; }();
+  int n_split = split_env > 0 ? split_env : (2 * m->sm_count) / n_cta;
+  { const int cap = T / 4 > 1 ? T / 4 : 1; if (n_split > cap) n_split = cap; if (n_split < 1) n_split = 1; }
+  A.n_split = n_split; A.part_JtJ = nullptr; A.part_trace = nullptr;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const size_t n_jtj = (size_t)Mn * P * P;
+  if (n_split > 1) {
+    spi_b200_model::FimPart* fp;
+    { std::lock_guard<std::mutex> lock(m->fim_part_mu); fp = &m->fim_part[st]; }
+    if (int rc = ensure(&fp->ptr, &fp->cap, (size_t)n_split * (n_jtj + Mn))) return rc;
+    A.part_JtJ = fp->ptr; A.part_trace = fp->ptr + (size_t)n_split * n_jtj;
+  }
+  fimtc::fim_contract_kernel<<<dim3(n_cta, n_split), fimtc::kRows, fimtc::kSmemBytes, st>>>(A);
+  if (int rc = check_launch("fim_contract_kernel")) return rc;
+  if (n_split > 1) {
+    if (out_JtJ) fimtc::fim_reduce_kernel<<<(unsigned)((n_jtj + 255) / 256), 256, 0, st>>>(A.part_JtJ, n_split, n_jtj, accumulate, out_JtJ);
+    if (out_trace) fimtc::fim_reduce_kernel<<<(Mn + 255) / 256, 256, 0, st>>>(A.part_trace, n_split, (size_t)Mn, accumulate, out_trace);
+    return check_launch("fim_reduce_kernel");
+  }
+  return 0;
 }
 
 int spi_b200_weighted_cost(spi_b200_model* m, const float* cost3, int C, float w_pos, float w_quat, float w_joint,

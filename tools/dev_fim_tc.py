@@ -34,3 +34,13 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); eng.fim_contract(h, 0.1, live=live); e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
 print(f"T={T} M={M} P={P}: {ms:.3f} ms; hist {h.numel()*4/1e9:.2f} GB -> {h.numel()*4/ms/1e6:.0f} GB/s; useful {2*M*P*P*25*T/ms/1e9:.2f} TFLOP/s, issued {3*2*128*128*32*T*(M/8)/ms/1e9:.1f} TFLOP/s tf32")
+# the chunk the rollout actually contracts: 64 steps
+for Tc in (64, 256):
+    hc, lc = h[:Tc].contiguous(), live[:Tc].contiguous()
+    for _ in range(3): eng.fim_contract(hc, 0.1, live=lc)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10): eng.fim_contract(hc, 0.1, live=lc)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"T={Tc} M={M} P={P}: {ms*1e3:.1f} us; hist {hc.numel()*4/1e6:.1f} MB -> {hc.numel()*4/ms/1e6:.0f} GB/s")
