@@ -18,6 +18,7 @@
 #include "fim_tc.cuh"
 #include "mlp_tc.cuh"
 #include "rollout_ws.cuh"
+#include "rollout_dual.cuh"
 
 using namespace spi;
 
@@ -752,7 +753,20 @@ int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C
   // sub-partition needs >= 3 leg warps in phase 1 at once and serialising them starves it (profiles/README.md r2).
   static const int halves_env = [] { const char* e = getenv("SPI_B200_WS_HALVES"); return e ? atoi(e) : 0; }();
   const bool two = halves_env == 2;
-  if (two) {
+  static const int dual_env = [] { const char* e = getenv("SPI_B200_WS_DUAL"); return e ? atoi(e) : -1; }();
+  const bool dual = dual_env >= 0 ? dual_env != 0 : false;
+  if (dual) {
+    static std::atomic<unsigned long long> attr_done{0};
+    int attr_dev = -1;
+    if (attr_needed_on_current_device(&attr_done, &attr_dev)) {
+      CUDA_OK(cudaFuncSetAttribute(ws::rollout_dual_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws::kDualSmemBytes));
+      CUDA_OK(cudaFuncSetAttribute(ws::rollout_dual_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws::kDualSmemBytes));
+      attr_mark_done(&attr_done, attr_dev);
+    }
+    const unsigned n2 = (unsigned)((n_cta + 1) / 2);
+    if (minb == 2) ws::rollout_dual_kernel<2><<<n2, ws::kDualThreads, ws::kDualSmemBytes, st>>>(A);
+    else ws::rollout_dual_kernel<3><<<n2, ws::kDualThreads, ws::kDualSmemBytes, st>>>(A);
+  } else if (two) {
     const unsigned n2 = (unsigned)((n_cta + 1) / 2);
     if (minb == 1) ws::rollout_ws2_kernel<1><<<n2, 2 * ws::kWsThreads, 0, st>>>(A);
     else ws::rollout_ws2_kernel<2><<<n2, 2 * ws::kWsThreads, 0, st>>>(A);
