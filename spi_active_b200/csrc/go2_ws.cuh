@@ -105,12 +105,8 @@ struct alignas(16) LegK {
   float cIbb, cIbc, cIcc, pad_i;   // (b, c) = (z, x) block of the projected rotational inertia
   float cHb[3], pad_hb, cHc[3], pad_hc;     // rows b, c of the projected coupling block
   float cMa[6], pad_ma[2];         // projected linear block, symmetric storage
-  // thigh articulated inertia BEFORE its own projection = thigh rigid inertia + the calf's constant projected inertia
-  // rotated by the calf angle and shifted by rc: every entry is a trigonometric polynomial a + b cos q + c sin q +
-  // d cos 2q + e sin 2q of the calf angle; the non-zero coefficients (kCalfMask), packed in entry order
-#if defined(SPI_WS_CALF_HARMONIC)
-  float calfA2[64];
-#endif
+  float cUadb, cUadc, pad_ud[2];   // U / D of the calf joint (what phase 2 multiplies with): angular b, c and
+  float cUld[3], pad_uld;          // linear components
 };
 static_assert(sizeof(LegK) % 16 == 0, "LegK must keep 16-byte alignment in the leg array");
 
@@ -185,10 +181,12 @@ template <int AX> WS_HD void rot_down(float cs, float sn, const float* v, float*
 struct Twist { float a[3]; float l[3]; };   // motion [w; v] or force [n; f]
 
 // what a joint keeps between the inward and the acceleration pass
+// (U / D and u / D rather than U, 1 / D and u: phase 2 is then  qdd = u/D - (U/D) . a'  without a final multiply, and the joint
+// keeps 12 floats instead of 14; (U/D)[a] == 1 is not stored)
 struct Keep {
   float cs, sn;
   float cab, cac, clb, clc;  // velocity-product acceleration c = v x (e_a qd): components b, c
-  float Ua[3], Ul[3], dinv, u;
+  float Uadb, Uadc, Uld[3], ud;
 };
 
 // ---- outward pass for one joint: velocity, velocity-product terms, bias force of the rigid body ---------
@@ -257,8 +255,9 @@ WS_HD void force_to_parent(const float* pa_a, const float* pa_l, float cs, float
 // ---- transform a projected inertia + force to the parent and accumulate -------------------------------
 // pa = pA + Ia c + U u / D must be given; IAp / pAp already hold the parent's own inertia / bias force.
 // PARENT_ZERO: IAp / pAp hold nothing yet (the hip's parent is the base, whose own inertia the base role adds) — the results
-// are assigned instead of added to zeros.
-template <int AX, int MASK, bool PARENT_ZERO = false>
+// are assigned instead of added to zeros.  PARENT_RIGID: IAp was filled by abi_from_rigid, i.e. M is diagonal and H is skew —
+// the structurally zero entries are assigned as well (x + 0.0f is not folded by the compiler: -0 + 0 = +0).
+template <int AX, int MASK, bool PARENT_ZERO = false, bool PARENT_RIGID = false>
 WS_HD void project_to_parent(const Proj& P, const float* pa_a, const float* pa_l, float cs, float sn, const float* r,
                              ABI& IAp, Twist& pAp) {
   constexpr int a = Ax<AX>::a, b = Ax<AX>::b, c = Ax<AX>::c;
@@ -339,57 +338,59 @@ WS_HD void project_to_parent(const Proj& P, const float* pa_a, const float* pa_l
 #pragma unroll
     for (int j = 0; j < 3; j++) {
       if (PARENT_ZERO) IAp.H[3 * i + j] = row_zero ? 0.f : Hp[3 * i + j];
-      else if (!row_zero) IAp.H[3 * i + j] += Hp[3 * i + j];
+      else if (!row_zero) IAp.H[3 * i + j] = (PARENT_RIGID && i == j) ? Hp[3 * i + j] : IAp.H[3 * i + j] + Hp[3 * i + j];
     }
   }
 #pragma unroll
-  for (int i = 0; i < 6; i++) IAp.M[i] = PARENT_ZERO ? M2[i] : IAp.M[i] + M2[i];
+  for (int i = 0; i < 6; i++) IAp.M[i] = (PARENT_ZERO || (PARENT_RIGID && i >= 3)) ? M2[i] : IAp.M[i] + M2[i];
   force_to_parent<AX, MASK, PARENT_ZERO>(pa_a, pa_l, cs, sn, r, pAp);
 }
 
 // ---- inward pass for a joint with a state-dependent articulated inertia (hip, thigh) ------------------------
-template <int AX, int MASK, bool PARENT_ZERO = false>
+template <int AX, int MASK, bool PARENT_ZERO = false, bool PARENT_RIGID = false>
 WS_HD void joint_inward(const ABI& IA, const Twist& pA, float tau, const float* r, Keep& k, ABI& IAp, Twist& pAp) {
   constexpr int a = Ax<AX>::a, b = Ax<AX>::b, c = Ax<AX>::c;
+  float Ua[3], Ul[3];
 #pragma unroll
-  for (int i = 0; i < 3; i++) { k.Ua[i] = IA.I[sidx(i, a)]; k.Ul[i] = IA.H[3 * a + i]; }
-  k.dinv = rcp_fast(k.Ua[a]);
-  k.u = tau - pA.a[a];
-  float Uad[3], Uld[3];
+  for (int i = 0; i < 3; i++) { Ua[i] = IA.I[sidx(i, a)]; Ul[i] = IA.H[3 * a + i]; }
+  const float dinv = rcp_fast(Ua[a]);
+  const float u = tau - pA.a[a];
+  k.Uadb = Ua[b] * dinv; k.Uadc = Ua[c] * dinv;
 #pragma unroll
-  for (int i = 0; i < 3; i++) { Uad[i] = k.Ua[i] * k.dinv; Uld[i] = k.Ul[i] * k.dinv; }
+  for (int i = 0; i < 3; i++) k.Uld[i] = Ul[i] * dinv;
   Proj P;
-  P.Ibb = IA.I[sidx(b, b)] - Uad[b] * k.Ua[b];
-  P.Ibc = IA.I[sidx(b, c)] - Uad[b] * k.Ua[c];
-  P.Icc = IA.I[sidx(c, c)] - Uad[c] * k.Ua[c];
+  P.Ibb = IA.I[sidx(b, b)] - k.Uadb * Ua[b];
+  P.Ibc = IA.I[sidx(b, c)] - k.Uadb * Ua[c];
+  P.Icc = IA.I[sidx(c, c)] - k.Uadc * Ua[c];
 #pragma unroll
   for (int j = 0; j < 3; j++) {
-    P.Hb[j] = IA.H[3 * b + j] - Uad[b] * k.Ul[j];
-    P.Hc[j] = IA.H[3 * c + j] - Uad[c] * k.Ul[j];
+    P.Hb[j] = IA.H[3 * b + j] - k.Uadb * Ul[j];
+    P.Hc[j] = IA.H[3 * c + j] - k.Uadc * Ul[j];
   }
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
-    for (int j = i; j < 3; j++) P.Ma[sidx(i, j)] = IA.M[sidx(i, j)] - Uld[i] * k.Ul[j];
-  // pa = pA + Ia c + U u / D     (c has no component along a)
-  const float ud = k.u * k.dinv;
+    for (int j = i; j < 3; j++) P.Ma[sidx(i, j)] = IA.M[sidx(i, j)] - k.Uld[i] * Ul[j];
+  // pa = pA + Ia c + U u / D     (c has no component along a;  pA[a] + U[a] u / D = pA[a] + u = tau)
+  const float ud = u * dinv;
+  k.ud = ud;
   float pa_a[3], pa_l[3];
-  pa_a[a] = pA.a[a] + ud * k.Ua[a];
-  pa_a[b] = pA.a[b] + P.Ibb * k.cab + P.Ibc * k.cac + P.Hb[b] * k.clb + P.Hb[c] * k.clc + ud * k.Ua[b];
-  pa_a[c] = pA.a[c] + P.Ibc * k.cab + P.Icc * k.cac + P.Hc[b] * k.clb + P.Hc[c] * k.clc + ud * k.Ua[c];
+  pa_a[a] = tau;
+  pa_a[b] = pA.a[b] + P.Ibb * k.cab + P.Ibc * k.cac + P.Hb[b] * k.clb + P.Hb[c] * k.clc + ud * Ua[b];
+  pa_a[c] = pA.a[c] + P.Ibc * k.cab + P.Icc * k.cac + P.Hc[b] * k.clb + P.Hc[c] * k.clc + ud * Ua[c];
 #pragma unroll
   for (int j = 0; j < 3; j++)
-    pa_l[j] = pA.l[j] + P.Hb[j] * k.cab + P.Hc[j] * k.cac + P.Ma[sidx(j, b)] * k.clb + P.Ma[sidx(j, c)] * k.clc + ud * k.Ul[j];
-  project_to_parent<AX, MASK, PARENT_ZERO>(P, pa_a, pa_l, k.cs, k.sn, r, IAp, pAp);
+    pa_l[j] = pA.l[j] + P.Hb[j] * k.cab + P.Hc[j] * k.cac + P.Ma[sidx(j, b)] * k.clb + P.Ma[sidx(j, c)] * k.clc + ud * Ul[j];
+  project_to_parent<AX, MASK, PARENT_ZERO, PARENT_RIGID>(P, pa_a, pa_l, k.cs, k.sn, r, IAp, pAp);
 }
 
 // ---- inward pass for the calf (leaf, axis y): the projection is the per-leg constant in LegK -----------------
 WS_HD void calf_inward(const LegK& L, const Twist& pA, float tau, Keep& k, ABI& IAp, Twist& pAp) {
   constexpr int a = 1, b = 2, c = 0;
-  k.u = tau - pA.a[a];
-  const float ud = k.u * L.cDinv;
+  const float ud = (tau - pA.a[a]) * L.cDinv;
+  k.ud = ud;
   float pa_a[3], pa_l[3];
-  pa_a[a] = pA.a[a] + ud * L.cUa[a];
+  pa_a[a] = tau;
   pa_a[b] = pA.a[b] + L.cIbb * k.cab + L.cIbc * k.cac + L.cHb[b] * k.clb + L.cHb[c] * k.clc + ud * L.cUa[b];
   pa_a[c] = pA.a[c] + L.cIbc * k.cab + L.cIcc * k.cac + L.cHc[b] * k.clb + L.cHc[c] * k.clc + ud * L.cUa[c];
 #pragma unroll
@@ -403,93 +404,31 @@ WS_HD void calf_inward(const LegK& L, const Twist& pA, float tau, Keep& k, ABI& 
 #pragma unroll
   for (int i = 0; i < 6; i++) P.Ma[i] = L.cMa[i];
   const float r[3] = {0.f, 0.f, L.rc};
-  project_to_parent<1, kMaskCalf>(P, pa_a, pa_l, k.cs, k.sn, r, IAp, pAp);
+  project_to_parent<1, kMaskCalf, false, true>(P, pa_a, pa_l, k.cs, k.sn, r, IAp, pAp);   // IAp = the thigh's rigid inertia
 }
 
-#if defined(SPI_WS_CALF_HARMONIC)   // experiment, off by default (measured slower: see leg_phase1)
-// ---- the calf's share of the thigh's articulated inertia as harmonics of the calf angle ------------------------------------
-// The calf is a leaf, so its projected inertia is constant in the calf frame; seen from the thigh frame (rotation about y by
-// the calf angle q, shift by (0, 0, rc)) every entry of  thigh rigid inertia + X(q)^T Ia X(q)  is
-//     a + b cos q + c sin q + d cos 2q + e sin 2q
-// with constant coefficients.  38 FFMA replace the ~110 instructions of rotating / shifting the 21 entries (project_to_parent),
-// and the entries that vanish identically (H[1][1], M off-diagonals xy, yz) become compile-time zeros for the thigh's
-// projection.  kCalfMask = which coefficients are non-zero for the Go2-family chain (bit 0 = a ... bit 4 = e; entry order I
-// (xx, yy, zz, xy, xz, yz), H row-major, M (xx, yy, zz, xy, xz, yz)); model_from_blob fits the coefficients by a discrete
-// Fourier sum over the direct evaluation (calf_inward) and refuses the fast path if a masked-out coefficient is not negligible.
-constexpr int kCalfEntries = 21;
-WS_HD constexpr unsigned calf_mask(int e) {
-  constexpr unsigned m[kCalfEntries] = {31, 25, 25, 25, 31, 25,  25, 7, 25, 25, 0, 25, 25, 7, 25,  25, 1, 25, 0, 24, 0};
-  return m[e];
-}
-WS_HD constexpr int calf_offset(int e, int bit) {   // index of coefficient (e, bit) in the packed array
-  int n = 0;
-  for (int i = 0; i < e; i++)
-    for (int b = 0; b < 5; b++) n += (calf_mask(i) >> b) & 1;
-  for (int b = 0; b < bit; b++) n += (calf_mask(e) >> b) & 1;
-  return n;
-}
-constexpr int kCalfCoefs = calf_offset(kCalfEntries, 0);
-static_assert(kCalfCoefs <= 64, "LegK::calfA2 too small");
-
-WS_HD float& abi_entry(ABI& A, int e) { return e < 6 ? A.I[e] : (e < 15 ? A.H[e - 6] : A.M[e - 15]); }
-
-template <int E> WS_HD float calf_entry(const LegK& L, const float* basis) {
-  float v = 0.f;
-  bool have = false;
-#pragma unroll
-  for (int b = 0; b < 5; b++) {
-    if ((calf_mask(E) >> b) & 1) {
-      const float k = L.calfA2[calf_offset(E, b)];
-      if (b == 0) v = k;
-      else v = have ? fmaf(k, basis[b], v) : k * basis[b];
-      have = true;
-    }
-  }
-  return v;    // entries without any coefficient are the literal 0.f
-}
-template <int E> WS_HD void calf_entries(const LegK& L, const float* basis, ABI& A2) {
-  abi_entry(A2, E) = calf_entry<E>(L, basis);
-  if constexpr (E + 1 < kCalfEntries) calf_entries<E + 1>(L, basis, A2);
-}
-WS_HD void calf_inertia(const LegK& L, float cs, float sn, ABI& A2) {
-  const float basis[5] = {1.f, cs, sn, cs * cs - sn * sn, 2.f * cs * sn};
-  calf_entries<0>(L, basis, A2);
-}
-// the force half of calf_inward: pa = pA + Ia c + U u / D, rotated / shifted to the thigh and added to its bias force
-WS_HD void calf_force(const LegK& L, const Twist& pA, float tau, Keep& k, Twist& pAp) {
-  constexpr int a = 1, b = 2, c = 0;
-  k.u = tau - pA.a[a];
-  const float ud = k.u * L.cDinv;
-  float pa_a[3], pa_l[3];
-  pa_a[a] = pA.a[a] + ud * L.cUa[a];
-  pa_a[b] = pA.a[b] + L.cIbb * k.cab + L.cIbc * k.cac + L.cHb[b] * k.clb + L.cHb[c] * k.clc + ud * L.cUa[b];
-  pa_a[c] = pA.a[c] + L.cIbc * k.cab + L.cIcc * k.cac + L.cHc[b] * k.clb + L.cHc[c] * k.clc + ud * L.cUa[c];
-#pragma unroll
-  for (int j = 0; j < 3; j++)
-    pa_l[j] = pA.l[j] + L.cHb[j] * k.cab + L.cHc[j] * k.cac + L.cMa[sidx(j, b)] * k.clb + L.cMa[sidx(j, c)] * k.clc +
-              ud * L.cUl[j];
-  const float r[3] = {0.f, 0.f, L.rc};
-  force_to_parent<1, kMaskCalf>(pa_a, pa_l, k.cs, k.sn, r, pAp);
-}
-
-#endif   // SPI_WS_CALF_HARMONIC
 
 // ---- outward acceleration pass for one joint --------------------------------------------------------------
 template <int AX, int MASK>
-WS_HD float joint_accel(const Twist& ap, const float* r, const float* Ua, const float* Ul, float dinv, const Keep& k,
-                        Twist& acc) {
+WS_HD float joint_accel(const Twist& ap, const float* r, float Uadb, float Uadc, const float* Uld, const Keep& k, Twist& acc) {
   constexpr int a = Ax<AX>::a, b = Ax<AX>::b, c = Ax<AX>::c;
   float t[3] = {ap.l[0], ap.l[1], ap.l[2]};
   add_cross_ar<MASK>(ap.a, r, t);
-  rot_down<AX>(k.cs, k.sn, ap.a, acc.a);
-  rot_down<AX>(k.cs, k.sn, t, acc.l);
-  acc.a[b] += k.cab; acc.a[c] += k.cac;
-  acc.l[b] += k.clb; acc.l[c] += k.clc;
-  const float dotU = Ua[0] * acc.a[0] + Ua[1] * acc.a[1] + Ua[2] * acc.a[2] +
-                     Ul[0] * acc.l[0] + Ul[1] * acc.l[1] + Ul[2] * acc.l[2];
-  const float qdd = (k.u - dotU) * dinv;
-  acc.a[a] += qdd;
-  return qdd;
+  // R^T a_parent + c as FMA chains that start from the velocity-product term (a separate FADD per component costs an issue slot)
+  acc.a[a] = ap.a[a];
+  acc.a[b] = fmaf(k.cs, ap.a[b], fmaf(k.sn, ap.a[c], k.cab));
+  acc.a[c] = fmaf(k.cs, ap.a[c], fmaf(-k.sn, ap.a[b], k.cac));
+  acc.l[a] = t[a];
+  acc.l[b] = fmaf(k.cs, t[b], fmaf(k.sn, t[c], k.clb));
+  acc.l[c] = fmaf(k.cs, t[c], fmaf(-k.sn, t[b], k.clc));
+  // qdd = (u - U . a') / D accumulated onto u / D;  (U / D)[a] == 1
+  float e = k.ud - acc.a[a];
+  e = fmaf(-Uadb, acc.a[b], e);
+  e = fmaf(-Uadc, acc.a[c], e);
+#pragma unroll
+  for (int i = 0; i < 3; i++) e = fmaf(-Uld[i], acc.l[i], e);
+  acc.a[a] += e;
+  return e;
 }
 
 // number of floats a leg hands to the base role: I(6) H(9) M(6) pA(6)
@@ -501,11 +440,21 @@ constexpr int kBcA0 = 0, kBcR = 6, kBcV0 = 15, kBcPz = 21;
 struct LegState { float q[3], qd[3]; };
 struct LegKeep { Keep k1, k2, k3; };
 
+// Parking policy of the leg role: phase 1 produces the joints' Keep records from the calf inwards and only phase 2 reads them
+// again, so a kernel that is short of registers may move each record out of the register file as soon as it is complete
+// (rollout_ws.cuh: shared memory, float4) and bring it back in phase 2.  The default keeps everything in registers.
+struct NoPark {
+  WS_HD void put_calf(const Keep&) const {}
+  WS_HD void put_thigh(const Keep&) const {}
+  WS_HD void get(LegKeep&) const {}
+};
+
 // ---- leg role, phase 1: outward pass, foot contact, inward pass -> 27 floats for the base ------------------
 // Rv0[22] = the base broadcast (a0 unused here).  out[27] = hip-projected inertia/force in base coordinates.
 // foot_force (optional): world-frame contact force on this leg's foot.
+template <class PK = NoPark>
 WS_HD void leg_phase1(const SimK& S, const LegK& L, const float* bc, const LegState& s, const float* tau, LegKeep& K,
-                      float* out, float* foot_force) {
+                      float* out, float* foot_force, const PK pk = PK()) {
   const float* R = bc + kBcR;
   Twist v0;
 #pragma unroll
@@ -519,20 +468,19 @@ WS_HD void leg_phase1(const SimK& S, const LegK& L, const float* bc, const LegSt
   // foot contact (compliant sphere on the plane z = 0)
   {
     float t3[3], t2[3], t1[3], u3[3], u2[3];
-    rot_up<1>(K.k3.cs, K.k3.sn, L.foot, t3);
-    u3[0] = t3[0]; u3[1] = t3[1]; u3[2] = L.rc + t3[2];
+    // (axis y: a, b, c = y, z, x; axis x: a, b, c = x, y, z) — the joint-origin offsets start the FMA chains they are added to
+    t3[0] = K.k3.sn * L.foot[2] + K.k3.cs * L.foot[0];
+    u3[0] = t3[0]; u3[1] = L.foot[1]; u3[2] = fmaf(K.k3.cs, L.foot[2], fmaf(-K.k3.sn, L.foot[0], L.rc));
     rot_up<1>(K.k2.cs, K.k2.sn, u3, t2);
     u2[0] = t2[0]; u2[1] = L.rt + t2[1]; u2[2] = t2[2];
-    rot_up<0>(K.k1.cs, K.k1.sn, u2, t1);
-    const float fbx = L.rh[0] + t1[0], fby = L.rh[1] + t1[1], fbz = t1[2];
+    t1[0] = u2[0]; t1[2] = K.k1.sn * u2[1] + K.k1.cs * u2[2];
+    const float fbx = L.rh[0] + t1[0], fby = fmaf(K.k1.cs, u2[1], fmaf(-K.k1.sn, u2[2], L.rh[1])), fbz = t1[2];
     const float pz = bc[kBcPz] + R[6] * fbx + R[7] * fby + R[8] * fbz;
     const float depth = S.radius - pz;
     float F[3] = {0.f, 0.f, 0.f};
     if (depth > 0.f) {
-      float wxo[3], vc[3], a2[3], a1[3], vb[3], vw[3];
-      cross3(v3.a, L.foot, wxo);
-#pragma unroll
-      for (int i = 0; i < 3; i++) vc[i] = v3.l[i] + wxo[i];
+      float vc[3] = {v3.l[0], v3.l[1], v3.l[2]}, a2[3], a1[3], vb[3], vw[3];
+      add_cross(v3.a, L.foot, vc);
       rot_up<1>(K.k3.cs, K.k3.sn, vc, a2);
       rot_up<1>(K.k2.cs, K.k2.sn, a2, a1);
       rot_up<0>(K.k1.cs, K.k1.sn, a1, vb);
@@ -543,31 +491,26 @@ WS_HD void leg_phase1(const SimK& S, const LegK& L, const float* bc, const LegSt
       const float speed2 = vw[0] * vw[0] + vw[1] * vw[1] + S.veps2;
       const float coef = fminf(S.dtan, S.mu * fn * rsqrt_fast(speed2));
       F[0] = -(coef * vw[0]); F[1] = -(coef * vw[1]); F[2] = fn;
-      float fb[3], g1[3], g2[3], fc[3], nc[3];
+      float fb[3], g1[3], g2[3], fc[3];
 #pragma unroll
       for (int i = 0; i < 3; i++) fb[i] = R[i] * F[0] + R[3 + i] * F[1] + R[6 + i] * F[2];
       rot_down<0>(K.k1.cs, K.k1.sn, fb, g1);
       rot_down<1>(K.k2.cs, K.k2.sn, g1, g2);
       rot_down<1>(K.k3.cs, K.k3.sn, g2, fc);
-      cross3(L.foot, fc, nc);
+      add_cross(fc, L.foot, p3.a);                    // p3.a -= foot x fc
 #pragma unroll
-      for (int i = 0; i < 3; i++) { p3.a[i] -= nc[i]; p3.l[i] -= fc[i]; }
+      for (int i = 0; i < 3; i++) p3.l[i] -= fc[i];
     }
     if (foot_force) { foot_force[0] = F[0]; foot_force[1] = F[1]; foot_force[2] = F[2]; }
   }
   // inward pass up the leg
   ABI A2, A1, A0;
-#if defined(SPI_WS_CALF_HARMONIC)
-  // measured (r2, C = 4096): 42.5 ms vs 41.5 ms for the direct formulation — 34 fewer FP instructions per sub-step but 28 more
-  // constant fetches (the leg index is a run-time value, so every coefficient is an LDCU / LDC, not an immediate) and 13 MOVs
-  calf_inertia(L, K.k3.cs, K.k3.sn, A2);
-  calf_force(L, p3, tau[2], K.k3, p2);
-#else
   abi_from_rigid(L.m[1], L.h[1], L.Io[1], A2);
   calf_inward(L, p3, tau[2], K.k3, A2, p2);
-#endif
+  pk.put_calf(K.k3);
   abi_from_rigid(L.m[0], L.h[0], L.Io[0], A1);
-  joint_inward<1, kMaskThigh>(A2, p2, tau[1], r1, K.k2, A1, p1);
+  joint_inward<1, kMaskThigh, false, true>(A2, p2, tau[1], r1, K.k2, A1, p1);       // A1 = the hip's rigid inertia
+  pk.put_thigh(K.k2);
   Twist p0;
   joint_inward<0, kMaskHip, true>(A1, p1, tau[0], r0, K.k1, A0, p0);
 #pragma unroll
@@ -579,15 +522,17 @@ WS_HD void leg_phase1(const SimK& S, const LegK& L, const float* bc, const LegSt
 }
 
 // ---- leg role, phase 2: acceleration pass + semi-implicit Euler of the 3 joints ------------------------------
-WS_HD void leg_phase2(const LegK& L, const float* bc, const LegKeep& K, LegState& s, float h) {
+template <class PK = NoPark>
+WS_HD void leg_phase2(const LegK& L, const float* bc, LegKeep& K, LegState& s, float h, const PK pk = PK()) {
+  pk.get(K);
   Twist a0, a1, a2, a3;
 #pragma unroll
   for (int i = 0; i < 3; i++) { a0.a[i] = bc[kBcA0 + i]; a0.l[i] = bc[kBcA0 + 3 + i]; }
   float r0[3], r1[3], r2[3];
   joint_r(L, 0, r0); joint_r(L, 1, r1); joint_r(L, 2, r2);
-  const float qdd0 = joint_accel<0, kMaskHip>(a0, r0, K.k1.Ua, K.k1.Ul, K.k1.dinv, K.k1, a1);
-  const float qdd1 = joint_accel<1, kMaskThigh>(a1, r1, K.k2.Ua, K.k2.Ul, K.k2.dinv, K.k2, a2);
-  const float qdd2 = joint_accel<1, kMaskCalf>(a2, r2, L.cUa, L.cUl, L.cDinv, K.k3, a3);
+  const float qdd0 = joint_accel<0, kMaskHip>(a0, r0, K.k1.Uadb, K.k1.Uadc, K.k1.Uld, K.k1, a1);
+  const float qdd1 = joint_accel<1, kMaskThigh>(a1, r1, K.k2.Uadb, K.k2.Uadc, K.k2.Uld, K.k2, a2);
+  const float qdd2 = joint_accel<1, kMaskCalf>(a2, r2, L.cUadb, L.cUadc, L.cUld, K.k3, a3);
   s.qd[0] += h * qdd0; s.q[0] += h * s.qd[0];
   s.qd[1] += h * qdd1; s.q[1] += h * s.qd[1];
   s.qd[2] += h * qdd2; s.q[2] += h * s.qd[2];
@@ -826,7 +771,7 @@ WS_HD void apply_candidate(const ModelK& M, const float* row, const ParamIdsK& i
 
 // host-side: blob -> ModelK (incl. the constant calf projection).  Returns 0, or a negative code when the
 // blob does not have the Go2-family structure this fast path is compiled for (the caller then uses the
-// generic leg-per-lane kernel): -1 axes, -2 joint-origin sparsity, -3 harmonic structure of the calf's inertia.
+// generic leg-per-lane kernel): -1 axes, -2 joint-origin sparsity.
 inline int model_from_blob(const float* b, ModelK* M) {
   M->sim.dt = b[SPI_BLOB_DT]; M->sim.gz = b[SPI_BLOB_GRAVITY_Z];
   M->sim.action_scale = b[SPI_BLOB_ACTION_SCALE]; M->sim.action_clip = b[SPI_BLOB_ACTION_CLIP];
@@ -877,6 +822,8 @@ inline int model_from_blob(const float* b, ModelK* M) {
       L.cDinv = 1.0f / L.cUa[a];
       float Uad[3], Uld[3];
       for (int i = 0; i < 3; i++) { Uad[i] = L.cUa[i] * L.cDinv; Uld[i] = L.cUl[i] * L.cDinv; }
+      L.cUadb = Uad[bb]; L.cUadc = Uad[cx];
+      for (int i = 0; i < 3; i++) L.cUld[i] = Uld[i];
       L.cIbb = A.I[sidx(bb, bb)] - Uad[bb] * L.cUa[bb];
       L.cIbc = A.I[sidx(bb, cx)] - Uad[bb] * L.cUa[cx];
       L.cIcc = A.I[sidx(cx, cx)] - Uad[cx] * L.cUa[cx];
@@ -889,39 +836,6 @@ inline int model_from_blob(const float* b, ModelK* M) {
     }
   }
   for (int j = 0; j < 12; j++) { M->kp[j] = b[SPI_BLOB_KP + j]; M->kd[j] = b[SPI_BLOB_KD + j]; }
-#if defined(SPI_WS_CALF_HARMONIC)
-  // harmonic coefficients of the thigh's articulated inertia in the calf angle: discrete Fourier sums (exact for a
-  // trigonometric polynomial of degree 2 sampled at N > 4 equispaced angles) of the direct evaluation, accumulated in double
-  for (int leg = 0; leg < 4; leg++) {
-    LegK& L = M->leg[leg];
-    constexpr int N = 32;
-    double acc[kCalfEntries][5];
-    for (int e = 0; e < kCalfEntries; e++) for (int h = 0; h < 5; h++) acc[e][h] = 0.0;
-    for (int k = 0; k < N; k++) {
-      const double q = 6.283185307179586 * k / N;
-      ABI A2;
-      abi_from_rigid(L.m[1], L.h[1], L.Io[1], A2);
-      Twist p3, p2;
-      for (int i = 0; i < 3; i++) { p3.a[i] = p3.l[i] = 0.f; p2.a[i] = p2.l[i] = 0.f; }
-      Keep kk = Keep();
-      kk.cs = (float)std::cos(q); kk.sn = (float)std::sin(q);
-      calf_inward(L, p3, 0.f, kk, A2, p2);
-      const double basis[5] = {1.0, std::cos(q), std::sin(q), std::cos(2 * q), std::sin(2 * q)};
-      for (int e = 0; e < kCalfEntries; e++)
-        for (int h = 0; h < 5; h++) acc[e][h] += (double)abi_entry(A2, e) * basis[h] * (h == 0 ? 1.0 : 2.0) / N;
-    }
-    for (int i = 0; i < 64; i++) L.calfA2[i] = 0.f;
-    for (int e = 0; e < kCalfEntries; e++) {
-      double scale = 1e-3;      // entries of a block share a physical scale: compare against the largest one of the block
-      const int e0 = e < 6 ? 0 : (e < 15 ? 6 : 15), e1 = e < 6 ? 6 : (e < 15 ? 15 : 21);
-      for (int i = e0; i < e1; i++) for (int h = 0; h < 5; h++) scale = std::fmax(scale, std::fabs(acc[i][h]));
-      for (int h = 0; h < 5; h++) {
-        if ((calf_mask(e) >> h) & 1) L.calfA2[calf_offset(e, h)] = (float)acc[e][h];
-        else if (std::fabs(acc[e][h]) > 2e-6 * scale) return -3;      // not the harmonic structure this path is compiled for
-      }
-    }
-  }
-#endif
   return 0;
 }
 

@@ -25,14 +25,35 @@ struct WsArgs {
   int n_cta_per_cand;
   int C_grid;          // number of candidate rows of the grid (C; 1 in paired mode)
   int rotate_roles;
-  int token_mode;
   int paired;          // 1: rollout r uses candidate row r AND segment r (one env per rollout; C == 1 for the grid)
   float* partial;      // [C][n_cta_per_cand][3]
   float* per_seg;      // [C][S][3] or null
   int* bad;            // [C]
   float* out_states;   // [C][S][H][37] (RECORD)
   const unsigned char* zero_mask;   // paired mode: [S] 1 = this env's action is replaced by 0 (terminated group), or null
+#if defined(SPI_WS_PROFILE)         // dev builds only (tools/ws_timeline.py): clock64 stamps of every barrier of a window of CTAs
+  long long* prof; int prof_blk0, prof_nblk;
+#endif
 };
+
+#if defined(SPI_WS_PROFILE)
+constexpr int kProfSlots = 256;
+struct WsProf {
+  long long* p; int n;
+  __device__ __forceinline__ void init(const WsArgs& A, int lane, int warp) {
+    const int b = (int)blockIdx.x - A.prof_blk0;
+    p = (A.prof && lane == 0 && b >= 0 && b < A.prof_nblk) ? A.prof + ((size_t)b * kWsWarps + warp) * kProfSlots : nullptr;
+    n = 1;
+    if (p) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p[0] = sm; }
+  }
+  __device__ __forceinline__ void stamp() { if (p && n < kProfSlots) p[n] = clock64(); n++; }
+};
+#define WS_PROF_INIT(warp) WsProf prof_; prof_.init(A, lane, warp)
+#define WS_STAMP() prof_.stamp()
+#else
+#define WS_PROF_INIT(warp)
+#define WS_STAMP()
+#endif
 
 // The roles exchange their per-sub-step data as float4 (LDS.128 / STS.128, lane stride 16 bytes: conflict-free): 7 + 6
 // shared-memory instructions per leg and 28 + 6 + 4 for the base instead of 27 + 22 and 108 + 22 + 12 scalar ones — the
@@ -45,6 +66,16 @@ struct WsSmem {
   float4 bc[kBcStateVec + kBcA0Vec][32];           // base -> legs, per sub-step: [0,4) state of the sub-step, [4,6) a0
   float ej[4][32];                                 // per-leg squared joint error (end of rollout)
   int finite[4][32];
+#if defined(SPI_WS_PARK)
+  float4 keep[4][5][32];        // Keep records of the calf (2 float4) and the thigh (3) between phase 1 and phase 2
+  float4 state[4][2][32];       // joint state q, qd
+  float4 bstate[4][32];         // base state p, quat, v, w (the base role only needs it behind [B1])
+#endif
+#if defined(SPI_WS_COLD_PARK)
+  // values a leg only needs once per physics step (PD gains, motor parameters, the clipped action): parked here instead of
+  // being held in registers through the dynamics, where the register file is what limits the resident warps
+  float4 cold[4][3][32];
+#endif
 };
 static_assert(kBaseOut - kBcR == 4 * kBcStateVec && kBcR == 6 && kBcA0 == 0, "bc packing");
 
@@ -76,56 +107,62 @@ __device__ __forceinline__ void ws_store_a0(WsSmem& sm, int lane, const float* a
   sm.bc[kBcStateVec + 1][lane] = make_float4(a0[4], a0[5], 0.f, 0.f);
 }
 
+#if defined(SPI_WS_PARK)
+struct SmemPark {
+  float4 (*keep)[32]; float4 (*state)[32]; int lane;
+  __device__ __forceinline__ void put_calf(const Keep& k) const {
+    keep[0][lane] = make_float4(k.cs, k.sn, k.cab, k.cac);
+    keep[1][lane] = make_float4(k.clb, k.clc, k.ud, 0.f);
+  }
+  __device__ __forceinline__ void put_thigh(const Keep& k) const {
+    keep[2][lane] = make_float4(k.cs, k.sn, k.cab, k.cac);
+    keep[3][lane] = make_float4(k.clb, k.clc, k.Uadb, k.Uadc);
+    keep[4][lane] = make_float4(k.Uld[0], k.Uld[1], k.Uld[2], k.ud);
+  }
+  __device__ __forceinline__ void get(LegKeep& K) const {
+    float4 t = ws_lds_volatile(&keep[0][lane]); K.k3.cs = t.x; K.k3.sn = t.y; K.k3.cab = t.z; K.k3.cac = t.w;
+    t = ws_lds_volatile(&keep[1][lane]); K.k3.clb = t.x; K.k3.clc = t.y; K.k3.ud = t.z;
+    t = ws_lds_volatile(&keep[2][lane]); K.k2.cs = t.x; K.k2.sn = t.y; K.k2.cab = t.z; K.k2.cac = t.w;
+    t = ws_lds_volatile(&keep[3][lane]); K.k2.clb = t.x; K.k2.clc = t.y; K.k2.Uadb = t.z; K.k2.Uadc = t.w;
+    t = ws_lds_volatile(&keep[4][lane]); K.k2.Uld[0] = t.x; K.k2.Uld[1] = t.y; K.k2.Uld[2] = t.z; K.k2.ud = t.w;
+  }
+  __device__ __forceinline__ void put_state(const LegState& s) const {
+    state[0][lane] = make_float4(s.q[0], s.q[1], s.q[2], s.qd[0]);
+    state[1][lane] = make_float4(s.qd[1], s.qd[2], 0.f, 0.f);
+  }
+  __device__ __forceinline__ void get_state(LegState& s) const {
+    const float4 a = ws_lds_volatile(&state[0][lane]), b = ws_lds_volatile(&state[1][lane]);
+    s.q[0] = a.x; s.q[1] = a.y; s.q[2] = a.z; s.qd[0] = a.w; s.qd[1] = b.x; s.qd[2] = b.y;
+  }
+};
+#endif
+
 __device__ __forceinline__ bool finite_acc(float acc) { return acc == 0.f; }  // NaN/Inf * 0 = NaN
 
 // CTA-wide barrier reached from role-specific code paths: a named barrier with an explicit thread count
 // (every role executes the same number of ws_barrier() calls).
 __device__ __forceinline__ void ws_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kWsThreads) : "memory"); }
 
-// Named-barrier plan.  HALVES == 1 (one 32-rollout group per CTA): barrier 1 = the group's 160 threads, 2 / 3 = the leg pairs.
-// HALVES == 2 (two groups per CTA, DESIGN.md 4.2 "anti-phase pairing"): group g uses 1 + 3 g, 2 + 3 g, 3 + 3 g, and the two
-// groups hand a token back and forth on barriers 7 / 8 (256 = the 8 leg warps) so that their leg phases 1 never overlap:
-// resident CTAs of this kernel otherwise fall into lock-step (all legs in phase 1, then all waiting for their base role),
-// which left 22 % of the issue slots empty although 2.1 warps per scheduler were eligible on average (profiles/README.md r2).
-template <int HALVES> struct WsBars {
-  int g;
-  int mode;   // experiment switch: 2 = token on every sub-step, 1 = first sub-step only (initial stagger), 0 = none
-  __device__ __forceinline__ void cta() const {
-    if (HALVES == 1) ws_barrier();
-    else asm volatile("bar.sync %0, %1;" ::"r"(1 + 3 * g), "n"(kWsThreads) : "memory");
-  }
+// Named-barrier plan: barrier 1 = the CTA's 160 threads, 2 / 3 = the two leg pairs (64 threads each).
+// (Round 2 also measured two 32-rollout groups per 10-warp CTA whose leg phases 1 were kept from overlapping by a token on
+// named barriers — 43.6 ms vs 41.4 ms, profiles/README.md r2; removed again, git history: commit 6ac9449.)
+struct WsBars {
+  __device__ __forceinline__ void cta() const { ws_barrier(); }
   __device__ __forceinline__ void pair_arrive(int leg) const {
-    if (HALVES == 1) {
-      if (leg < 2) asm volatile("bar.arrive 2, 64;" ::: "memory");
-      else asm volatile("bar.arrive 3, 64;" ::: "memory");
-    } else asm volatile("bar.arrive %0, 64;" ::"r"(2 + 3 * g + (leg >> 1)) : "memory");
+    if (leg < 2) asm volatile("bar.arrive 2, 64;" ::: "memory");
+    else asm volatile("bar.arrive 3, 64;" ::: "memory");
   }
   __device__ __forceinline__ void pair_sync(int leg) const {
-    if (HALVES == 1) {
-      if (leg < 2) asm volatile("bar.sync 2, 64;" ::: "memory");
-      else asm volatile("bar.sync 3, 64;" ::: "memory");
-    } else asm volatile("bar.sync %0, 64;" ::"r"(2 + 3 * g + (leg >> 1)) : "memory");
-  }
-  // phase-1 token: group 0 owns it first.  wait = before phase 1 (n = index of the sub-step), pass = after phase 1.
-  __device__ __forceinline__ void token_wait(int n) const {
-    if (HALVES == 1 || mode == 0) return;
-    if (mode == 1) { if (g == 1 && n == 0) asm volatile("bar.sync 7, 256;" ::: "memory"); return; }
-    if (g == 0) { if (n > 0) asm volatile("bar.sync 8, 256;" ::: "memory"); }
-    else asm volatile("bar.sync 7, 256;" ::: "memory");
-  }
-  __device__ __forceinline__ void token_pass(int n, int n_total) const {
-    if (HALVES == 1 || mode == 0) return;
-    if (mode == 1) { if (g == 0 && n == 0) asm volatile("bar.arrive 7, 256;" ::: "memory"); return; }
-    if (g == 0) asm volatile("bar.arrive 7, 256;" ::: "memory");
-    else if (n + 1 < n_total) asm volatile("bar.arrive 8, 256;" ::: "memory");
+    if (leg < 2) asm volatile("bar.sync 2, 64;" ::: "memory");
+    else asm volatile("bar.sync 3, 64;" ::: "memory");
   }
 };
 
 // LEG is a warp-uniform run-time value (one code copy for the four legs: four template copies overflow the
 // instruction cache — profiles/README.md, experiment ws-templated); the leg's constants are then fetched through
 // the constant bank with a uniform offset.
-template <bool RECORD, int HALVES>
-__device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, const WsBars<HALVES> bars, int lane, const int LEG,
+template <bool RECORD>
+__device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, const WsBars bars, int lane, const int LEG,
                                             int c, int seg, bool active) {
   const SimK& S = A.M.sim;
   const LegK& L = A.M.leg[LEG];
@@ -163,25 +200,52 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, const W
   const float* act_row = A.seg_actions + (size_t)seg * A.H * 12 + 3 * LEG;
   LegKeep K;
   const bool zero_act = A.zero_mask && A.zero_mask[seg] != 0;
+#if defined(SPI_WS_PARK)
+  const SmemPark pk{sm.keep[LEG], sm.state[LEG], lane};
+  pk.put_state(s);
+#else
+  const NoPark pk;
+#endif
+#if defined(SPI_WS_COLD_PARK)
+  sm.cold[LEG][0][lane] = make_float4(kp[0], kp[1], kp[2], kd[0]);
+  sm.cold[LEG][1][lane] = make_float4(kd[1], kd[2], motor[0], motor[1]);
+#endif
+  WS_PROF_INIT(LEG);
   bars.cta();   // [S0] the base role has published R / v0 / pz of the initial state
-  const int n_sub_total = A.H * A.decimation * S.nsub;
-  int i_sub = 0;
   for (int k = 0; k < A.H; k++) {
     float act[3];
 #pragma unroll
     for (int j = 0; j < 3; j++)
       act[j] = zero_act ? 0.f : fminf(fmaxf(__ldg(act_row + 12 * k + j), -S.action_clip), S.action_clip);
+#if defined(SPI_WS_COLD_PARK)
+    sm.cold[LEG][2][lane] = make_float4(motor[2], act[0], act[1], act[2]);
+#endif
     for (int d = 0; d < A.decimation; d++) {
       float tau[3];
+#if defined(SPI_WS_PARK)
+      pk.get_state(s);
+#endif
+#if defined(SPI_WS_COLD_PARK)
+      {
+        const float4 c0 = ws_lds_volatile(&sm.cold[LEG][0][lane]), c1 = ws_lds_volatile(&sm.cold[LEG][1][lane]),
+                     c2 = ws_lds_volatile(&sm.cold[LEG][2][lane]);
+        const float kp_[3] = {c0.x, c0.y, c0.z}, kd_[3] = {c0.w, c1.x, c1.y}, motor_[3] = {c1.z, c1.w, c2.x}, act_[3] = {c2.y, c2.z, c2.w};
+        leg_torques(S, L, act_, s.q, s.qd, kp_, kd_, motor_, A.motor_model, A.flags, tau);
+      }
+#else
       leg_torques(S, L, act, s.q, s.qd, kp, kd, motor, A.motor_model, A.flags, tau);
-      for (int n = 0; n < S.nsub; n++, i_sub++) {
-        bars.token_wait(i_sub);      // HALVES == 2: the other group's legs have finished their phase 1
+#endif
+      for (int n = 0; n < S.nsub; n++) {
+        WS_STAMP();   // 0: phase 1 starts
         float bc[kBaseOut];
         ws_load_state(sm, lane, bc);
         float out[4 * kLegVec];
         out[4 * kLegVec - 1] = 0.f;
-        leg_phase1(S, L, bc, s, tau, K, out, nullptr);
-        bars.token_pass(i_sub, n_sub_total);
+#if defined(SPI_WS_PARK)
+        if (n > 0) pk.get_state(s);
+#endif
+        leg_phase1(S, L, bc, s, tau, K, out, nullptr, pk);
+        WS_STAMP();   // 1: phase 1 computed
         // the four legs are summed pairwise: the even leg of a pair publishes and signals (bar.arrive on the pair's own named
         // barrier, 64 threads), the odd leg waits for it, adds its own contribution and publishes the pair sum — the base
         // role then only adds two vectors in its serial section ((p0 + p1) + (p2 + p3), the same order as before)
@@ -198,10 +262,20 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, const W
             sm.part[LEG][v][lane] = make_float4(p.x + out[4 * v], p.y + out[4 * v + 1], p.z + out[4 * v + 2], p.w + out[4 * v + 3]);
           }
         }
+        WS_STAMP();   // 2: published (odd legs: after the pair wait + sum)
         bars.cta();   // [A]  the pair sums are in shared memory
+        WS_STAMP();   // 3: [A] released
         bars.cta();   // [B1] the base role has published a0
+        WS_STAMP();   // 4: [B1] released
         ws_load_a0(sm, lane, bc + kBcA0);
-        leg_phase2(L, bc, K, s, h);
+#if defined(SPI_WS_PARK)
+        pk.get_state(s);
+        leg_phase2(L, bc, K, s, h, pk);
+        pk.put_state(s);
+#else
+        leg_phase2(L, bc, K, s, h, pk);
+#endif
+        WS_STAMP();   // 5: phase 2 done
         bars.cta();   // [B2] the base role has published R / v0 / pz of the new state
       }
     }
@@ -229,8 +303,8 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, const W
   bars.cta();   // [C]
 }
 
-template <bool RECORD, int HALVES>
-__device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, const WsBars<HALVES> bars, int lane, int c,
+template <bool RECORD>
+__device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, const WsBars bars, int lane, int c,
                                              int cta_in_cand, int seg, bool active, bool group_live) {
   const SimK& S = A.M.sim;
   BaseInertia B;
@@ -251,14 +325,23 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, const 
   for (int i = 0; i < 6; i++) bc[i] = 0.f;
   base_publish(s, bc);
   ws_store_state(sm, lane, bc);
+#if defined(SPI_WS_PARK)
+  sm.bstate[0][lane] = make_float4(s.p[0], s.p[1], s.p[2], s.quat[0]);
+  sm.bstate[1][lane] = make_float4(s.quat[1], s.quat[2], s.quat[3], s.v[0]);
+  sm.bstate[2][lane] = make_float4(s.v[1], s.v[2], s.w[0], s.w[1]);
+  sm.bstate[3][lane] = make_float4(s.w[2], 0.f, 0.f, 0.f);
+#endif
   float pb[6];
   base_bias(B, bc, pb);
+  WS_PROF_INIT(4);
   bars.cta();   // [S0]
   const float h = S.dt / (float)S.nsub;
   for (int k = 0; k < A.H; k++) {
     for (int d = 0; d < A.decimation; d++) {
       for (int n = 0; n < S.nsub; n++) {
+        WS_STAMP();   // 0: waiting for [A]
         bars.cta();   // [A]
+        WS_STAMP();   // 1: [A] released
         float legsum[4 * kLegVec];
 #pragma unroll
         for (int v = 0; v < kLegVec; v++) {
@@ -271,7 +354,9 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, const 
         float a0[6];
         base_solve(B, legsum, pb, a0);
         ws_store_a0(sm, lane, a0);
+        WS_STAMP();   // 2: solved
         bars.cta();   // [B1] the legs start their acceleration pass
+        WS_STAMP();   // 3: [B1] released
         // keep the integration BEHIND the barrier: it only needs registers, so ptxas would otherwise schedule it between
         // the a0 stores and the barrier and delay the legs by ~90 instructions.  Reading a0 back from shared memory is a
         // dependency the scheduler cannot move across bar.sync (6 LDS, off the critical path).
@@ -279,9 +364,30 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, const 
           const float4 t0 = ws_lds_volatile(&sm.bc[kBcStateVec][lane]), t1 = ws_lds_volatile(&sm.bc[kBcStateVec + 1][lane]);
           a0[0] = t0.x; a0[1] = t0.y; a0[2] = t0.z; a0[3] = t0.w; a0[4] = t1.x; a0[5] = t1.y;
         }
+#if defined(SPI_WS_PARK)
+        {   // R / v0 of the current state and the base state come back from shared memory: nothing of them is live during the solve
+#pragma unroll
+          for (int v = 0; v < kBcStateVec; v++) {
+            const float4 t = ws_lds_volatile(&sm.bc[v][lane]);
+            bc[kBcR + 4 * v] = t.x; bc[kBcR + 4 * v + 1] = t.y; bc[kBcR + 4 * v + 2] = t.z; bc[kBcR + 4 * v + 3] = t.w;
+          }
+          const float4 b0 = ws_lds_volatile(&sm.bstate[0][lane]), b1 = ws_lds_volatile(&sm.bstate[1][lane]),
+                       b2 = ws_lds_volatile(&sm.bstate[2][lane]), b3 = ws_lds_volatile(&sm.bstate[3][lane]);
+          s.p[0] = b0.x; s.p[1] = b0.y; s.p[2] = b0.z; s.quat[0] = b0.w; s.quat[1] = b1.x; s.quat[2] = b1.y; s.quat[3] = b1.z;
+          s.v[0] = b1.w; s.v[1] = b2.x; s.v[2] = b2.y; s.w[0] = b2.z; s.w[1] = b2.w; s.w[2] = b3.x;
+        }
+#endif
         base_advance(S, a0, s, h, bc);
         ws_store_state(sm, lane, bc);
+#if defined(SPI_WS_PARK)
+        sm.bstate[0][lane] = make_float4(s.p[0], s.p[1], s.p[2], s.quat[0]);
+        sm.bstate[1][lane] = make_float4(s.quat[1], s.quat[2], s.quat[3], s.v[0]);
+        sm.bstate[2][lane] = make_float4(s.v[1], s.v[2], s.w[0], s.w[1]);
+        sm.bstate[3][lane] = make_float4(s.w[2], 0.f, 0.f, 0.f);
+#endif
+        WS_STAMP();   // 4: advanced
         bars.cta();   // [B2]
+        WS_STAMP();   // 5: [B2] released
         // velocity-product bias of the next sub-step: after the barrier, so that it overlaps the legs' phase 1 instead
         // of delaying their release (re-read through shared memory for the same reason as a0 above)
         {                                              // logical bc[15 .. 21) = floats 9 .. 14 of the packed state
@@ -341,49 +447,26 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, const 
   }
 }
 
-// HALVES == 1: blockIdx = one group of 32 rollouts, warps 0..3 = legs, warp 4 = base.
-// HALVES == 2: blockIdx = two consecutive groups; warps 0..3 / 4..7 = the legs of group 0 / 1 (leg i of both groups shares a
-// sub-partition, and the phase-1 token makes them take turns on it), warps 8 / 9 = the two base roles (highest warp ids: the
-// arbiter favours them).  An odd group count leaves the last CTA's second group without work: it replays the last group with
-// every write suppressed (the token protocol needs both groups).
-template <bool RECORD, int HALVES>
+// blockIdx = one group of 32 rollouts, warps 0..3 = legs, warp 4 = base.
+template <bool RECORD>
 __device__ __forceinline__ void rollout_ws_body(const WsArgs& A) {
-  __shared__ WsSmem sm_all[HALVES];
+  __shared__ WsSmem sm;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int role, g;
-  if (HALVES == 1) {
-    role = __shfl_sync(0xffffffffu, A.rotate_roles ? (warp + blockIdx.x) % kWsWarps : warp, 0);  // warp-uniform
-    g = 0;
-  } else {
-    const int w = __shfl_sync(0xffffffffu, warp, 0);
-    role = (w < 8) ? (w & 3) : 4;
-    g = (w < 8) ? (w >> 2) : (w - 8);
-  }
-  const long long n_groups = (long long)A.C_grid * A.n_cta_per_cand;
-  long long grp = (long long)blockIdx.x * HALVES + g;
-  const bool group_live = grp < n_groups;
-  if (!group_live) grp = n_groups - 1;
-  const int cg = (int)(grp / A.n_cta_per_cand);
-  const int cta_in_cand = (int)(grp - (long long)cg * A.n_cta_per_cand);
+  const int role = __shfl_sync(0xffffffffu, A.rotate_roles ? (warp + blockIdx.x) % kWsWarps : warp, 0);  // warp-uniform
+  const int cg = (int)(blockIdx.x / A.n_cta_per_cand);
+  const int cta_in_cand = (int)(blockIdx.x - (unsigned)cg * A.n_cta_per_cand);
   const int seg_raw = cta_in_cand * kWsRollouts + lane;
-  const bool active = group_live && seg_raw < A.S;
+  const bool active = seg_raw < A.S;
   const int seg = seg_raw < A.S ? seg_raw : A.S - 1;
   const int c = A.paired ? seg : cg;
-  WsSmem& sm = sm_all[g];
-  const WsBars<HALVES> bars{g, A.token_mode};
-  if (role < 4) ws_leg_role<RECORD, HALVES>(A, sm, bars, lane, role, c, seg, active);
-  else ws_base_role<RECORD, HALVES>(A, sm, bars, lane, c, cta_in_cand, seg, active, group_live);
+  const WsBars bars{};
+  if (role < 4) ws_leg_role<RECORD>(A, sm, bars, lane, role, c, seg, active);
+  else ws_base_role<RECORD>(A, sm, bars, lane, c, cta_in_cand, seg, active, true);
 }
 
 template <bool RECORD, int MINB>
 __global__ void __launch_bounds__(kWsThreads, MINB) rollout_ws_kernel(const __grid_constant__ WsArgs A) {
-  rollout_ws_body<RECORD, 1>(A);
-}
-
-// two anti-phased groups per CTA (evaluation only; the RECORD / paired launches are latency-bound single waves)
-template <int MINB>
-__global__ void __launch_bounds__(2 * kWsThreads, MINB) rollout_ws2_kernel(const __grid_constant__ WsArgs A) {
-  rollout_ws_body<false, 2>(A);
+  rollout_ws_body<RECORD>(A);
 }
 
 }  // namespace ws

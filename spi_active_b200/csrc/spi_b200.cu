@@ -18,7 +18,6 @@
 #include "fim_tc.cuh"
 #include "mlp_tc.cuh"
 #include "rollout_ws.cuh"
-#include "rollout_dual.cuh"
 
 using namespace spi;
 
@@ -706,6 +705,10 @@ int minb_choice() {
   return v;
 }
 
+#if defined(SPI_WS_PROFILE)   // dev builds only: tools/ws_timeline.py
+long long* g_ws_prof = nullptr; int g_ws_prof_blk0 = 0, g_ws_prof_nblk = 0;
+#endif
+
 int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C, int P, const int* param_ids,
                       const float* seg_init, const float* seg_actions, const float* seg_target, const float* seg_gains,
                       const unsigned char* seg_mask, int S, int H, int decimation, int motor_model, unsigned flags,
@@ -723,10 +726,12 @@ int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C
   A.seg_mask = seg_mask; A.S = S; A.H = H; A.decimation = decimation; A.motor_model = motor_model; A.flags = flags;
   A.n_cta_per_cand = (S + ws::kWsRollouts - 1) / ws::kWsRollouts;
   A.paired = paired; A.zero_mask = zero_mask; A.C_grid = C;
-  { static const int tm = getenv("SPI_B200_WS_TOKEN") ? atoi(getenv("SPI_B200_WS_TOKEN")) : 2; A.token_mode = tm; }
   { static const int rot = getenv("SPI_B200_WS_ROT") ? atoi(getenv("SPI_B200_WS_ROT")) : 0; A.rotate_roles = rot; }
   const long long n_cta = (long long)C * A.n_cta_per_cand;
   if (n_cta > 2147483647LL) return fail(-3, "C * ceil(S/32) exceeds the grid limit");
+#if defined(SPI_WS_PROFILE)
+  A.prof = g_ws_prof; A.prof_blk0 = g_ws_prof_blk0; A.prof_nblk = g_ws_prof_nblk;
+#endif
   const int minb = minb_choice();
   if (record) {
     A.out_states = out_states;
@@ -747,34 +752,12 @@ int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C
     if (int rc = timing_events(m, &e0, &e1)) return rc;
     CUDA_OK(cudaEventRecord(e0, st));
   }
-  // SPI_B200_WS_HALVES=2 (experiment, off): two 32-rollout groups per CTA whose leg phases 1 are kept from overlapping by a
-  // token on named barriers (rollout_ws.cuh).  Measured slower than the independent 5-warp CTAs (43.6 vs 41.4 ms at C = 4096;
-  // SPI_B200_WS_TOKEN=0 / 1, i.e. no token / initial stagger only: 42.2 ms) — a leg warp alone issues at ~0.33 IPC, so a
-  // sub-partition needs >= 3 leg warps in phase 1 at once and serialising them starves it (profiles/README.md r2).
-  static const int halves_env = [] { const char* e = getenv("SPI_B200_WS_HALVES"); return e ? atoi(e) : 0; }();
-  const bool two = halves_env == 2;
-  static const int dual_env = [] { const char* e = getenv("SPI_B200_WS_DUAL"); return e ? atoi(e) : -1; }();
-  const bool dual = dual_env >= 0 ? dual_env != 0 : false;
-  if (dual) {
-    static std::atomic<unsigned long long> attr_done{0};
-    int attr_dev = -1;
-    if (attr_needed_on_current_device(&attr_done, &attr_dev)) {
-      CUDA_OK(cudaFuncSetAttribute(ws::rollout_dual_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws::kDualSmemBytes));
-      CUDA_OK(cudaFuncSetAttribute(ws::rollout_dual_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws::kDualSmemBytes));
-      attr_mark_done(&attr_done, attr_dev);
-    }
-    const unsigned n2 = (unsigned)((n_cta + 1) / 2);
-    if (minb == 2) ws::rollout_dual_kernel<2><<<n2, ws::kDualThreads, ws::kDualSmemBytes, st>>>(A);
-    else ws::rollout_dual_kernel<3><<<n2, ws::kDualThreads, ws::kDualSmemBytes, st>>>(A);
-  } else if (two) {
-    const unsigned n2 = (unsigned)((n_cta + 1) / 2);
-    if (minb == 1) ws::rollout_ws2_kernel<1><<<n2, 2 * ws::kWsThreads, 0, st>>>(A);
-    else ws::rollout_ws2_kernel<2><<<n2, 2 * ws::kWsThreads, 0, st>>>(A);
-  } else if (minb == 2 || (minb == 0 && n_cta <= 2LL * m->sm_count))
+  if (minb == 2 || (minb == 0 && n_cta <= 2LL * m->sm_count))
     // small grids (a mass_opt trial is 55 CTAs, the 20-point landscape 1100 -> no: only grids that fit 2 CTAs per SM): the
     // uncapped-register build has the shorter per-CTA latency, and latency is all a sub-wave launch has
     ws::rollout_ws_kernel<false, 2><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
   else if (minb == 3) ws::rollout_ws_kernel<false, 3><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
+  else if (minb == 5) ws::rollout_ws_kernel<false, 5><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
   else ws::rollout_ws_kernel<false, 4><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
   if (int rc = check_launch("rollout_ws_kernel")) return rc;
   if (m->timing) {
@@ -1525,3 +1508,11 @@ int spi_b200_fp32_peak(int iters, float* out_tflops, float* out_ms, void* cuda_s
 }
 
 }  // extern "C"
+
+#if defined(SPI_WS_PROFILE)
+// dev builds only (not part of include/spi_b200.h): device buffer [nblk][5][256] of clock64 stamps for CTAs blk0 .. blk0 + nblk
+extern "C" int spi_b200_debug_ws_prof(long long* buf, int blk0, int nblk) {
+  g_ws_prof = buf; g_ws_prof_blk0 = blk0; g_ws_prof_nblk = nblk;
+  return 0;
+}
+#endif

@@ -1,5 +1,5 @@
 """dev helper (not a test): time the rollout kernel at the bench shape and dump the costs, so that two builds / launch
-shapes (SPI_B200_WS_HALVES=1|2, SPI_B200_LIB=...) can be compared bit for bit:  python tools/dev_halves.py TAG [C ...]"""
+shapes (SPI_B200_MINB=2..5, SPI_B200_LIB=...) can be compared bit for bit:  python tools/dev_rollout_time.py TAG [C ...]"""
 import os, sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -28,5 +28,5 @@ for C in [int(x) for x in (sys.argv[2:] or ["4096"])]:
     ms = e0.elapsed_time(e1) / n
     tf = C * S * 311470.87 / ms * 1e3 / 1e12
     np.save(out / f"cost_{tag}_{C}.npy", cost.cpu().numpy())
-    print(f"{tag} halves={os.environ.get('SPI_B200_WS_HALVES','auto')} C={C} ms={ms:.3f} env-steps/s={C*S*5/ms*1e3:.3e} "
+    print(f"{tag} minb={os.environ.get("SPI_B200_MINB","auto")} C={C} ms={ms:.3f} env-steps/s={C*S*5/ms*1e3:.3e} "
           f"alg TFLOP/s={tf:.2f} frac={tf/peak:.3f} (peak {peak:.1f})", flush=True)
