@@ -440,21 +440,21 @@ constexpr int kBcA0 = 0, kBcR = 6, kBcV0 = 15, kBcPz = 21;
 struct LegState { float q[3], qd[3]; };
 struct LegKeep { Keep k1, k2, k3; };
 
-// Parking policy of the leg role: phase 1 produces the joints' Keep records from the calf inwards and only phase 2 reads them
-// again, so a kernel that is short of registers may move each record out of the register file as soon as it is complete
-// (rollout_ws.cuh: shared memory, float4) and bring it back in phase 2.  The default keeps everything in registers.
-struct NoPark {
-  WS_HD void put_calf(const Keep&) const {}
-  WS_HD void put_thigh(const Keep&) const {}
-  WS_HD void get(LegKeep&) const {}
+// Where phase 1 gets the joint torques from.  They are only needed when the inward pass starts (after ~55 % of phase 1), so a
+// source may block there instead of before the phase: the warp-specialised kernel lets the BASE role evaluate the PD law and the
+// motor model of all 12 joints while it would otherwise idle, and the legs pick the result up from shared memory behind a named
+// barrier (rollout_ws.cuh).  TauArray = torques already at hand (host emulation, tests).
+struct TauArray {
+  const float* t;
+  WS_HD void get(float* o) const { o[0] = t[0]; o[1] = t[1]; o[2] = t[2]; }
 };
 
 // ---- leg role, phase 1: outward pass, foot contact, inward pass -> 27 floats for the base ------------------
 // Rv0[22] = the base broadcast (a0 unused here).  out[27] = hip-projected inertia/force in base coordinates.
 // foot_force (optional): world-frame contact force on this leg's foot.
-template <class PK = NoPark>
-WS_HD void leg_phase1(const SimK& S, const LegK& L, const float* bc, const LegState& s, const float* tau, LegKeep& K,
-                      float* out, float* foot_force, const PK pk = PK()) {
+template <class TS>
+WS_HD void leg_phase1_src(const SimK& S, const LegK& L, const float* bc, const LegState& s, const TS tau_src, LegKeep& K,
+                          float* out, float* foot_force) {
   const float* R = bc + kBcR;
   Twist v0;
 #pragma unroll
@@ -504,13 +504,13 @@ WS_HD void leg_phase1(const SimK& S, const LegK& L, const float* bc, const LegSt
     if (foot_force) { foot_force[0] = F[0]; foot_force[1] = F[1]; foot_force[2] = F[2]; }
   }
   // inward pass up the leg
+  float tau[3];
+  tau_src.get(tau);
   ABI A2, A1, A0;
   abi_from_rigid(L.m[1], L.h[1], L.Io[1], A2);
   calf_inward(L, p3, tau[2], K.k3, A2, p2);
-  pk.put_calf(K.k3);
   abi_from_rigid(L.m[0], L.h[0], L.Io[0], A1);
   joint_inward<1, kMaskThigh, false, true>(A2, p2, tau[1], r1, K.k2, A1, p1);       // A1 = the hip's rigid inertia
-  pk.put_thigh(K.k2);
   Twist p0;
   joint_inward<0, kMaskHip, true>(A1, p1, tau[0], r0, K.k1, A0, p0);
 #pragma unroll
@@ -521,10 +521,13 @@ WS_HD void leg_phase1(const SimK& S, const LegK& L, const float* bc, const LegSt
   for (int i = 0; i < 3; i++) { out[21 + i] = p0.a[i]; out[24 + i] = p0.l[i]; }
 }
 
+WS_HD void leg_phase1(const SimK& S, const LegK& L, const float* bc, const LegState& s, const float* tau, LegKeep& K,
+                      float* out, float* foot_force) {
+  leg_phase1_src(S, L, bc, s, TauArray{tau}, K, out, foot_force);
+}
+
 // ---- leg role, phase 2: acceleration pass + semi-implicit Euler of the 3 joints ------------------------------
-template <class PK = NoPark>
-WS_HD void leg_phase2(const LegK& L, const float* bc, LegKeep& K, LegState& s, float h, const PK pk = PK()) {
-  pk.get(K);
+WS_HD void leg_phase2(const LegK& L, const float* bc, const LegKeep& K, LegState& s, float h) {
   Twist a0, a1, a2, a3;
 #pragma unroll
   for (int i = 0; i < 3; i++) { a0.a[i] = bc[kBcA0 + i]; a0.l[i] = bc[kBcA0 + 3 + i]; }
@@ -702,25 +705,43 @@ WS_HD void base_advance(const SimK& S, const float* a0v, BaseState& s, float h, 
 
 // PD law + torque clip + motor model for one leg's 3 joints
 // (legged_robot_base.py:545,557; go2_omni.py:436-437; active_sysid_openloop.py:184-186,356-400)
-WS_HD void leg_torques(const SimK& S, const LegK& L, const float* act /*clipped*/, const float* q, const float* qd,
-                       const float* kp, const float* kd, const float* motor, int motor_model, unsigned flags, float* tau) {
+// MODEL / TANH_FIRST are compile-time so that the three joints (and, in the base role of rollout_ws.cuh, the four legs) are ONE
+// basic block whose MUFU round trips overlap: with run-time branches per joint every joint was its own serial chain — measured
+// 1 360 cycles per physics step for 3 joints in a leg warp (tools/ws_timeline.py).  motor_inv = rcp_fast(motor), hoisted.
+template <int MODEL, bool TANH_FIRST>
+WS_HD void leg_torques_t(const SimK& S, const LegK& L, const float* act /*clipped*/, const float* q, const float* qd,
+                         const float* kp, const float* kd, const float* motor, const float* motor_inv, float hip_scale,
+                         float* tau) {
 #pragma unroll
   for (int j = 0; j < 3; j++) {
     float as = act[j] * S.action_scale;
-    if (j == 0 && (flags & SPI_FLAG_HIP_HALF)) as *= 0.5f;
+    if (j == 0) as *= hip_scale;
     float t = kp[j] * (as + L.qdef[j] - q[j]) - kd[j] * qd[j];
     const float g = motor[j];
-    if (motor_model == SPI_MOTOR_VEC3_TANH && (flags & SPI_FLAG_TANH_BEFORE_CLIP)) {
-      t = g * tanh_fast(rcp_fast(g) * t);
+    if (MODEL == SPI_MOTOR_VEC3_TANH && TANH_FIRST) {
+      t = g * tanh_fast(motor_inv[j] * t);
       t = fminf(fmaxf(t, -L.tlim[j]), L.tlim[j]);
     } else {
       t = fminf(fmaxf(t, -L.tlim[j]), L.tlim[j]);
-      if (motor_model == SPI_MOTOR_SCALAR) t *= motor[0];
-      else if (motor_model == SPI_MOTOR_VEC3) t *= g;
-      else if (motor_model == SPI_MOTOR_VEC3_TANH) t = g * tanh_fast(rcp_fast(g) * t);
+      if (MODEL == SPI_MOTOR_SCALAR) t *= motor[0];
+      else if (MODEL == SPI_MOTOR_VEC3) t *= g;
+      else if (MODEL == SPI_MOTOR_VEC3_TANH) t = g * tanh_fast(motor_inv[j] * t);
     }
     tau[j] = t;
   }
+}
+
+// run-time dispatch (host emulation, tests); the kernels dispatch once around their unrolled joint loops instead
+WS_HD void leg_torques(const SimK& S, const LegK& L, const float* act /*clipped*/, const float* q, const float* qd,
+                       const float* kp, const float* kd, const float* motor, int motor_model, unsigned flags, float* tau) {
+  const float hip_scale = (flags & SPI_FLAG_HIP_HALF) ? 0.5f : 1.0f;
+  const float inv[3] = {rcp_fast(motor[0]), rcp_fast(motor[1]), rcp_fast(motor[2])};
+  if (motor_model == SPI_MOTOR_VEC3_TANH) {
+    if (flags & SPI_FLAG_TANH_BEFORE_CLIP) leg_torques_t<SPI_MOTOR_VEC3_TANH, true>(S, L, act, q, qd, kp, kd, motor, inv, hip_scale, tau);
+    else leg_torques_t<SPI_MOTOR_VEC3_TANH, false>(S, L, act, q, qd, kp, kd, motor, inv, hip_scale, tau);
+  } else if (motor_model == SPI_MOTOR_SCALAR) leg_torques_t<SPI_MOTOR_SCALAR, false>(S, L, act, q, qd, kp, kd, motor, inv, hip_scale, tau);
+  else if (motor_model == SPI_MOTOR_VEC3) leg_torques_t<SPI_MOTOR_VEC3, false>(S, L, act, q, qd, kp, kd, motor, inv, hip_scale, tau);
+  else leg_torques_t<SPI_MOTOR_NONE, false>(S, L, act, q, qd, kp, kd, motor, inv, hip_scale, tau);
 }
 
 // candidate row -> base rigid inertia (+ head lumps) and motor parameters

@@ -70,32 +70,38 @@ def analyse(t):
     import numpy as np
     nblk = t.shape[0]
     smid = t[:, 0, 0]
-    st = t[:, :, 1:1 + 240].reshape(nblk, WARPS, 40, 6).astype(np.float64)     # [blk, warp, sub-step, stamp]
-    leg, base = st[:, :4], st[:, 4]
-    ok = (leg[:, :, :, 0] > 0).all(axis=(1, 2))
+    # stamps (rollout_ws.cuh, every one predicated on the data of the event):
+    #   leg : 0 state arrived ([B2] released)  1 phase 1 computed  2 published (odd legs: partner arrived + added)
+    #         3 a0 arrived ([B1] released)     4 phase 2 done
+    #   base: 0 torques + bias done  1 pair sums arrived ([A] released)  2 solved  3 [B1] released  4 advanced
+    leg = t[:, :4, 1:1 + 200].reshape(nblk, 4, 40, 5).astype(np.float64)
+    base = t[:, 4, 1:1 + 200].reshape(nblk, 40, 5).astype(np.float64)
+    ok = (leg[:, :, :, 0] > 0).all(axis=(1, 2)) & (base[:, :, 0] > 0).all(axis=1)
     leg, base, smid = leg[ok], base[ok], smid[ok]
     print(f"{ok.sum()} of {nblk} CTAs complete")
     mid = slice(4, 36)
-    def m(x): return f"{np.mean(x):7.0f} (p10 {np.percentile(x, 10):6.0f}, p90 {np.percentile(x, 90):6.0f})"
+    def m(x): return f"{np.mean(x):7.0f} (p10 {np.percentile(x, 10):6.0f}, p50 {np.percentile(x, 50):6.0f}, p90 {np.percentile(x, 90):6.0f})"
     rnd = leg[:, :, 1:, 0] - leg[:, :, :-1, 0]
-    print("round (phase-1 start to phase-1 start)     ", m(rnd[:, :, mid]))
-    print("leg: phase 1 compute                       ", m((leg[..., 1] - leg[..., 0])[:, :, mid]))
-    print("leg even: publish / odd: pair wait + sum   ", m((leg[:, 0::2, :, 2] - leg[:, 0::2, :, 1])[:, :, mid]), "/",
-          m((leg[:, 1::2, :, 2] - leg[:, 1::2, :, 1])[:, :, mid]))
-    print("leg: wait at [A]                           ", m((leg[..., 3] - leg[..., 2])[:, :, mid]))
-    print("leg: wait at [B1] (base solve)             ", m((leg[..., 4] - leg[..., 3])[:, :, mid]))
-    print("leg: phase 2                               ", m((leg[..., 5] - leg[..., 4])[:, :, mid]))
-    print("leg: wait at [B2]                          ", m((leg[:, :, 1:, 0] - leg[:, :, :-1, 5])[:, :, mid]))
-    print("base: wait at [A]                          ", m((base[..., 1] - base[..., 0])[:, mid]))
-    print("base: load + solve + store                 ", m((base[..., 2] - base[..., 1])[:, mid]))
-    print("base: [B1] barrier                         ", m((base[..., 3] - base[..., 2])[:, mid]))
-    print("base: advance                              ", m((base[..., 4] - base[..., 3])[:, mid]))
-    print("base: wait at [B2]                         ", m((base[..., 5] - base[..., 4])[:, mid]))
-    print("base: bias of the next sub-step            ", m((base[:, 1:, 0] - base[:, :-1, 5])[:, mid]))
-    last_leg = leg[..., 2].max(axis=1)
-    print("critical: last leg published -> [A] release (base) ", m((base[..., 1] - last_leg)[:, mid]))
-    print("critical: last leg published -> legs leave [B1]    ", m((leg[..., 4].min(axis=1) - last_leg)[:, mid]))
-    print("slowest - fastest leg at [A]               ", m((leg[..., 2].max(axis=1) - leg[..., 2].min(axis=1))[:, mid]))
+    print("round (state arrived -> state arrived)           ", m(rnd[:, :, mid]))
+    print("leg: phase 1 compute                             ", m((leg[..., 1] - leg[..., 0])[:, :, mid]))
+    print("leg even: publish                                ", m((leg[:, 0::2, :, 2] - leg[:, 0::2, :, 1])[:, :, mid]))
+    print("leg odd: wait for the partner + add + publish    ", m((leg[:, 1::2, :, 2] - leg[:, 1::2, :, 1])[:, :, mid]))
+    print("leg: published -> a0 arrived ([A] + solve + [B1])", m((leg[..., 3] - leg[..., 2])[:, :, mid]))
+    print("leg: phase 2 compute                             ", m((leg[..., 4] - leg[..., 3])[:, :, mid]))
+    print("leg: phase 2 done -> next state arrived ([B2])   ", m((leg[:, :, 1:, 0] - leg[:, :, :-1, 4])[:, :, mid]))
+    last_pub = leg[..., 2].max(axis=1)
+    first_pub = leg[..., 2].min(axis=1)
+    print("slowest - fastest leg published                  ", m((last_pub - first_pub)[:, mid]))
+    print("base: bias done -> pair sums arrived (wait [A])  ", m((base[..., 1] - base[..., 0])[:, mid]))
+    print("CRITICAL last leg published -> base has the sums ", m((base[..., 1] - last_pub)[:, mid]))
+    print("CRITICAL base: solve                             ", m((base[..., 2] - base[..., 1])[:, mid]))
+    print("CRITICAL solved -> first leg has a0              ", m((leg[..., 3].min(axis=1) - base[..., 2])[:, mid]))
+    print("         solved -> last leg has a0               ", m((leg[..., 3].max(axis=1) - base[..., 2])[:, mid]))
+    print("base: solved -> [B1] released                    ", m((base[..., 3] - base[..., 2])[:, mid]))
+    print("base: advance                                    ", m((base[..., 4] - base[..., 3])[:, mid]))
+    print("base: advanced -> torques + bias of the next done", m((base[:, 1:, 0] - base[:, :-1, 4])[:, mid]))
+    print("last leg phase 2 done -> first leg next state    ", m((leg[:, :, 1:, 0].min(axis=1) - leg[:, :, :-1, 4].max(axis=1))[:, mid]))
+    print("base advanced - last leg phase 2 done (>0: legs wait for the base)", m((base[:, :, 4] - leg[..., 4].max(axis=1))[:, mid]))
     # lock-step: for every SM, sample times; count CTAs whose leg 0 is inside [stamp 0, stamp 2) = phase 1
     hist = np.zeros(8)
     resident = np.zeros(8)
@@ -104,11 +110,11 @@ def analyse(t):
         if len(idx) < 4:
             continue
         L = leg[idx]                                   # [n, 4, 40, 6]
-        t0, t1 = L[:, 0, 0, 0].max(), L[:, 0, -1, 5].min()
+        t0, t1 = L[:, 0, 0, 0].max(), L[:, 0, -1, 4].min()
         # the window in which at least 4 CTAs of this SM were recorded concurrently is what we can judge
-        ts = np.linspace(L[:, 0, 0, 0].min(), L[:, 0, -1, 5].max(), 4000)
+        ts = np.linspace(L[:, 0, 0, 0].min(), L[:, 0, -1, 4].max(), 4000)
         for tt in ts:
-            alive = (L[:, 0, 0, 0] <= tt) & (L[:, 0, -1, 5] > tt)
+            alive = (L[:, 0, 0, 0] <= tt) & (L[:, 0, -1, 4] > tt)
             na = int(alive.sum())
             if na != 4:
                 continue
