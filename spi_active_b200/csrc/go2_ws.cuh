@@ -34,11 +34,14 @@ namespace ws {
 WS_HD constexpr int sidx(int i, int j) { return (i == j) ? i : ((i + j == 1) ? 3 : ((i + j == 2) ? 4 : 5)); }
 
 // ---- fast scalar helpers -------------------------------------------------------------------------------
+// MUFU.RCP: max error 1 ulp (2^-23 relative) — as accurate as any other fp32 operation of the recursion.  (Round 1 added a
+// Newton step; its two dependent instructions sat on every serial chain of the kernel — joint projections, the base solve, the
+// motor model — and bought nothing measurable: deviation from the fp64 oracle unchanged, tests/tools/dev_accuracy.py.)
 WS_HD float rcp_fast(float x) {
 #if defined(__CUDA_ARCH__)
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r * fmaf(-x, r, 2.0f);   // one Newton step: full fp32 accuracy without the IEEE slow path
+  return r;
 #else
   return 1.0f / x;
 #endif
@@ -61,6 +64,19 @@ WS_HD float tanh_fast(float x) {
   return copysignf(r, x);
 #else
   return tanhf(x);
+#endif
+}
+// the motor model a tanh(t / a) with k2 = 2 log2(e) / a precomputed: 8 dependent instructions, two of them MUFU
+constexpr float kTwoLog2e = 2.8853900817779268f;
+WS_HD float motor_tanh(float t, float g, float k2) {
+#if defined(__CUDA_ARCH__) && defined(SPI_WS_FAST_TANH)
+  const float ax = fminf(fabsf(t) * k2, 15.0f * kTwoLog2e);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax));
+  const float r = fmaf(-2.0f, rcp_fast(e + 1.0f), 1.0f);
+  return copysignf(g * r, t);
+#else
+  return g * tanhf(t * (k2 * (1.0f / kTwoLog2e)));
 #endif
 }
 
@@ -191,10 +207,10 @@ struct Keep {
 
 // ---- outward pass for one joint: velocity, velocity-product terms, bias force of the rigid body ---------
 template <int AX, int MASK>
-WS_HD void joint_outward(const Twist& vp, const float* r, float q, float qd, float mass, const float* h,
+WS_HD void joint_outward(const Twist& vp, const float* r, float qd, float mass, const float* h,
                          const float* Io, Twist& v, Keep& k, Twist& pA) {
   constexpr int a = Ax<AX>::a, b = Ax<AX>::b, c = Ax<AX>::c;
-  sincos_joint(q, &k.sn, &k.cs);
+  // (k.cs / k.sn of the joint angle are set by leg_angles)
   float t[3] = {vp.l[0], vp.l[1], vp.l[2]};
   add_cross_ar<MASK>(vp.a, r, t);
   rot_down<AX>(k.cs, k.sn, vp.a, v.a);
@@ -440,21 +456,18 @@ constexpr int kBcA0 = 0, kBcR = 6, kBcV0 = 15, kBcPz = 21;
 struct LegState { float q[3], qd[3]; };
 struct LegKeep { Keep k1, k2, k3; };
 
-// Where phase 1 gets the joint torques from.  They are only needed when the inward pass starts (after ~55 % of phase 1), so a
-// source may block there instead of before the phase: the warp-specialised kernel lets the BASE role evaluate the PD law and the
-// motor model of all 12 joints while it would otherwise idle, and the legs pick the result up from shared memory behind a named
-// barrier (rollout_ws.cuh).  TauArray = torques already at hand (host emulation, tests).
-struct TauArray {
-  const float* t;
-  WS_HD void get(float* o) const { o[0] = t[0]; o[1] = t[1]; o[2] = t[2]; }
-};
-
+// sin / cos of the joint angles: the only part of phase 1 that does not need the base state of the sub-step — the kernel
+// evaluates it (and the torques of a new physics step) BEFORE it waits for that state
+WS_HD void leg_angles(const float* q, LegKeep& K) {
+  sincos_joint(q[0], &K.k1.sn, &K.k1.cs);
+  sincos_joint(q[1], &K.k2.sn, &K.k2.cs);
+  sincos_joint(q[2], &K.k3.sn, &K.k3.cs);
+}
 // ---- leg role, phase 1: outward pass, foot contact, inward pass -> 27 floats for the base ------------------
 // Rv0[22] = the base broadcast (a0 unused here).  out[27] = hip-projected inertia/force in base coordinates.
-// foot_force (optional): world-frame contact force on this leg's foot.
-template <class TS>
-WS_HD void leg_phase1_src(const SimK& S, const LegK& L, const float* bc, const LegState& s, const TS tau_src, LegKeep& K,
-                          float* out, float* foot_force) {
+// foot_force (optional): world-frame contact force on this leg's foot.  K.k*.cs / sn must hold sin / cos of the joint angles.
+WS_HD void leg_phase1_core(const SimK& S, const LegK& L, const float* bc, const LegState& s, const float* tau, LegKeep& K,
+                           float* out, float* foot_force) {
   const float* R = bc + kBcR;
   Twist v0;
 #pragma unroll
@@ -462,9 +475,9 @@ WS_HD void leg_phase1_src(const SimK& S, const LegK& L, const float* bc, const L
   float r0[3], r1[3], r2[3];
   joint_r(L, 0, r0); joint_r(L, 1, r1); joint_r(L, 2, r2);
   Twist v1, v2, v3, p1, p2, p3;
-  joint_outward<0, kMaskHip>(v0, r0, s.q[0], s.qd[0], L.m[0], L.h[0], L.Io[0], v1, K.k1, p1);
-  joint_outward<1, kMaskThigh>(v1, r1, s.q[1], s.qd[1], L.m[1], L.h[1], L.Io[1], v2, K.k2, p2);
-  joint_outward<1, kMaskCalf>(v2, r2, s.q[2], s.qd[2], L.m[2], L.h[2], L.Io[2], v3, K.k3, p3);
+  joint_outward<0, kMaskHip>(v0, r0, s.qd[0], L.m[0], L.h[0], L.Io[0], v1, K.k1, p1);
+  joint_outward<1, kMaskThigh>(v1, r1, s.qd[1], L.m[1], L.h[1], L.Io[1], v2, K.k2, p2);
+  joint_outward<1, kMaskCalf>(v2, r2, s.qd[2], L.m[2], L.h[2], L.Io[2], v3, K.k3, p3);
   // foot contact (compliant sphere on the plane z = 0)
   {
     float t3[3], t2[3], t1[3], u3[3], u2[3];
@@ -504,8 +517,6 @@ WS_HD void leg_phase1_src(const SimK& S, const LegK& L, const float* bc, const L
     if (foot_force) { foot_force[0] = F[0]; foot_force[1] = F[1]; foot_force[2] = F[2]; }
   }
   // inward pass up the leg
-  float tau[3];
-  tau_src.get(tau);
   ABI A2, A1, A0;
   abi_from_rigid(L.m[1], L.h[1], L.Io[1], A2);
   calf_inward(L, p3, tau[2], K.k3, A2, p2);
@@ -523,7 +534,8 @@ WS_HD void leg_phase1_src(const SimK& S, const LegK& L, const float* bc, const L
 
 WS_HD void leg_phase1(const SimK& S, const LegK& L, const float* bc, const LegState& s, const float* tau, LegKeep& K,
                       float* out, float* foot_force) {
-  leg_phase1_src(S, L, bc, s, TauArray{tau}, K, out, foot_force);
+  leg_angles(s.q, K);
+  leg_phase1_core(S, L, bc, s, tau, K, out, foot_force);
 }
 
 // ---- leg role, phase 2: acceleration pass + semi-implicit Euler of the 3 joints ------------------------------
@@ -705,43 +717,58 @@ WS_HD void base_advance(const SimK& S, const float* a0v, BaseState& s, float h, 
 
 // PD law + torque clip + motor model for one leg's 3 joints
 // (legged_robot_base.py:545,557; go2_omni.py:436-437; active_sysid_openloop.py:184-186,356-400)
-// MODEL / TANH_FIRST are compile-time so that the three joints (and, in the base role of rollout_ws.cuh, the four legs) are ONE
-// basic block whose MUFU round trips overlap: with run-time branches per joint every joint was its own serial chain — measured
-// 1 360 cycles per physics step for 3 joints in a leg warp (tools/ws_timeline.py).  motor_inv = rcp_fast(motor), hoisted.
-template <int MODEL, bool TANH_FIRST>
-WS_HD void leg_torques_t(const SimK& S, const LegK& L, const float* act /*clipped*/, const float* q, const float* qd,
-                         const float* kp, const float* kd, const float* motor, const float* motor_inv, float hip_scale,
-                         float* tau) {
+// The evaluation sits in front of the dynamics of every physics step as a serial section of the leg warp, so it is kept short:
+//   * MODEL / TANH_FIRST are compile-time: the three joints are ONE basic block whose MUFU round trips overlap (with run-time
+//     branches per joint every joint was its own serial chain: 1 360 cycles per physics step, tools/ws_timeline.py);
+//   * what only changes with the control step is precomputed once per control step (leg_pd_bias): kp (a s + q_default);
+//   * what never changes is precomputed once per rollout: k2 = 2 log2(e) / motor gain.
+WS_HD void leg_pd_bias(const SimK& S, const LegK& L, const float* act /*clipped*/, const float* kp, float hip_scale, float* pdb) {
 #pragma unroll
   for (int j = 0; j < 3; j++) {
     float as = act[j] * S.action_scale;
     if (j == 0) as *= hip_scale;
-    float t = kp[j] * (as + L.qdef[j] - q[j]) - kd[j] * qd[j];
+    pdb[j] = kp[j] * (as + L.qdef[j]);
+  }
+}
+template <int MODEL, bool TANH_FIRST>
+WS_HD void leg_torques_t(const LegK& L, const float* pdb, const float* q, const float* qd, const float* kp, const float* kd,
+                         const float* motor, const float* motor_k2, float* tau) {
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    float t = fmaf(-kd[j], qd[j], fmaf(-kp[j], q[j], pdb[j]));      // kp (a s + q_default - q) - kd qd
     const float g = motor[j];
     if (MODEL == SPI_MOTOR_VEC3_TANH && TANH_FIRST) {
-      t = g * tanh_fast(motor_inv[j] * t);
+      t = motor_tanh(t, g, motor_k2[j]);
       t = fminf(fmaxf(t, -L.tlim[j]), L.tlim[j]);
     } else {
       t = fminf(fmaxf(t, -L.tlim[j]), L.tlim[j]);
       if (MODEL == SPI_MOTOR_SCALAR) t *= motor[0];
       else if (MODEL == SPI_MOTOR_VEC3) t *= g;
-      else if (MODEL == SPI_MOTOR_VEC3_TANH) t = g * tanh_fast(motor_inv[j] * t);
+      else if (MODEL == SPI_MOTOR_VEC3_TANH) t = motor_tanh(t, g, motor_k2[j]);
     }
     tau[j] = t;
   }
 }
+// the motor model is dispatched AROUND the joint loop
+WS_HD void leg_torques_dispatch(const LegK& L, const float* pdb, const float* q, const float* qd, const float* kp,
+                                const float* kd, const float* motor, const float* motor_k2, int motor_model, unsigned flags,
+                                float* tau) {
+  if (motor_model == SPI_MOTOR_VEC3_TANH) {
+    if (flags & SPI_FLAG_TANH_BEFORE_CLIP) leg_torques_t<SPI_MOTOR_VEC3_TANH, true>(L, pdb, q, qd, kp, kd, motor, motor_k2, tau);
+    else leg_torques_t<SPI_MOTOR_VEC3_TANH, false>(L, pdb, q, qd, kp, kd, motor, motor_k2, tau);
+  } else if (motor_model == SPI_MOTOR_SCALAR) leg_torques_t<SPI_MOTOR_SCALAR, false>(L, pdb, q, qd, kp, kd, motor, motor_k2, tau);
+  else if (motor_model == SPI_MOTOR_VEC3) leg_torques_t<SPI_MOTOR_VEC3, false>(L, pdb, q, qd, kp, kd, motor, motor_k2, tau);
+  else leg_torques_t<SPI_MOTOR_NONE, false>(L, pdb, q, qd, kp, kd, motor, motor_k2, tau);
+}
 
-// run-time dispatch (host emulation, tests); the kernels dispatch once around their unrolled joint loops instead
+// everything from the clipped action (host emulation, tests)
 WS_HD void leg_torques(const SimK& S, const LegK& L, const float* act /*clipped*/, const float* q, const float* qd,
                        const float* kp, const float* kd, const float* motor, int motor_model, unsigned flags, float* tau) {
-  const float hip_scale = (flags & SPI_FLAG_HIP_HALF) ? 0.5f : 1.0f;
-  const float inv[3] = {rcp_fast(motor[0]), rcp_fast(motor[1]), rcp_fast(motor[2])};
-  if (motor_model == SPI_MOTOR_VEC3_TANH) {
-    if (flags & SPI_FLAG_TANH_BEFORE_CLIP) leg_torques_t<SPI_MOTOR_VEC3_TANH, true>(S, L, act, q, qd, kp, kd, motor, inv, hip_scale, tau);
-    else leg_torques_t<SPI_MOTOR_VEC3_TANH, false>(S, L, act, q, qd, kp, kd, motor, inv, hip_scale, tau);
-  } else if (motor_model == SPI_MOTOR_SCALAR) leg_torques_t<SPI_MOTOR_SCALAR, false>(S, L, act, q, qd, kp, kd, motor, inv, hip_scale, tau);
-  else if (motor_model == SPI_MOTOR_VEC3) leg_torques_t<SPI_MOTOR_VEC3, false>(S, L, act, q, qd, kp, kd, motor, inv, hip_scale, tau);
-  else leg_torques_t<SPI_MOTOR_NONE, false>(S, L, act, q, qd, kp, kd, motor, inv, hip_scale, tau);
+  float pdb[3], k2[3];
+  leg_pd_bias(S, L, act, kp, (flags & SPI_FLAG_HIP_HALF) ? 0.5f : 1.0f, pdb);
+#pragma unroll
+  for (int j = 0; j < 3; j++) k2[j] = kTwoLog2e * rcp_fast(motor[j]);
+  leg_torques_dispatch(L, pdb, q, qd, kp, kd, motor, k2, motor_model, flags, tau);
 }
 
 // candidate row -> base rigid inertia (+ head lumps) and motor parameters

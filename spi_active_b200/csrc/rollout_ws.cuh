@@ -135,8 +135,8 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, const W
                                             int c, int seg, bool active) {
   const SimK& S = A.M.sim;
   const LegK& L = A.M.leg[LEG];
-  // this leg's motor parameters (act2tau_scalar uses one gain for every joint) and their reciprocals
-  float motor[3], motor_inv[3];
+  // this leg's motor parameters (act2tau_scalar uses one gain for every joint) and k2 = 2 log2(e) / gain
+  float motor[3], motor_k2[3];
   {
     float m3[3] = {20.0f, 20.0f, 20.0f};
     if (A.params) {
@@ -149,7 +149,7 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, const W
       }
     }
 #pragma unroll
-    for (int j = 0; j < 3; j++) { motor[j] = m3[j]; motor_inv[j] = rcp_fast(m3[j]); }
+    for (int j = 0; j < 3; j++) { motor[j] = m3[j]; motor_k2[j] = kTwoLog2e * rcp_fast(m3[j]); }
   }
   const float hip_scale = (A.flags & SPI_FLAG_HIP_HALF) ? 0.5f : 1.0f;
   LegState s;
@@ -170,24 +170,27 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, const W
   const float* act_row = A.seg_actions + (size_t)seg * A.H * 12 + 3 * LEG;
   LegKeep K;
   const bool zero_act = A.zero_mask && A.zero_mask[seg] != 0;
+  // (Measured and dropped, profiles/README.md r2: evaluating the torques / sin / cos of the next sub-step in the TAIL of the
+  // previous one, in front of [B2] — the legs hardly wait there, so it only delays the barrier: 39.9 ms vs 39.2 ms; parking the
+  // PD bias / gains / motor gains in shared memory: 39.2 - 39.4 ms, and the extra 4 KB per CTA keep a rollout CTA from sharing an
+  // SM with an actor-MLP CTA in the pipelined exploration rollout; 5 CTAs per SM at 72 registers: 40.8 ms, 3 at 126: 43.1 ms.)
   WS_PROF_INIT(LEG);
   bars.cta();   // [S0] the base role has published R / v0 / pz of the initial state
   for (int k = 0; k < A.H; k++) {
-    float act[3];
+    float pdb[3];        // kp (a s + q_default): what the PD law needs of the control step
+    {
+      float act[3];
 #pragma unroll
-    for (int j = 0; j < 3; j++)
-      act[j] = zero_act ? 0.f : fminf(fmaxf(__ldg(act_row + 12 * k + j), -S.action_clip), S.action_clip);
+      for (int j = 0; j < 3; j++)
+        act[j] = zero_act ? 0.f : fminf(fmaxf(__ldg(act_row + 12 * k + j), -S.action_clip), S.action_clip);
+      // the next control step's actions: into L1 now, so that their load is a hit (L2: ~800 cycles under load)
+      if (k + 1 < A.H) asm volatile("prefetch.global.L1 [%0];" ::"l"(act_row + 12 * (k + 1)));
+      leg_pd_bias(S, L, act, kp, hip_scale, pdb);
+    }
     for (int d = 0; d < A.decimation; d++) {
-      // PD law + clip + motor model, once per physics step.  The motor model is dispatched AROUND the joint loop: with the
-      // branches inside it every joint was its own serial chain of three MUFU round trips between branches — measured
-      // 1 360 cycles per physics step in which the warp issued ~45 instructions (tools/ws_timeline.py, profiles/README.md r2)
+      // PD law + clip + motor model, once per physics step (go2_ws.cuh: leg_torques_t)
       float tau[3];
-      if (A.motor_model == SPI_MOTOR_VEC3_TANH) {
-        if (A.flags & SPI_FLAG_TANH_BEFORE_CLIP) leg_torques_t<SPI_MOTOR_VEC3_TANH, true>(S, L, act, s.q, s.qd, kp, kd, motor, motor_inv, hip_scale, tau);
-        else leg_torques_t<SPI_MOTOR_VEC3_TANH, false>(S, L, act, s.q, s.qd, kp, kd, motor, motor_inv, hip_scale, tau);
-      } else if (A.motor_model == SPI_MOTOR_SCALAR) leg_torques_t<SPI_MOTOR_SCALAR, false>(S, L, act, s.q, s.qd, kp, kd, motor, motor_inv, hip_scale, tau);
-      else if (A.motor_model == SPI_MOTOR_VEC3) leg_torques_t<SPI_MOTOR_VEC3, false>(S, L, act, s.q, s.qd, kp, kd, motor, motor_inv, hip_scale, tau);
-      else leg_torques_t<SPI_MOTOR_NONE, false>(S, L, act, s.q, s.qd, kp, kd, motor, motor_inv, hip_scale, tau);
+      leg_torques_dispatch(L, pdb, s.q, s.qd, kp, kd, motor, motor_k2, A.motor_model, A.flags, tau);
       for (int n = 0; n < S.nsub; n++) {
         float bc[kBaseOut];
         ws_load_state(sm, lane, bc);
@@ -225,13 +228,10 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, const W
         bars.cta();   // [B2] the base role has published R / v0 / pz of the new state
       }
     }
-    if (RECORD) {
-      if (active) {
-        float* row = A.out_states + (((size_t)(A.paired ? 0 : c) * A.S + seg) * A.H + k) * SPI_STATE_DIM;
+    if (RECORD && active) {
+      float* row = A.out_states + (((size_t)(A.paired ? 0 : c) * A.S + seg) * A.H + k) * SPI_STATE_DIM;
 #pragma unroll
-        for (int j = 0; j < 3; j++) { row[13 + 3 * LEG + j] = s.q[j]; row[25 + 3 * LEG + j] = s.qd[j]; }
-      }
-      bars.cta();   // [R] keeps the barrier count of the base role (which writes its rows here)
+      for (int j = 0; j < 3; j++) { row[13 + 3 * LEG + j] = s.q[j]; row[25 + 3 * LEG + j] = s.qd[j]; }
     }
   }
   if (RECORD) return;
@@ -324,7 +324,6 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, const 
 #pragma unroll
         for (int i = 0; i < 4; i++) row[3 + i] = s.quat[i];
       }
-      bars.cta();   // [R]
     }
   }
   if (RECORD) return;
