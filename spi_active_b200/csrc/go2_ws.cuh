@@ -84,6 +84,7 @@ WS_HD void sincos_joint(float q, float* s, float* c) {
 #if defined(__CUDA_ARCH__)
 #if defined(SPI_WS_FAST_SINCOS)
   // MUFU path: reduce to [-pi, pi] (joint angles are bounded, |q| < ~5), abs error <= 2^-21
+  // (measured r2: __sincosf without the explicit reduction is 12 instructions shorter per sub-step and 1.2 - 1.9 % SLOWER)
   const float k = rintf(q * 0.15915494309189535f);
   float r = fmaf(k, -6.2831854820251465f, q);
   r = fmaf(k, 1.7484555314695172e-07f, r);
