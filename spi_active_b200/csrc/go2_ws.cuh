@@ -124,6 +124,12 @@ struct alignas(16) LegK {
   float cMa[6], pad_ma[2];         // projected linear block, symmetric storage
   float cUadb, cUadc, pad_ud[2];   // U / D of the calf joint (what phase 2 multiplies with): angular b, c and
   float cUld[3], pad_uld;          // linear components
+#if defined(SPI_WS_CALF_HARMONIC)
+  // thigh articulated inertia BEFORE its own projection = thigh rigid inertia + the calf's constant projected inertia
+  // rotated by the calf angle and shifted by rc: every entry is a trigonometric polynomial a + b cos q + c sin q +
+  // d cos 2q + e sin 2q of the calf angle; the non-zero coefficients (calf_mask), packed in entry order
+  float calfA2[64];
+#endif
 };
 static_assert(sizeof(LegK) % 16 == 0, "LegK must keep 16-byte alignment in the leg array");
 
@@ -274,10 +280,15 @@ WS_HD void force_to_parent(const float* pa_a, const float* pa_l, float cs, float
 // PARENT_ZERO: IAp / pAp hold nothing yet (the hip's parent is the base, whose own inertia the base role adds) — the results
 // are assigned instead of added to zeros.  PARENT_RIGID: IAp was filled by abi_from_rigid, i.e. M is diagonal and H is skew —
 // the structurally zero entries are assigned as well (x + 0.0f is not folded by the compiler: -0 + 0 = +0).
-template <int AX, int MASK, bool PARENT_ZERO = false, bool PARENT_RIGID = false>
+// AD ("axis-decoupled"): the projected linear block has M[a][b] = M[a][c] = 0 — true for the thigh of a Go2-family leg: its
+// own M is diagonal, and the calf's share has no such entries because the coupling block of a rigid LEAF is skew, so U_l of the
+// calf joint has no component along the (parallel) joint axis — a structural zero for any rigid calf, not a symmetry of the
+// Go2's (tests/test_ws_emulation.py: an asymmetric calf).  The products with those zeros are skipped (x * 0.0f is not folded).
+template <int AX, int MASK, bool PARENT_ZERO = false, bool PARENT_RIGID = false, bool AD = false>
 WS_HD void project_to_parent(const Proj& P, const float* pa_a, const float* pa_l, float cs, float sn, const float* r,
                              ABI& IAp, Twist& pAp) {
   constexpr int a = Ax<AX>::a, b = Ax<AX>::b, c = Ax<AX>::c;
+  auto mzero = [](int i, int j) constexpr { return AD && ((i == a) != (j == a)); };   // M2[i][j] is structurally zero
   // rotate the blocks to parent orientation:  X' = R X R^T
   //   I: only the (b,c) 2x2 block is non-zero; its second rotation is folded into the accumulation of Ip below
   const float t1 = cs * P.Ibb - sn * P.Ibc, t2 = cs * P.Ibc - sn * P.Icc;
@@ -294,8 +305,8 @@ WS_HD void project_to_parent(const Proj& P, const float* pa_a, const float* pa_l
     const float Bbb = cs * P.Ma[sidx(b, b)] - sn * P.Ma[sidx(c, b)], Bbc = cs * P.Ma[sidx(b, c)] - sn * P.Ma[sidx(c, c)];
     const float Bcb = sn * P.Ma[sidx(b, b)] + cs * P.Ma[sidx(c, b)], Bcc = sn * P.Ma[sidx(b, c)] + cs * P.Ma[sidx(c, c)];
     M2[sidx(a, a)] = P.Ma[sidx(a, a)];
-    M2[sidx(a, b)] = cs * P.Ma[sidx(a, b)] - sn * P.Ma[sidx(a, c)];
-    M2[sidx(a, c)] = sn * P.Ma[sidx(a, b)] + cs * P.Ma[sidx(a, c)];
+    M2[sidx(a, b)] = AD ? 0.f : cs * P.Ma[sidx(a, b)] - sn * P.Ma[sidx(a, c)];
+    M2[sidx(a, c)] = AD ? 0.f : sn * P.Ma[sidx(a, b)] + cs * P.Ma[sidx(a, c)];
     M2[sidx(b, b)] = cs * Bbb - sn * Bbc;
     M2[sidx(b, c)] = sn * Bbb + cs * Bbc;
     M2[sidx(c, c)] = sn * Bcb + cs * Bcc;
@@ -310,8 +321,8 @@ WS_HD void project_to_parent(const Proj& P, const float* pa_a, const float* pa_l
     for (int j = 0; j < 3; j++) {
       float v = (i == b) ? H2b[j] : ((i == c) ? H2c[j] : 0.f);
       bool have = (i != a);
-      if ((MASK >> i1) & 1) { v = have ? fmaf(r[i1], M2[sidx(i2, j)], v) : r[i1] * M2[sidx(i2, j)]; have = true; }
-      if ((MASK >> i2) & 1) { v = have ? fmaf(-r[i2], M2[sidx(i1, j)], v) : -(r[i2] * M2[sidx(i1, j)]); have = true; }
+      if (((MASK >> i1) & 1) && !mzero(i2, j)) { v = have ? fmaf(r[i1], M2[sidx(i2, j)], v) : r[i1] * M2[sidx(i2, j)]; have = true; }
+      if (((MASK >> i2) & 1) && !mzero(i1, j)) { v = have ? fmaf(-r[i2], M2[sidx(i1, j)], v) : -(r[i2] * M2[sidx(i1, j)]); have = true; }
       Hp[3 * i + j] = have ? v : 0.f;
     }
   }
@@ -364,7 +375,9 @@ WS_HD void project_to_parent(const Proj& P, const float* pa_a, const float* pa_l
 }
 
 // ---- inward pass for a joint with a state-dependent articulated inertia (hip, thigh) ------------------------
-template <int AX, int MASK, bool PARENT_ZERO = false, bool PARENT_RIGID = false>
+// AD: IA has H[a][a] = 0 and M[a][b] = M[a][c] = 0 (see project_to_parent); then U_l[a] = 0 and the a-row / a-column of the
+// projected linear block is the one of IA.
+template <int AX, int MASK, bool PARENT_ZERO = false, bool PARENT_RIGID = false, bool AD = false>
 WS_HD void joint_inward(const ABI& IA, const Twist& pA, float tau, const float* r, Keep& k, ABI& IAp, Twist& pAp) {
   constexpr int a = Ax<AX>::a, b = Ax<AX>::b, c = Ax<AX>::c;
   float Ua[3], Ul[3];
@@ -374,20 +387,23 @@ WS_HD void joint_inward(const ABI& IA, const Twist& pA, float tau, const float* 
   const float u = tau - pA.a[a];
   k.Uadb = Ua[b] * dinv; k.Uadc = Ua[c] * dinv;
 #pragma unroll
-  for (int i = 0; i < 3; i++) k.Uld[i] = Ul[i] * dinv;
+  for (int i = 0; i < 3; i++) k.Uld[i] = (AD && i == a) ? 0.f : Ul[i] * dinv;
   Proj P;
   P.Ibb = IA.I[sidx(b, b)] - k.Uadb * Ua[b];
   P.Ibc = IA.I[sidx(b, c)] - k.Uadb * Ua[c];
   P.Icc = IA.I[sidx(c, c)] - k.Uadc * Ua[c];
 #pragma unroll
   for (int j = 0; j < 3; j++) {
-    P.Hb[j] = IA.H[3 * b + j] - k.Uadb * Ul[j];
-    P.Hc[j] = IA.H[3 * c + j] - k.Uadc * Ul[j];
+    P.Hb[j] = (AD && j == a) ? IA.H[3 * b + j] : IA.H[3 * b + j] - k.Uadb * Ul[j];
+    P.Hc[j] = (AD && j == a) ? IA.H[3 * c + j] : IA.H[3 * c + j] - k.Uadc * Ul[j];
   }
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
-    for (int j = i; j < 3; j++) P.Ma[sidx(i, j)] = IA.M[sidx(i, j)] - k.Uld[i] * Ul[j];
+    for (int j = i; j < 3; j++) {
+      if (AD && (i == a || j == a)) P.Ma[sidx(i, j)] = (i == j) ? IA.M[sidx(i, j)] : 0.f;
+      else P.Ma[sidx(i, j)] = IA.M[sidx(i, j)] - k.Uld[i] * Ul[j];
+    }
   // pa = pA + Ia c + U u / D     (c has no component along a;  pA[a] + U[a] u / D = pA[a] + u = tau)
   const float ud = u * dinv;
   k.ud = ud;
@@ -396,9 +412,11 @@ WS_HD void joint_inward(const ABI& IA, const Twist& pA, float tau, const float* 
   pa_a[b] = pA.a[b] + P.Ibb * k.cab + P.Ibc * k.cac + P.Hb[b] * k.clb + P.Hb[c] * k.clc + ud * Ua[b];
   pa_a[c] = pA.a[c] + P.Ibc * k.cab + P.Icc * k.cac + P.Hc[b] * k.clb + P.Hc[c] * k.clc + ud * Ua[c];
 #pragma unroll
-  for (int j = 0; j < 3; j++)
-    pa_l[j] = pA.l[j] + P.Hb[j] * k.cab + P.Hc[j] * k.cac + P.Ma[sidx(j, b)] * k.clb + P.Ma[sidx(j, c)] * k.clc + ud * Ul[j];
-  project_to_parent<AX, MASK, PARENT_ZERO, PARENT_RIGID>(P, pa_a, pa_l, k.cs, k.sn, r, IAp, pAp);
+  for (int j = 0; j < 3; j++) {
+    if (AD && j == a) pa_l[j] = pA.l[j] + P.Hb[j] * k.cab + P.Hc[j] * k.cac;
+    else pa_l[j] = pA.l[j] + P.Hb[j] * k.cab + P.Hc[j] * k.cac + P.Ma[sidx(j, b)] * k.clb + P.Ma[sidx(j, c)] * k.clc + ud * Ul[j];
+  }
+  project_to_parent<AX, MASK, PARENT_ZERO, PARENT_RIGID, AD>(P, pa_a, pa_l, k.cs, k.sn, r, IAp, pAp);
 }
 
 // ---- inward pass for the calf (leaf, axis y): the projection is the per-leg constant in LegK -----------------
@@ -425,8 +443,79 @@ WS_HD void calf_inward(const LegK& L, const Twist& pA, float tau, Keep& k, ABI& 
 }
 
 
+#if defined(SPI_WS_CALF_HARMONIC)
+// ---- the calf's share of the thigh's articulated inertia as harmonics of the calf angle ------------------------------------
+// The calf is a leaf, so its projected inertia is constant in the calf frame; seen from the thigh frame (rotation about y by
+// the calf angle q, shift by (0, 0, rc)) every entry of  thigh rigid inertia + X(q)^T Ia X(q)  is
+//     a + b cos q + c sin q + d cos 2q + e sin 2q
+// with constant coefficients: 38 FFMA replace the rotation / shift of the 21 entries.  calf_mask = which coefficients are
+// non-zero for the Go2-family chain (bit 0 = a ... bit 4 = e; entry order I (xx, yy, zz, xy, xz, yz), H row-major, M (xx, yy,
+// zz, xy, xz, yz)); model_from_blob fits the coefficients by a discrete Fourier sum over the direct evaluation (calf_inward)
+// and refuses the fast path if a masked-out coefficient is not negligible (it cannot be for a rigid calf behind a y-axis joint
+// with a z-only offset — the check guards the derivation, not the model).  `coef` = the leg's 55 packed coefficients: the
+// kernel keeps them in SHARED memory (the leg index is a run-time value, so in the constant bank every coefficient would be
+// its own LDCU — that is what made this formulation slower in the first r2 session; from shared memory they arrive four at
+// a time).
+constexpr int kCalfEntries = 21;
+WS_HD constexpr unsigned calf_mask(int e) {
+  constexpr unsigned m[kCalfEntries] = {31, 25, 25, 25, 31, 25,  25, 7, 25, 25, 0, 25, 25, 7, 25,  25, 1, 25, 0, 24, 0};
+  return m[e];
+}
+WS_HD constexpr int calf_offset(int e, int bit) {   // index of coefficient (e, bit) in the packed array
+  int n = 0;
+  for (int i = 0; i < e; i++)
+    for (int b = 0; b < 5; b++) n += (calf_mask(i) >> b) & 1;
+  for (int b = 0; b < bit; b++) n += (calf_mask(e) >> b) & 1;
+  return n;
+}
+constexpr int kCalfCoefs = calf_offset(kCalfEntries, 0);
+static_assert(kCalfCoefs <= 64, "LegK::calfA2 too small");
+
+WS_HD float& abi_entry(ABI& A, int e) { return e < 6 ? A.I[e] : (e < 15 ? A.H[e - 6] : A.M[e - 15]); }
+
+template <int E> WS_HD float calf_entry(const float* coef, const float* basis) {
+  float v = 0.f;
+  bool have = false;
+#pragma unroll
+  for (int b = 0; b < 5; b++) {
+    if ((calf_mask(E) >> b) & 1) {
+      const float k = coef[calf_offset(E, b)];
+      if (b == 0) v = k;
+      else v = have ? fmaf(k, basis[b], v) : k * basis[b];
+      have = true;
+    }
+  }
+  return v;    // entries without any coefficient are the literal 0.f
+}
+template <int E> WS_HD void calf_entries(const float* coef, const float* basis, ABI& A2) {
+  abi_entry(A2, E) = calf_entry<E>(coef, basis);
+  if constexpr (E + 1 < kCalfEntries) calf_entries<E + 1>(coef, basis, A2);
+}
+WS_HD void calf_inertia_harmonic(const float* coef, float cs, float sn, ABI& A2) {
+  const float basis[5] = {1.f, cs, sn, cs * cs - sn * sn, 2.f * cs * sn};
+  calf_entries<0>(coef, basis, A2);
+}
+#endif   // SPI_WS_CALF_HARMONIC
+
+// the force half of calf_inward: pa = pA + Ia c + U u / D, rotated / shifted to the thigh and added to its bias force
+WS_HD void calf_force(const LegK& L, const Twist& pA, float tau, Keep& k, Twist& pAp) {
+  constexpr int a = 1, b = 2, c = 0;
+  const float ud = (tau - pA.a[a]) * L.cDinv;
+  k.ud = ud;
+  float pa_a[3], pa_l[3];
+  pa_a[a] = tau;
+  pa_a[b] = pA.a[b] + L.cIbb * k.cab + L.cIbc * k.cac + L.cHb[b] * k.clb + L.cHb[c] * k.clc + ud * L.cUa[b];
+  pa_a[c] = pA.a[c] + L.cIbc * k.cab + L.cIcc * k.cac + L.cHc[b] * k.clb + L.cHc[c] * k.clc + ud * L.cUa[c];
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+    pa_l[j] = pA.l[j] + L.cHb[j] * k.cab + L.cHc[j] * k.cac + L.cMa[sidx(j, b)] * k.clb + L.cMa[sidx(j, c)] * k.clc +
+              ud * L.cUl[j];
+  const float r[3] = {0.f, 0.f, L.rc};
+  force_to_parent<1, kMaskCalf>(pa_a, pa_l, k.cs, k.sn, r, pAp);
+}
+
 // ---- outward acceleration pass for one joint --------------------------------------------------------------
-template <int AX, int MASK>
+template <int AX, int MASK, bool AD = false>
 WS_HD float joint_accel(const Twist& ap, const float* r, float Uadb, float Uadc, const float* Uld, const Keep& k, Twist& acc) {
   constexpr int a = Ax<AX>::a, b = Ax<AX>::b, c = Ax<AX>::c;
   float t[3] = {ap.l[0], ap.l[1], ap.l[2]};
@@ -443,7 +532,8 @@ WS_HD float joint_accel(const Twist& ap, const float* r, float Uadb, float Uadc,
   e = fmaf(-Uadb, acc.a[b], e);
   e = fmaf(-Uadc, acc.a[c], e);
 #pragma unroll
-  for (int i = 0; i < 3; i++) e = fmaf(-Uld[i], acc.l[i], e);
+  for (int i = 0; i < 3; i++)
+    if (!(AD && i == a)) e = fmaf(-Uld[i], acc.l[i], e);
   acc.a[a] += e;
   return e;
 }
@@ -467,8 +557,9 @@ WS_HD void leg_angles(const float* q, LegKeep& K) {
 // ---- leg role, phase 1: outward pass, foot contact, inward pass -> 27 floats for the base ------------------
 // Rv0[22] = the base broadcast (a0 unused here).  out[27] = hip-projected inertia/force in base coordinates.
 // foot_force (optional): world-frame contact force on this leg's foot.  K.k*.cs / sn must hold sin / cos of the joint angles.
+// calf_coef (SPI_WS_CALF_HARMONIC builds): the leg's packed harmonic coefficients (LegK::calfA2, or the kernel's shared-memory copy)
 WS_HD void leg_phase1_core(const SimK& S, const LegK& L, const float* bc, const LegState& s, const float* tau, LegKeep& K,
-                           float* out, float* foot_force) {
+                           float* out, float* foot_force, const float* calf_coef = nullptr) {
   const float* R = bc + kBcR;
   Twist v0;
 #pragma unroll
@@ -519,10 +610,19 @@ WS_HD void leg_phase1_core(const SimK& S, const LegK& L, const float* bc, const 
   }
   // inward pass up the leg
   ABI A2, A1, A0;
+#if defined(SPI_WS_CALF_HARMONIC)
+  calf_inertia_harmonic(calf_coef, K.k3.cs, K.k3.sn, A2);
+  calf_force(L, p3, tau[2], K.k3, p2);
+#else
   abi_from_rigid(L.m[1], L.h[1], L.Io[1], A2);
   calf_inward(L, p3, tau[2], K.k3, A2, p2);
+#endif
   abi_from_rigid(L.m[0], L.h[0], L.Io[0], A1);
+#if defined(SPI_WS_CALF_HARMONIC)
+  joint_inward<1, kMaskThigh, false, true, true>(A2, p2, tau[1], r1, K.k2, A1, p1);       // A1 = the hip's rigid inertia
+#else
   joint_inward<1, kMaskThigh, false, true>(A2, p2, tau[1], r1, K.k2, A1, p1);       // A1 = the hip's rigid inertia
+#endif
   Twist p0;
   joint_inward<0, kMaskHip, true>(A1, p1, tau[0], r0, K.k1, A0, p0);
 #pragma unroll
@@ -536,7 +636,11 @@ WS_HD void leg_phase1_core(const SimK& S, const LegK& L, const float* bc, const 
 WS_HD void leg_phase1(const SimK& S, const LegK& L, const float* bc, const LegState& s, const float* tau, LegKeep& K,
                       float* out, float* foot_force) {
   leg_angles(s.q, K);
+#if defined(SPI_WS_CALF_HARMONIC)
+  leg_phase1_core(S, L, bc, s, tau, K, out, foot_force, L.calfA2);
+#else
   leg_phase1_core(S, L, bc, s, tau, K, out, foot_force);
+#endif
 }
 
 // ---- leg role, phase 2: acceleration pass + semi-implicit Euler of the 3 joints ------------------------------
@@ -547,7 +651,11 @@ WS_HD void leg_phase2(const LegK& L, const float* bc, const LegKeep& K, LegState
   float r0[3], r1[3], r2[3];
   joint_r(L, 0, r0); joint_r(L, 1, r1); joint_r(L, 2, r2);
   const float qdd0 = joint_accel<0, kMaskHip>(a0, r0, K.k1.Uadb, K.k1.Uadc, K.k1.Uld, K.k1, a1);
+#if defined(SPI_WS_CALF_HARMONIC)
+  const float qdd1 = joint_accel<1, kMaskThigh, true>(a1, r1, K.k2.Uadb, K.k2.Uadc, K.k2.Uld, K.k2, a2);
+#else
   const float qdd1 = joint_accel<1, kMaskThigh>(a1, r1, K.k2.Uadb, K.k2.Uadc, K.k2.Uld, K.k2, a2);
+#endif
   const float qdd2 = joint_accel<1, kMaskCalf>(a2, r2, L.cUadb, L.cUadc, L.cUld, K.k3, a3);
   s.qd[0] += h * qdd0; s.q[0] += h * s.qd[0];
   s.qd[1] += h * qdd1; s.q[1] += h * s.qd[1];
@@ -820,7 +928,7 @@ WS_HD void apply_candidate(const ModelK& M, const float* row, const ParamIdsK& i
 
 // host-side: blob -> ModelK (incl. the constant calf projection).  Returns 0, or a negative code when the
 // blob does not have the Go2-family structure this fast path is compiled for (the caller then uses the
-// generic leg-per-lane kernel): -1 axes, -2 joint-origin sparsity.
+// generic leg-per-lane kernel): -1 axes, -2 joint-origin sparsity, -3 (SPI_WS_CALF_HARMONIC builds) harmonic structure of the calf's inertia.
 inline int model_from_blob(const float* b, ModelK* M) {
   M->sim.dt = b[SPI_BLOB_DT]; M->sim.gz = b[SPI_BLOB_GRAVITY_Z];
   M->sim.action_scale = b[SPI_BLOB_ACTION_SCALE]; M->sim.action_clip = b[SPI_BLOB_ACTION_CLIP];
@@ -885,6 +993,39 @@ inline int model_from_blob(const float* b, ModelK* M) {
     }
   }
   for (int j = 0; j < 12; j++) { M->kp[j] = b[SPI_BLOB_KP + j]; M->kd[j] = b[SPI_BLOB_KD + j]; }
+#if defined(SPI_WS_CALF_HARMONIC)
+  // harmonic coefficients of the thigh's articulated inertia in the calf angle: discrete Fourier sums (exact for a
+  // trigonometric polynomial of degree 2 sampled at N > 4 equispaced angles) of the direct evaluation, accumulated in double
+  for (int leg = 0; leg < 4; leg++) {
+    LegK& L = M->leg[leg];
+    constexpr int N = 32;
+    double acc[kCalfEntries][5];
+    for (int e = 0; e < kCalfEntries; e++) for (int h = 0; h < 5; h++) acc[e][h] = 0.0;
+    for (int k = 0; k < N; k++) {
+      const double q = 6.283185307179586 * k / N;
+      ABI A2;
+      abi_from_rigid(L.m[1], L.h[1], L.Io[1], A2);
+      Twist p3, p2;
+      for (int i = 0; i < 3; i++) { p3.a[i] = p3.l[i] = 0.f; p2.a[i] = p2.l[i] = 0.f; }
+      Keep kk = Keep();
+      kk.cs = (float)std::cos(q); kk.sn = (float)std::sin(q);
+      calf_inward(L, p3, 0.f, kk, A2, p2);
+      const double basis[5] = {1.0, std::cos(q), std::sin(q), std::cos(2 * q), std::sin(2 * q)};
+      for (int e = 0; e < kCalfEntries; e++)
+        for (int h = 0; h < 5; h++) acc[e][h] += (double)abi_entry(A2, e) * basis[h] * (h == 0 ? 1.0 : 2.0) / N;
+    }
+    for (int i = 0; i < 64; i++) L.calfA2[i] = 0.f;
+    for (int e = 0; e < kCalfEntries; e++) {
+      double scale = 1e-3;      // entries of a block share a physical scale: compare against the largest one of the block
+      const int e0 = e < 6 ? 0 : (e < 15 ? 6 : 15), e1 = e < 6 ? 6 : (e < 15 ? 15 : 21);
+      for (int i = e0; i < e1; i++) for (int h = 0; h < 5; h++) scale = std::fmax(scale, std::fabs(acc[i][h]));
+      for (int h = 0; h < 5; h++) {
+        if ((calf_mask(e) >> h) & 1) L.calfA2[calf_offset(e, h)] = (float)acc[e][h];
+        else if (std::fabs(acc[e][h]) > 2e-6 * scale) return -3;      // not the harmonic structure this path is compiled for
+      }
+    }
+  }
+#endif
   return 0;
 }
 

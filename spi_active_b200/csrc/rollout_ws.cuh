@@ -74,6 +74,9 @@ struct WsSmem {
   float4 bc[kBcStateVec + kBcA0Vec][32];           // base -> legs, per sub-step: [0,4) state of the sub-step, [4,6) a0
   float ej[4][32];                                 // per-leg squared joint error (end of rollout)
   int finite[4][32];
+#if defined(SPI_WS_CALF_HARMONIC)
+  alignas(16) float calf[4][64];                   // per leg: harmonic coefficients of the calf's share of the thigh inertia
+#endif
 };
 static_assert(kBaseOut - kBcR == 4 * kBcStateVec && kBcR == 6 && kBcA0 == 0, "bc packing");
 
@@ -174,6 +177,12 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, const W
   // previous one, in front of [B2] — the legs hardly wait there, so it only delays the barrier: 39.9 ms vs 39.2 ms; parking the
   // PD bias / gains / motor gains in shared memory: 39.2 - 39.4 ms, and the extra 4 KB per CTA keep a rollout CTA from sharing an
   // SM with an actor-MLP CTA in the pipelined exploration rollout; 5 CTAs per SM at 72 registers: 40.8 ms, 3 at 126: 43.1 ms.)
+#if defined(SPI_WS_CALF_HARMONIC)
+  sm.calf[LEG][lane] = L.calfA2[lane];
+  sm.calf[LEG][lane + 32] = L.calfA2[lane + 32];
+  __syncwarp();
+  const float* calf_coef = sm.calf[LEG];
+#endif
   WS_PROF_INIT(LEG);
   bars.cta();   // [S0] the base role has published R / v0 / pz of the initial state
   for (int k = 0; k < A.H; k++) {
@@ -197,7 +206,12 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, const W
         WS_STAMP(bc[kBcPz]);   // 0: [B2] released, the state of the sub-step has arrived: phase 1 starts
         float out[4 * kLegVec];
         out[4 * kLegVec - 1] = 0.f;
-        leg_phase1(S, L, bc, s, tau, K, out, nullptr);
+        leg_angles(s.q, K);
+#if defined(SPI_WS_CALF_HARMONIC)
+        leg_phase1_core(S, L, bc, s, tau, K, out, nullptr, calf_coef);
+#else
+        leg_phase1_core(S, L, bc, s, tau, K, out, nullptr);
+#endif
         WS_STAMP(out[26]);   // 1: phase 1 computed
         // the four legs are summed pairwise: the even leg of a pair publishes and signals (bar.arrive on the pair's own named
         // barrier, 64 threads), the odd leg waits for it, adds its own contribution and publishes the pair sum — the base

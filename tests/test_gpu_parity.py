@@ -238,3 +238,26 @@ def test_argument_errors_and_degenerate_sizes(engine, oracle_lib, blob):
                                         cost_denominator=1.0)
     np.testing.assert_allclose(cost.cpu().numpy(), ref, rtol=5e-5, atol=2e-6)
     assert int(status.item()) == 0
+
+
+@pytest.mark.gpu
+def test_asymmetric_calf_runs_on_the_fast_path(oracle_lib, nominal_model):
+    """The harmonic calf inertia of the fast path (SPI_WS_CALF_HARMONIC) only relies on the joint-axis / joint-offset pattern
+    of the chain, not on a symmetry of the calf: a calf with a lateral centre-of-mass offset and extra products of inertia is
+    accepted by 'ws' and matches the oracle."""
+    import copy
+    from spi_active_b200.engine import RolloutEngine
+    m = copy.deepcopy(nominal_model)
+    for leg in range(4):
+        calf = m.leg_bodies[3 * leg + 2]
+        inertia = list(calf.inertia); inertia[3] += 2e-4; inertia[5] += 2e-4
+        m.leg_bodies[3 * leg + 2] = type(calf)(calf.mass, [calf.com[0], calf.com[1] + 0.03, calf.com[2]], inertia)
+    eng = RolloutEngine(m)
+    eng.set_kernel("ws")
+    S, ds, segs = _segs("sine", 5, eng.device)
+    params = (np.linspace(0.7, 1.5, 5) * 6.921).astype(np.float32)[:, None]
+    cost = eng.evaluate_candidates(torch.from_numpy(params), ["mass"], segs)
+    torch.cuda.synchronize()
+    init, act, tgt, gains, mask, denom = synth.pack_numpy(ds)
+    ref_cost, _ = oracle_lib.eval_candidates(eng.blob, params, [0], init, act, tgt, gains, mask, cost_denominator=denom)
+    np.testing.assert_allclose(cost.cpu().numpy(), ref_cost, rtol=5e-5, atol=2e-6)
