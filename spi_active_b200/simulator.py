@@ -68,6 +68,30 @@ MOVING_BODY_OF_ISAAC_BODY = [0, 1, 2, 3, 3, 4, 5, 6, 6, 0, 0, 7, 8, 9, 9, 10, 11
 ISAAC_BODY_OF_MOVING_BODY = [0, 1, 2, 3, 5, 6, 7, 11, 12, 13, 15, 16, 17]
 
 
+def go2_body_spheres():
+    """Contact spheres for the links that are NOT feet: (Isaac body index, centre in that link's frame, radius), read off the
+    collision geometry of spigym/data/robots/go2/urdf/go2.urdf — the 8 corners of the trunk box (0.3762 x 0.0935 x 0.114), the
+    two head shapes, the hip cylinders (r = 0.046 at y = +-0.08), the two ends of the thigh box (0.11 x 0.0245 x 0.034 along z at
+    z = -0.1065) and of the calf cylinder (r = 0.012, 0.12 long, tilted -0.21 rad about y at (0.008, 0, -0.06)).  Isaac Gym
+    collides those shapes with the plane; here every sphere uses the engine's compliant foot-contact law."""
+    out = []
+    for sx in (-1.0, 1.0):
+        for sy in (-1.0, 1.0):
+            for sz in (-1.0, 1.0):
+                out.append((0, (sx * 0.1881, sy * 0.04675, sz * 0.057), 0.0))
+    out.append((gm.BODY_NAMES.index("Head_upper"), (0.0, 0.0, 0.0), 0.05))
+    out.append((gm.BODY_NAMES.index("Head_lower"), (0.0, 0.0, 0.0), 0.047))
+    ax = (float(np.sin(-0.21)), 0.0, float(np.cos(-0.21)))
+    for leg in gm.LEGS:
+        side = 1.0 if leg[1] == "L" else -1.0
+        out.append((gm.BODY_NAMES.index(f"{leg}_hip"), (0.0, side * 0.08, 0.0), 0.046))
+        for z in (-0.0515, -0.1615):
+            out.append((gm.BODY_NAMES.index(f"{leg}_thigh"), (0.0, 0.0, z), 0.017))
+        for e in (-0.06, 0.06):
+            out.append((gm.BODY_NAMES.index(f"{leg}_calf"), (0.008 + e * ax[0], 0.0, -0.06 + e * ax[2]), 0.012))
+    return out
+
+
 class _RigidBodyProps:
     """The fields of gymapi.RigidBodyProperties the reference touches (mass, com, inertia)."""
 
@@ -152,6 +176,9 @@ class B200Sim(BaseSimulator):
                 if v is not None:
                     setattr(cp, key, cast(v))
         self._backend = backend
+        # b200.contact.body_spheres: collide the non-foot links with the plane as well (go2_body_spheres).  Off by default:
+        # the fused operator (boundary B2) models the feet only, and the two boundaries must agree on recorded data
+        self.body_spheres = go2_body_spheres() if bool(_get(contact_cfg, "body_spheres", False)) else None
         self.inertia_keep = bool(_get(config, "simulator.config.b200.inertia_keep", False))
         self.strict_inertiay = bool(_get(config, "simulator.config.b200.strict_inertiay", False))
         self.params_dict = _get(config, "params_dict")   # isaacgym_active_sysid.py:34
@@ -255,6 +282,11 @@ class B200Sim(BaseSimulator):
         self._torques = z(N, 12)
         self._ext_wrench = None
         self._foot_force = z(N, 4, 3)
+        self._body_contact_force = z(N, 19, 3)      # non-foot contacts (b200.contact.body_spheres), world frame
+        if self.body_spheres is not None:
+            self._sphere_body = torch.tensor([b for b, _, _ in self.body_spheres], device=dev)
+            self._sphere_offset = torch.tensor([o for _, o, _ in self.body_spheres], dtype=torch.float32, device=dev)
+            self._sphere_radius = torch.tensor([r for _, _, r in self.body_spheres], dtype=torch.float32, device=dev)
         self.all_root_states = z(N, 13)
         self.robot_root_states = self.all_root_states            # one actor per env (isaacgym.py:567-571)
         self.base_quat = self.robot_root_states[..., 3:7]
@@ -278,7 +310,7 @@ class B200Sim(BaseSimulator):
     def refresh_sim_tensors(self):
         self.all_root_states.copy_(self._state[:, 0:13])
         self._refresh_dof()
-        self.contact_forces.zero_()
+        self.contact_forces.copy_(self._body_contact_force)
         self.contact_forces[:, self._feet_idx, :] = self._foot_force
         if hasattr(self._backend, "body_states"):                  # all 19 links by forward kinematics (CUDA)
             self._backend.body_states(self._state, out=self._rigid_body_state)
@@ -307,6 +339,27 @@ class B200Sim(BaseSimulator):
         if ds.data_ptr() != self.dof_state.data_ptr():
             self.dof_state.view(self.num_envs, 12, 2)[ids] = ds[ids].to(torch.float32)
 
+    @staticmethod
+    def _rotate(quat, v, inverse=False):
+        """R v (or R^T v) for unit quaternions xyzw, body -> world."""
+        u, w = quat[..., :3], quat[..., 3:4]
+        t = 2.0 * torch.cross(u, v, dim=-1)
+        return v + (-w if inverse else w) * t + torch.cross(u, t, dim=-1)
+
+    def _wrench_from_point_forces(self, body, f, p_world):
+        """World-frame forces f [N,K,3] acting at world positions p_world [N,K,3] on the Isaac bodies body [K] -> one
+        [torque; force] wrench per MOVING body in its own link frame [N,13,6] (feet act on their calf, the head links on the
+        base), the input of spi_b200_sim_step_ext.  self._rigid_body_state must hold the poses of the current state."""
+        N, dev = self.num_envs, self._state.device
+        mb = torch.tensor(MOVING_BODY_OF_ISAAC_BODY, device=dev)[body]                # [K] moving body of every point
+        own = torch.tensor(ISAAC_BODY_OF_MOVING_BODY, device=dev)
+        origin = self._rigid_body_state[:, own, 0:3]                                  # [N,13,3]
+        quat = self._rigid_body_state[:, own, 3:7]                                    # [N,13,4]
+        torque_w = torch.cross(p_world - origin[:, mb], f, dim=-1)                    # about the moving body's link origin
+        fw = torch.zeros(N, 13, 3, device=dev).index_add_(1, mb, f)
+        tw = torch.zeros(N, 13, 3, device=dev).index_add_(1, mb, torque_w)
+        return torch.cat([self._rotate(quat, tw, inverse=True), self._rotate(quat, fw, inverse=True)], dim=-1).contiguous()
+
     def apply_rigid_body_force_at_pos_tensor(self, force_tensor, pos_tensor):
         """isaacgym.py:609-613: forces [N,19,3] on the 19 Isaac Gym bodies at positions [N,19,3] in ENV_SPACE (world axes,
         relative to the env origin), consumed by the NEXT physics step.  Converted here to one [torque; force] wrench per
@@ -320,19 +373,29 @@ class B200Sim(BaseSimulator):
             self._backend.body_states(self._state, out=self._rigid_body_state)       # poses of the CURRENT state
         else:
             raise NotImplementedError("external forces need a backend with body_states")
-        mb = torch.tensor(MOVING_BODY_OF_ISAAC_BODY, device=dev)
-        own = torch.tensor(ISAAC_BODY_OF_MOVING_BODY, device=dev)
-        origin = self._rigid_body_state[:, own, 0:3]                                  # [N,13,3]
-        quat = self._rigid_body_state[:, own, 3:7]                                    # [N,13,4] xyzw, body -> world
-        torque_w = torch.cross(p - origin[:, mb], f, dim=-1)                          # about the moving body's link origin
-        fw = torch.zeros(N, 13, 3, device=dev).index_add_(1, mb, f)
-        tw = torch.zeros(N, 13, 3, device=dev).index_add_(1, mb, torque_w)
+        self._ext_wrench = self._wrench_from_point_forces(torch.arange(19, device=dev), f, p)
 
-        def to_body(v):                                                               # R^T v for unit quaternions
-            u, w = quat[..., :3], quat[..., 3:4]
-            t = 2.0 * torch.cross(u, v, dim=-1)
-            return v - w * t + torch.cross(u, t, dim=-1)
-        self._ext_wrench = torch.cat([to_body(tw), to_body(fw)], dim=-1).contiguous()
+    def _body_sphere_wrench(self):
+        """Non-foot contacts (b200.contact.body_spheres): every sphere of go2_body_spheres() against the plane z = 0 with the
+        engine's foot-contact law (Hunt-Crossley normal force, Coulomb-capped viscous friction; oracle/spi_oracle.hpp foot
+        contact), evaluated on the state at the START of the physics step and held over it through the external-wrench
+        input of the engine (explicit in time: at kn = 1e4 N/m and dt = 5 ms far inside the stability limit of the lightest
+        link).  Returns the wrench [N,13,6] and leaves the per-body world forces in self._body_contact_force."""
+        c = self.model.contact
+        self._backend.body_states(self._state, out=self._rigid_body_state)
+        rb = self._rigid_body_state[:, self._sphere_body]                             # [N,K,13]
+        arm = self._rotate(rb[..., 3:7], self._sphere_offset.expand(self.num_envs, -1, -1))
+        p = rb[..., 0:3] + arm
+        v = rb[..., 7:10] + torch.cross(rb[..., 10:13], arm, dim=-1)
+        depth = self._sphere_radius - p[..., 2]
+        fn = torch.clamp(c.kn * depth * (1.0 - c.cn * v[..., 2]), min=0.0)
+        fn = torch.where(depth > 0, fn, torch.zeros_like(fn))
+        speed = torch.sqrt(v[..., 0] ** 2 + v[..., 1] ** 2 + c.veps ** 2)
+        coef = torch.minimum(torch.full_like(fn, c.dt), c.mu * fn / speed)
+        coef = torch.where(depth > 0, coef, torch.zeros_like(coef))
+        f = torch.stack([-coef * v[..., 0], -coef * v[..., 1], fn], dim=-1)
+        self._body_contact_force.zero_().index_add_(1, self._sphere_body, f)
+        return self._wrench_from_point_forces(self._sphere_body, f, p)
 
     def simulate_at_each_physics_step(self):
         """Advance ONE physics step (sim_dt) under the applied torques, refresh dof_state only
@@ -341,6 +404,9 @@ class B200Sim(BaseSimulator):
             self._upload_params()
         flags = gm.FLAG_INERTIA_KEEP   # the per-env rows already carry the final inertia tensor: never rescale it
         kw = {}
+        if self.body_spheres is not None:
+            w = self._body_sphere_wrench()
+            self._ext_wrench = w if self._ext_wrench is None else self._ext_wrench + w
         if self._ext_wrench is not None:          # consumed by this step only, like Isaac Gym's force tensors
             kw["ext_wrench"], self._ext_wrench = self._ext_wrench, None
         self._backend.sim_step(self._state, self._torques, 1, params=self._params, param_names=self.PARAM_NAMES,

@@ -43,11 +43,13 @@ class OracleBackend:
         pass
 
 
-def _config(num_envs, params_dict=None):
+def _config(num_envs, params_dict=None, body_spheres=False):
     m = gm.go2_nominal()
+    b200 = SimpleNamespace(contact=SimpleNamespace(body_spheres=True)) if body_spheres else None
     return SimpleNamespace(
         num_envs=num_envs, headless=True, params_dict=params_dict,
-        simulator=SimpleNamespace(config=SimpleNamespace(sim=SimpleNamespace(fps=200, control_decimation=4, substeps=1))),
+        simulator=SimpleNamespace(config=SimpleNamespace(sim=SimpleNamespace(fps=200, control_decimation=4, substeps=1),
+                                                         b200=b200)),
         robot=SimpleNamespace(dof_names=list(gm.DOF_NAMES), body_names=list(gm.BODY_NAMES),
                               dof_vel_limit_list=list(m.qd_limit), dof_effort_limit_list=list(m.torque_limit)),
         rewards=SimpleNamespace(reward_limit=SimpleNamespace(soft_dof_pos_limit=0.9)),
@@ -55,8 +57,8 @@ def _config(num_envs, params_dict=None):
         terrain=SimpleNamespace(mesh_type="plane"))
 
 
-def _make_sim(num_envs, device, backend=None, params_dict=None):
-    sim = B200Sim(config=_config(num_envs, params_dict), device=device, backend=backend)
+def _make_sim(num_envs, device, backend=None, params_dict=None, body_spheres=False):
+    sim = B200Sim(config=_config(num_envs, params_dict, body_spheres), device=device, backend=backend)
     sim.set_headless(True)
     sim.setup()
     sim.setup_terrain("plane")
@@ -143,7 +145,8 @@ def test_contact_block_of_the_yaml_reaches_the_model(blob):
     from pathlib import Path
     y = yaml.safe_load((Path(__file__).resolve().parent.parent / "config" / "simulator" / "b200.yaml").read_text())
     d = gm.ContactParams()                      # the shipped yaml states the defaults
-    assert y["simulator"]["config"]["b200"]["contact"] == dict(kn=d.kn, cn=d.cn, mu=d.mu, dt=d.dt, nsub=d.nsub)
+    assert y["simulator"]["config"]["b200"]["contact"] == dict(kn=d.kn, cn=d.cn, mu=d.mu, dt=d.dt, nsub=d.nsub,
+                                                               body_spheres=False)
 
 
 def test_params_dict_overrides(blob):
@@ -325,3 +328,63 @@ def test_external_force_kernel_matches_oracle(engine, oracle_lib, blob, nominal_
     np.testing.assert_allclose(gpu._state.cpu().numpy()[:, :7], cpu._state.numpy()[:, :7], atol=2e-5)
     np.testing.assert_allclose(gpu._state.cpu().numpy()[:, 13:25], cpu._state.numpy()[:, 13:25], atol=2e-5)
     np.testing.assert_allclose(gpu._state.cpu().numpy()[:, 7:13], cpu._state.numpy()[:, 7:13], atol=1e-3)
+
+
+# ---- non-foot contacts (b200.contact.body_spheres; isaacgym.py:577 contact_forces[N, 19, 3]) ----------------------------------
+def _belly_scenario(sim, steps):
+    """Legs folded over the back (feet above the trunk), trunk dropped from 10 cm: the robot can only land on its trunk
+    corners, head and hips.  PD torques hold the folded pose."""
+    N, dev = sim.num_envs, sim.all_root_states.device
+    env_ids = torch.arange(N, device=dev)
+    root = sim.robot_root_states.clone()
+    root[:, 0:3] = torch.tensor([0.0, 0.0, 0.16], device=dev)
+    root[:, 3:7] = torch.tensor([0.0, 0.0, 0.0, 1.0], device=dev)
+    root[:, 7:13] = 0.0
+    sim.set_actor_root_state_tensor(env_ids, root)
+    q_fold = torch.tensor([0.0, 2.6, -0.9] * 4, dtype=torch.float32, device=dev)
+    dof = sim.dof_state.view(N, 12, 2)
+    dof[:, :, 0], dof[:, :, 1] = q_fold, 0.0
+    sim.set_dof_state_tensor(env_ids, sim.dof_state)
+    sim.refresh_sim_tensors()
+    for _ in range(steps):
+        tau = 30.0 * (q_fold - sim.dof_pos) - 0.8 * sim.dof_vel
+        sim.apply_torques_at_dof(torch.clip(tau, -23.7, 23.7))
+        sim.simulate_at_each_physics_step()
+    sim.refresh_sim_tensors()
+
+
+def test_body_spheres_carry_the_robot_on_its_belly(blob, nominal_model):
+    """With b200.contact.body_spheres the trunk / head / hip shapes of the URDF collide with the plane: a robot dropped with
+    its legs folded away comes to rest on them, they carry its weight, and contact_forces reports them on the right bodies;
+    without the option (default, = the fused operator's model) the same robot falls through the plane."""
+    sim, _ = _make_sim(2, "cpu", OracleBackend(blob), body_spheres=True)
+    _belly_scenario(sim, 400)                                   # 2 s
+    weight = float(np.sum(nominal_model.body_masses_isaac_order())) * 9.81
+    cf = sim.contact_forces[0]
+    feet = [sim.find_rigid_body_indice(f"{leg}_foot") for leg in gm.LEGS]
+    assert torch.all(cf[feet] == 0)                             # the feet are in the air
+    assert abs(float(cf[:, 2].sum()) - weight) < 0.03 * weight  # at rest: the body contacts carry the weight
+    assert float(cf[sim.find_rigid_body_indice("base"), 2]) > 0 or float(cf[sim.find_rigid_body_indice("Head_lower"), 2]) > 0
+    z = float(sim.robot_root_states[0, 2])
+    assert 0.04 < z < 0.12, z                                   # lying on the trunk, not fallen through
+    assert float(sim.robot_root_states[0, 7:13].abs().max()) < 0.05
+    # default: feet only -> nothing stops the trunk
+    sim0, _ = _make_sim(1, "cpu", OracleBackend(blob))
+    _belly_scenario(sim0, 100)
+    assert float(sim0.robot_root_states[0, 2]) < 0.0
+    non_feet = [i for i in range(19) if i not in feet]
+    assert torch.all(sim0.contact_forces[:, non_feet] == 0)
+
+
+@pytest.mark.gpu
+def test_body_spheres_on_gpu_match_the_oracle_backend(engine, blob):
+    """The same drop through the CUDA engine (spi_b200_body_states + spi_b200_sim_step_ext) and through the oracle backend."""
+    dev = str(engine.device)
+    sim_g, _ = _make_sim(3, dev, None, body_spheres=True)
+    sim_c, _ = _make_sim(3, "cpu", OracleBackend(blob), body_spheres=True)
+    _belly_scenario(sim_g, 60)
+    _belly_scenario(sim_c, 60)
+    np.testing.assert_allclose(sim_g.robot_root_states.cpu().numpy(), sim_c.robot_root_states.numpy(), atol=2e-3)
+    np.testing.assert_allclose(sim_g.dof_pos.cpu().numpy(), sim_c.dof_pos.numpy(), atol=2e-3)
+    scale = float(sim_c.contact_forces.abs().max())
+    np.testing.assert_allclose(sim_g.contact_forces.cpu().numpy(), sim_c.contact_forces.numpy(), atol=0.02 * scale)
