@@ -1,12 +1,12 @@
 // rollout_ws.cuh — the warp-specialised fused rollout kernel (see go2_ws.cuh for the role arithmetic and
 // DESIGN.md §4.2 for the mapping).  One CTA = 32 (candidate, segment) rollouts x 5 warps:
-//   4 leg warps (lane = rollout) + 1 base warp.  The base role sits on the HIGHEST warp id of the CTA: it is the
-//   critical path between the two leg phases and the sub-partition arbiter favours high warp ids (measured:
-//   +8.6 % over rotating the roles with blockIdx, profiles/README.md).  5-warp CTAs spread over the 4
-//   sub-partitions by themselves.
-// Per integrator sub-step:   legs: phase 1 -> smem[27] | barrier | base: sum, 6x6 solve, integrate ->
-//   a0 -> smem[6] | barrier | legs: phase 2, overlapped with base: integrate, publish R / v0 / pz -> smem[16],
-//   bias force of the next sub-step | barrier.
+//   4 leg warps (lane = rollout) + 1 base warp.  The base role sits on the HIGHEST warp id of the CTA: 5-warp CTAs then spread
+//   over the 4 sub-partitions so that each hosts exactly one base warp and four leg warps of four different CTAs (rotating the
+//   roles with blockIdx clusters base warps: 8.6 % slower, profiles/README.md).
+// Per integrator sub-step:   legs: [torques of a new physics step] phase 1 -> pair sums -> smem[27] | barrier [A] |
+//   base: sum, 6x6 solve -> a0 -> smem[6] | barrier [B1] | legs: phase 2, overlapped with base: integrate, publish
+//   R / v0 / pz -> smem[16] | barrier [B2] | base: bias force of the next sub-step.
+// The kernel is bound by the latency of this round, not by issue bandwidth (tools/ws_timeline.py).
 #pragma once
 #include "go2_ws.cuh"
 
