@@ -26,6 +26,9 @@ HEADERS = [_PKG / "csrc" / "aba_leg.cuh", _PKG / "csrc" / "go2_ws.cuh", _PKG / "
 # leg loop 843 -> 814 instructions, 38.8 -> 38.3 ms; models without that structure fall back to the generic kernel
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-DSPI_WS_FAST_SINCOS",
               "-DSPI_WS_FAST_TANH", "-DSPI_WS_CALF_HARMONIC",
+              # flush-to-zero fp32 (FFMA.FTZ ...): nothing on this path comes near 1e-38, and the rollout kernel is 1 % faster
+              # (38.2 -> 37.9 ms; no change of the deviation from the fp64 oracle)
+              "-ftz=true",
               "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
 
 _lib = None
@@ -42,11 +45,19 @@ def _nvcc() -> str:
     raise SpiB200Error("nvcc not found; cannot build libspi_b200.so")
 
 
+def _flags_stamp() -> Path:
+    return LIB_PATH.with_suffix(".so.flags")
+
+
 def needs_build() -> bool:
+    """Rebuild when a source is newer than the library or when it was built with other compiler flags."""
     if not LIB_PATH.exists():
         return True
     newest = max(p.stat().st_mtime for p in SOURCES + HEADERS)
-    return LIB_PATH.stat().st_mtime < newest
+    if LIB_PATH.stat().st_mtime < newest:
+        return True
+    stamp = _flags_stamp()
+    return not stamp.exists() or stamp.read_text() != " ".join(NVCC_FLAGS)
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
@@ -58,6 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         print(" ".join(cmd)); print(res.stdout)
     if res.returncode != 0:
         raise SpiB200Error(f"nvcc failed:\n{res.stdout}")
+    _flags_stamp().write_text(" ".join(NVCC_FLAGS))
     return LIB_PATH
 
 

@@ -48,7 +48,11 @@ WS_HD float rcp_fast(float x) {
 }
 WS_HD float rsqrt_fast(float x) {
 #if defined(__CUDA_ARCH__)
-  return rsqrtf(x);
+  // bare MUFU.RSQ: rsqrtf() wraps it in a denormal-input rescue (a compare and two predicated multiplies) that sits on the
+  // contact model's dependency chain in the middle of phase 1; its arguments here are >= veps^2 resp. ~1 (measured: 38.3 -> 37.9 ms)
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 #else
   return 1.0f / std::sqrt(x);
 #endif

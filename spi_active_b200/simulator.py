@@ -377,8 +377,8 @@ class B200Sim(BaseSimulator):
 
     def _body_sphere_wrench(self):
         """Non-foot contacts (b200.contact.body_spheres): every sphere of go2_body_spheres() against the plane z = 0 with the
-        engine's foot-contact law (Hunt-Crossley normal force, Coulomb-capped viscous friction; oracle/spi_oracle.hpp foot
-        contact), evaluated on the state at the START of the physics step and held over it through the external-wrench
+        engine's foot-contact law (Hunt-Crossley normal force, Coulomb-capped viscous friction: csrc/go2_ws.cuh),
+        evaluated on the state at the START of the physics step and held over it through the external-wrench
         input of the engine (explicit in time: at kn = 1e4 N/m and dt = 5 ms far inside the stability limit of the lightest
         link).  Returns the wrench [N,13,6] and leaves the per-body world forces in self._body_contact_force."""
         c = self.model.contact
