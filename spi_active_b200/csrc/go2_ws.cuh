@@ -715,6 +715,9 @@ WS_HD void sym3_adjugate(const float* A, float* C, float* det) {   // A, C symme
   C[5] = A[3] * A[4] - A[0] * A[5];
   *det = A[0] * C[0] + A[3] * C[3] + A[4] * C[4];
 }
+// The angular part is solved UNNORMALISED (S' = det(M) S, t' = det(M) t, so that a_w = adj(S') t' / det(S')): the reciprocal of
+// det(M) is then only needed for a_v at the very end and leaves the dependency chain adj(M) -> S -> adj(S) -> a_w, which carries
+// ONE MUFU round trip instead of two in a row (magnitudes: det(M) ~ 3e3, det(S') ~ 1e8 ... 1e10 — far from the fp32 range).
 WS_HD void solve_base(const ABI& A, const Twist& pA, Twist& a0) {
   float Cm[6], detm;
   sym3_adjugate(A.M, Cm, &detm);
@@ -726,21 +729,21 @@ WS_HD void solve_base(const ABI& A, const Twist& pA, Twist& a0) {
 #pragma unroll
     for (int j = 0; j < 3; j++)
       Yc[3 * i + j] = A.H[3 * i] * Cm[sidx(0, j)] + A.H[3 * i + 1] * Cm[sidx(1, j)] + A.H[3 * i + 2] * Cm[sidx(2, j)];
-  // S = I - Y H^T, symmetric
+  // S' = det(M) I - Yc H^T = det(M) (I - Y H^T), symmetric
   float S[6];
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
     for (int j = i; j < 3; j++) {
       const float yh = Yc[3 * i] * A.H[3 * j] + Yc[3 * i + 1] * A.H[3 * j + 1] + Yc[3 * i + 2] * A.H[3 * j + 2];
-      S[sidx(i, j)] = fmaf(-rm, yh, A.I[sidx(i, j)]);
+      S[sidx(i, j)] = fmaf(detm, A.I[sidx(i, j)], -yh);
     }
-  // t = b_w - Y b_v  with b = -pA:  t = -pA.a + Y pA.l
+  // t' = det(M) (b_w - Y b_v)  with b = -pA:  t' = -det(M) pA.a + Yc pA.l
   float t[3];
 #pragma unroll
   for (int i = 0; i < 3; i++) {
     const float yb = Yc[3 * i] * pA.l[0] + Yc[3 * i + 1] * pA.l[1] + Yc[3 * i + 2] * pA.l[2];
-    t[i] = fmaf(rm, yb, -pA.a[i]);
+    t[i] = fmaf(-detm, pA.a[i], yb);
   }
   float Cs[6], dets;
   sym3_adjugate(S, Cs, &dets);
@@ -748,13 +751,14 @@ WS_HD void solve_base(const ABI& A, const Twist& pA, Twist& a0) {
 #pragma unroll
   for (int i = 0; i < 3; i++)
     a0.a[i] = (Cs[sidx(i, 0)] * t[0] + Cs[sidx(i, 1)] * t[1] + Cs[sidx(i, 2)] * t[2]) * rs;
-  // a_v = Minv (b_v - H^T a_w) = -adj(M) (pA.l + H^T a_w) / det M
-  float u[3];
+  // a_v = Minv (b_v - H^T a_w) = -(adj(M) pA.l + Yc^T a_w) / det M   (adj(M) H^T = Yc^T): the first product does not wait for
+  // a_w, so only one 3-term chain and a scale follow it
 #pragma unroll
-  for (int j = 0; j < 3; j++) u[j] = pA.l[j] + (A.H[j] * a0.a[0] + A.H[3 + j] * a0.a[1] + A.H[6 + j] * a0.a[2]);
-#pragma unroll
-  for (int i = 0; i < 3; i++)
-    a0.l[i] = -((Cm[sidx(i, 0)] * u[0] + Cm[sidx(i, 1)] * u[1] + Cm[sidx(i, 2)] * u[2]) * rm);
+  for (int i = 0; i < 3; i++) {
+    float w = Cm[sidx(i, 0)] * pA.l[0] + Cm[sidx(i, 1)] * pA.l[1] + Cm[sidx(i, 2)] * pA.l[2];
+    w = fmaf(Yc[i], a0.a[0], fmaf(Yc[3 + i], a0.a[1], fmaf(Yc[6 + i], a0.a[2], w)));
+    a0.l[i] = -(w * rm);
+  }
 }
 
 // Base role, split in two so that the legs' acceleration pass overlaps the base integration:
