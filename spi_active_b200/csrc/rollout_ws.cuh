@@ -133,7 +133,10 @@ struct WsBars {
 // LEG is a warp-uniform run-time value (one code copy for the four legs: four template copies overflow the
 // instruction cache — profiles/README.md, experiment ws-templated); the leg's constants are then fetched through
 // the constant bank with a uniform offset.
-template <bool RECORD>
+// MOTOR >= 0: the motor model is a compile-time constant (2 * SPI_MOTOR_* + tanh-before-clip): the throughput kernel is
+// instantiated per model so that the per-physics-step torque block carries no dispatch (a chain of uniform compares / branches);
+// MOTOR < 0: run-time dispatch on A.motor_model / A.flags.
+template <bool RECORD, int MOTOR>
 __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, const WsBars bars, int lane, const int LEG,
                                             int c, int seg, bool active) {
   const SimK& S = A.M.sim;
@@ -199,7 +202,8 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, const W
     for (int d = 0; d < A.decimation; d++) {
       // PD law + clip + motor model, once per physics step (go2_ws.cuh: leg_torques_t)
       float tau[3];
-      leg_torques_dispatch(L, pdb, s.q, s.qd, kp, kd, motor, motor_k2, A.motor_model, A.flags, tau);
+      if constexpr (MOTOR >= 0) leg_torques_t<MOTOR / 2, (MOTOR & 1) != 0>(L, pdb, s.q, s.qd, kp, kd, motor, motor_k2, tau);
+      else leg_torques_dispatch(L, pdb, s.q, s.qd, kp, kd, motor, motor_k2, A.motor_model, A.flags, tau);
       for (int n = 0; n < S.nsub; n++) {
         float bc[kBaseOut];
         ws_load_state(sm, lane, bc);
@@ -380,7 +384,7 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, const 
 }
 
 // blockIdx = one group of 32 rollouts, warps 0..3 = legs, warp 4 = base.
-template <bool RECORD>
+template <bool RECORD, int MOTOR = -1>
 __device__ __forceinline__ void rollout_ws_body(const WsArgs& A) {
   __shared__ WsSmem sm;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -392,13 +396,13 @@ __device__ __forceinline__ void rollout_ws_body(const WsArgs& A) {
   const int seg = seg_raw < A.S ? seg_raw : A.S - 1;
   const int c = A.paired ? seg : cg;
   const WsBars bars{};
-  if (role < 4) ws_leg_role<RECORD>(A, sm, bars, lane, role, c, seg, active);
+  if (role < 4) ws_leg_role<RECORD, MOTOR>(A, sm, bars, lane, role, c, seg, active);
   else ws_base_role<RECORD>(A, sm, bars, lane, c, cta_in_cand, seg, active, true);
 }
 
-template <bool RECORD, int MINB>
+template <bool RECORD, int MINB, int MOTOR = -1>
 __global__ void __launch_bounds__(kWsThreads, MINB) rollout_ws_kernel(const __grid_constant__ WsArgs A) {
-  rollout_ws_body<RECORD>(A);
+  rollout_ws_body<RECORD, MOTOR>(A);
 }
 
 }  // namespace ws

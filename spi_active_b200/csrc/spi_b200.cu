@@ -758,7 +758,19 @@ int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C
     ws::rollout_ws_kernel<false, 2><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
   else if (minb == 3) ws::rollout_ws_kernel<false, 3><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
   else if (minb == 5) ws::rollout_ws_kernel<false, 5><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
-  else ws::rollout_ws_kernel<false, 4><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
+  else {
+    // the throughput kernel, one instance per motor model (rollout_ws.cuh: MOTOR = 2 * model + tanh-before-clip)
+    const int motor = 2 * motor_model + ((motor_model == SPI_MOTOR_VEC3_TANH && (flags & SPI_FLAG_TANH_BEFORE_CLIP)) ? 1 : 0);
+    const unsigned g = (unsigned)n_cta;
+    switch (motor) {
+      case 2 * SPI_MOTOR_NONE: ws::rollout_ws_kernel<false, 4, 2 * SPI_MOTOR_NONE><<<g, ws::kWsThreads, 0, st>>>(A); break;
+      case 2 * SPI_MOTOR_SCALAR: ws::rollout_ws_kernel<false, 4, 2 * SPI_MOTOR_SCALAR><<<g, ws::kWsThreads, 0, st>>>(A); break;
+      case 2 * SPI_MOTOR_VEC3: ws::rollout_ws_kernel<false, 4, 2 * SPI_MOTOR_VEC3><<<g, ws::kWsThreads, 0, st>>>(A); break;
+      case 2 * SPI_MOTOR_VEC3_TANH: ws::rollout_ws_kernel<false, 4, 2 * SPI_MOTOR_VEC3_TANH><<<g, ws::kWsThreads, 0, st>>>(A); break;
+      case 2 * SPI_MOTOR_VEC3_TANH + 1: ws::rollout_ws_kernel<false, 4, 2 * SPI_MOTOR_VEC3_TANH + 1><<<g, ws::kWsThreads, 0, st>>>(A); break;
+      default: ws::rollout_ws_kernel<false, 4><<<g, ws::kWsThreads, 0, st>>>(A); break;
+    }
+  }
   if (int rc = check_launch("rollout_ws_kernel")) return rc;
   if (m->timing) {
     CUDA_OK(cudaEventRecord(e1, st));
