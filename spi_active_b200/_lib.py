@@ -15,7 +15,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("SPI_B200_LIB", _PKG / "libspi_b200.so"))  # override: kernel experiments only
 SOURCES = [_PKG / "csrc" / "spi_b200.cu"]
 HEADERS = [_PKG / "csrc" / "aba_leg.cuh", _PKG / "csrc" / "go2_ws.cuh", _PKG / "csrc" / "rollout_ws.cuh",
-           _PKG / "csrc" / "fim_tc.cuh", _PKG / "csrc" / "active_step.cuh", _PKG / "csrc" / "mlp_tc.cuh", _PKG / "csrc" / "tiled_layout.cuh",
+           _PKG / "csrc" / "fim_tc.cuh", _PKG / "csrc" / "active_step.cuh", _PKG / "csrc" / "mlp_tc.cuh", _PKG / "csrc" / "tiled_layout.cuh", _PKG / "csrc" / "pdl.cuh",
            _PKG.parent / "include" / "spi_b200.h"]
 # SPI_WS_FAST_SINCOS: joint sin/cos through MUFU after a 2-constant reduction to [-pi, pi]; measured deviation from
 # the fp64 oracle stays at the fp32 noise floor of the oracle itself (profiles/README.md, tests/tools/dev_accuracy.py)

@@ -23,6 +23,7 @@
 #include <stdint.h>
 
 #include "tiled_layout.cuh"
+#include "pdl.cuh"
 
 namespace activestep {
 
@@ -95,6 +96,8 @@ inline size_t smem_bytes(int P1, bool ring = false) {
 // A step past the last scheduled row (an extra advance_rollout() / graph replay) re-reads the last row: stale inputs, but
 // never an index outside the command / FIM / observation rings.
 __global__ void tick_kernel(const int* schedule, int n_rows, int* counter, int* ctrl) {
+  pdl::trigger();
+  pdl::wait();
   const int c0 = counter[0];
   const int c = c0 < n_rows ? c0 : n_rows - 1;
   ctrl[0] = schedule[4 * c]; ctrl[1] = schedule[4 * c + 1]; ctrl[2] = schedule[4 * c + 2]; ctrl[3] = schedule[4 * c + 3];
@@ -103,6 +106,8 @@ __global__ void tick_kernel(const int* schedule, int n_rows, int* counter, int* 
 
 __global__ void __launch_bounds__(32 * kMaxGroup) active_post_step_kernel(const Args A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl::trigger();
+  pdl::wait();
   const bool ring = A.ring_slots > 0;
   struct View {
     float* base; int* flag; int stride;

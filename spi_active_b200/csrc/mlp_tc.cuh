@@ -30,6 +30,7 @@
 
 #include "fim_tc.cuh"   // smem_u32, mbarrier / tcgen05 helpers
 #include "tiled_layout.cuh"
+#include "pdl.cuh"
 
 namespace mlptc {
 
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
   const uint32_t pair_rank = PAIR ? cluster_ctarank() : 0u;         // 0 = leader: issues the MMAs of the pair
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * kTile, n0 = blockIdx.y * BN;
+  pdl::trigger();          // the next kernel of the chain may be scheduled; it waits for this grid where it first reads memory
   MLP_STAMP(0);
 
   float* bias_s = reinterpret_cast<float*>(tail + kTailBias);     // [BN] bias of this n-tile
@@ -277,6 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
   if (PAIR) cluster_sync();        // the peer's barriers and TMEM exist before anything is signalled / issued across the pair
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *tmem_slot;
+  pdl::wait();             // set-up (TMEM, barriers) overlapped the predecessor's tail; its activations / ring head are read below
   MLP_STAMP(1);
   const int n_blocks = L.Kp / kBK;
   const int n_groups = (n_blocks + kGroup - 1) / kGroup;
@@ -400,6 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const LayerArgs 
       mbar_arrive(smem_u32(accempty + (g & 1)));
     }
     MLP_STAMP(2);
+    pdl::trigger_late();     // main loop done: the next layer's CTAs may be placed (on other SMs) and set up while this one runs its epilogue
     // every MMA has retired (the last accfull arrived) and every copy has landed: the stages are free
     if (MODE == 0) {
       // ELU(acc / (s_a s_w) + b) x s_a -> fp16 hi / lo, written as the next layer's operand tiles (tiled_layout.cuh): 128

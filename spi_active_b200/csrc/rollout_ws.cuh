@@ -9,6 +9,7 @@
 // The kernel is bound by the latency of this round, not by issue bandwidth (tools/ws_timeline.py).
 #pragma once
 #include "go2_ws.cuh"
+#include "pdl.cuh"
 
 namespace ws {
 
@@ -402,6 +403,8 @@ __device__ __forceinline__ void rollout_ws_body(const WsArgs& A) {
 
 template <bool RECORD, int MINB, int MOTOR = -1>
 __global__ void __launch_bounds__(kWsThreads, MINB) rollout_ws_kernel(const __grid_constant__ WsArgs A) {
+  pdl::trigger();
+  pdl::wait();             // (no-ops unless launched with programmatic stream serialisation: spi_b200_env_step)
   rollout_ws_body<RECORD, MOTOR>(A);
 }
 

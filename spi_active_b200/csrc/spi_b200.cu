@@ -700,6 +700,11 @@ int kernel_choice() {
   static const int v = [] { const char* e = getenv("SPI_B200_KERNEL"); return (e && std::string(e) == "lane") ? 1 : 0; }();
   return v;
 }
+// SPI_B200_PDL=0 disables programmatic dependent launch of the closed-loop step's kernels (pdl.cuh); default on
+bool pdl_on() {
+  static const int v = [] { const char* e = getenv("SPI_B200_PDL"); return e ? atoi(e) : 1; }();
+  return v != 0;
+}
 int minb_choice() {
   static const int v = [] { const char* e = getenv("SPI_B200_MINB"); return e ? atoi(e) : 0; }();
   return v;
@@ -739,8 +744,9 @@ int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C
     // e.g. the 352 CTAs of a config-5 control step) the 4-CTAs-per-SM build keeps the step in a single wave
     static const int rec_minb = [] { const char* e = getenv("SPI_B200_RECORD_MINB"); return e ? atoi(e) : 0; }();
     const bool four = rec_minb ? (rec_minb == 4) : (n_cta > 2LL * m->sm_count);
-    if (four) ws::rollout_ws_kernel<true, 4><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
-    else ws::rollout_ws_kernel<true, 2><<<(unsigned)n_cta, ws::kWsThreads, 0, st>>>(A);
+    // (programmatic dependent launch: in the closed-loop step this kernel follows the actor's last layer on the same stream)
+    if (four) CUDA_OK(pdl::launch(pdl_on(), ws::rollout_ws_kernel<true, 4>, dim3((unsigned)n_cta), dim3(ws::kWsThreads), 0, st, A));
+    else CUDA_OK(pdl::launch(pdl_on(), ws::rollout_ws_kernel<true, 2>, dim3((unsigned)n_cta), dim3(ws::kWsThreads), 0, st, A));
     return check_launch("rollout_ws_kernel<record>");
   }
   if (int rc = ensure(&m->d_partial, &m->partial_cap, (size_t)C * A.n_cta_per_cand * 3)) return rc;
@@ -1099,9 +1105,10 @@ int spi_b200_active_post_step(spi_b200_model* m, float* state, const float* raw_
   A.grav_x = grav_x; A.grav_y = grav_y;
   for (int j = 0; j < 12; j++) A.q_default[j] = q_default[j];
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  activestep::tick_kernel<<<1, 1, 0, st>>>(schedule, schedule_rows, counter, ctrl);
+  CUDA_OK(pdl::launch(pdl_on(), activestep::tick_kernel, dim3(1), dim3(1), 0, st, schedule, schedule_rows, counter, ctrl));
   if (int rc = check_launch("tick_kernel")) return rc;
-  activestep::active_post_step_kernel<<<Mn, 32 * P1, activestep::smem_bytes(P1, ring_slots > 0), st>>>(A);
+  CUDA_OK(pdl::launch(pdl_on(), activestep::active_post_step_kernel, dim3(Mn), dim3(32 * P1),
+                      activestep::smem_bytes(P1, ring_slots > 0), st, A));
   return check_launch("active_post_step_kernel");
 }
 
@@ -1176,7 +1183,7 @@ static cudaError_t mlp_launch(int mode, int layer, mlptc::LayerArgs L, int m_til
   (void)layer;
 #endif
   if (mode == 1) {
-    mlptc::mlp_layer_kernel<1, 128><<<dim3(m_tiles, 1), mlptc::kThreads, mlptc::kSmemBytes, st>>>(L);
+    return pdl::launch(pdl_on(), mlptc::mlp_layer_kernel<1, 128>, dim3(m_tiles, 1), dim3(mlptc::kThreads), mlptc::kSmemBytes, st, L);
   } else if (pair && L.N % 256 == 0 && m_tiles % 2 == 0) {
     cudaLaunchConfig_t cfg;
     std::memset(&cfg, 0, sizeof(cfg));
@@ -1188,9 +1195,9 @@ static cudaError_t mlp_launch(int mode, int layer, mlptc::LayerArgs L, int m_til
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, mlptc::mlp_layer_kernel<0, 256, true>, L);
   } else if (wide && L.N % 256 == 0) {
-    mlptc::mlp_layer_kernel<0, 256><<<dim3(m_tiles, L.N / 256), mlptc::kThreads, mlptc::kSmemBytes, st>>>(L);
+    return pdl::launch(pdl_on(), mlptc::mlp_layer_kernel<0, 256>, dim3(m_tiles, L.N / 256), dim3(mlptc::kThreads), mlptc::kSmemBytes, st, L);
   } else {
-    mlptc::mlp_layer_kernel<0, 128><<<dim3(m_tiles, L.N / 128), mlptc::kThreads, mlptc::kSmemBytes, st>>>(L);
+    return pdl::launch(pdl_on(), mlptc::mlp_layer_kernel<0, 128>, dim3(m_tiles, L.N / 128), dim3(mlptc::kThreads), mlptc::kSmemBytes, st, L);
   }
   return cudaGetLastError();
 }
