@@ -528,7 +528,7 @@ def run_extras(eng, segs, cfg, S, rank, world, barrier, max_over_ranks):
     rng = np.random.default_rng(rank)
     r = np.asarray(act.COMMAND_RANGES)
     vals = rng.uniform(r[act.COMMAND_SAMPLING_IDXS, 0], r[act.COMMAND_SAMPLING_IDXS, 1], (M, 5, 3)).astype(np.float32)
-    cmds = torch.from_numpy(np.stack([act.expand_commands(act.commands_constant(v, 250)) for v in vals]))
+    cmds = torch.from_numpy(np.stack([act.expand_commands(act.commands_constant(v, 250)) for v in vals])).pin_memory()
     res = {}
 
     def rollout():
@@ -644,7 +644,7 @@ def run_active(args):
     rng = np.random.default_rng(rank)
     r = np.asarray(act.COMMAND_RANGES)
     vals = rng.uniform(r[act.COMMAND_SAMPLING_IDXS, 0], r[act.COMMAND_SAMPLING_IDXS, 1], (M, 5, 3)).astype(np.float32)
-    cmds = torch.from_numpy(np.stack([act.expand_commands(act.commands_constant(v, 250)) for v in vals]))
+    cmds = torch.from_numpy(np.stack([act.expand_commands(act.commands_constant(v, 250)) for v in vals])).pin_memory()
 
     def barrier():
         if world > 1:

@@ -460,17 +460,20 @@ class ActiveExploration:
         — what _advance_inputs computes step by step, uploaded once."""
         k, K = self.cfg.ksync_steps, (self.hist.shape[0] if self.hist is not None else 1)
         n_rows = n_calls + 4              # + the rows the graph warm-up / capture steps read past the end
-        rows = np.zeros((n_rows, 4), dtype=np.int32)
-        for i in range(n_rows):
-            idx = i + 1                                                  # step_idx after the increment
-            rows[i, 0] = min(idx, T - 1)
-            rows[i, 1] = int((k == 1) or (k > 1 and idx % k == 1))
-            rows[i, 2] = 0 if i == 0 else (i - 1) % K                    # call 0 is the reset step (dropped)
-            rows[i, 3] = (-i) % RING_SLOTS                               # observation ring: the head moves down one slot per step
-        if getattr(self, "schedule", None) is None or self.schedule.shape[0] < n_rows:
-            self.schedule = torch.zeros((n_rows, 4), dtype=torch.int32, device=self.device)
-            self._graph = None            # a captured step holds the old buffer's address
-        self.schedule[:n_rows].copy_(torch.from_numpy(rows))
+        key = (n_rows, T, k, K)
+        if getattr(self, "_schedule_key", None) != key:      # same rollout shape as last time: the rows are already on the device
+            i = np.arange(n_rows)
+            idx = i + 1                                                      # step_idx after the increment
+            rows = np.zeros((n_rows, 4), dtype=np.int32)
+            rows[:, 0] = np.minimum(idx, T - 1)
+            rows[:, 1] = 1 if k == 1 else ((idx % k == 1) if k > 1 else 0)
+            rows[:, 2] = np.where(i == 0, 0, (i - 1) % K)                    # call 0 is the reset step (dropped)
+            rows[:, 3] = (-i) % RING_SLOTS                                   # observation ring: the head moves down one slot per step
+            if getattr(self, "schedule", None) is None or self.schedule.shape[0] < n_rows:
+                self.schedule = torch.zeros((n_rows, 4), dtype=torch.int32, device=self.device)
+                self._graph = None        # a captured step holds the old buffer's address
+            self.schedule[:n_rows].copy_(torch.from_numpy(rows))
+            self._schedule_key = key
         self.counter.zero_()
 
     # ---- reset ---------------------------------------------------------------------------------------------------------------
@@ -488,14 +491,15 @@ class ActiveExploration:
         return s
 
     def reset_all(self, main_commands: torch.Tensor, total_steps: Optional[int] = None,
-                  initial_main_states: Optional[torch.Tensor] = None):
-        """active_sysid_openloop.py:116-131 + base_task.py:90-100: reset, then ONE env step with zero actions."""
+                  initial_main_states: Optional[torch.Tensor] = None, materialize: bool = True):
+        """active_sysid_openloop.py:116-131 + base_task.py:90-100: reset, then ONE env step with zero actions.
+        `materialize=False` skips the return value (in ring mode it costs a host sync and a rebuild of the 900-dim rows)."""
         c, N, P1 = self.cfg, self.num_envs, self.param_dim + 1
-        mc = main_commands.to(self.device, torch.float32)
-        if getattr(self, "main_commands", None) is None or self.main_commands.shape != mc.shape:
-            self.main_commands = torch.empty_like(mc, memory_format=torch.contiguous_format)
+        if getattr(self, "main_commands", None) is None or self.main_commands.shape != main_commands.shape:
+            self.main_commands = torch.empty(tuple(main_commands.shape), dtype=torch.float32, device=self.device)
             self._graph = None            # persistent buffer: a captured step reads the command rows from it
-        self.main_commands.copy_(mc)
+        # straight into the persistent buffer; asynchronous on this stream when the caller's tensor is pinned host memory
+        self.main_commands.copy_(main_commands, non_blocking=True)
         fused = self.step_impl == "fused"
         if not fused:
             self.expanded_main_commands = self.main_commands.repeat_interleave(P1, dim=0)
@@ -518,7 +522,7 @@ class ActiveExploration:
             self.gait_indices.copy_(g); self.clock.copy_(clk)
             self.step_idx += 1
             self._fused_step(self.zero_actions)
-            return self.materialize_observation()
+            return self.materialize_observation() if materialize else None
         self._advance_inputs()
         self._env_step(torch.zeros(N, 12, device=self.device))
         return self.obs
@@ -551,7 +555,7 @@ class ActiveExploration:
         """Reset + the reset step (+ capture of the step graph); returns the number of advance_rollout() calls of the rollout."""
         total_steps = int(total_steps or self.total_steps)
         assert commands.shape[0] == self.num_main_envs and commands.shape[2] == 14
-        self.reset_all(commands, total_steps, initial_main_states)
+        self.reset_all(commands, total_steps, initial_main_states, materialize=False)
         self.total_reward.zero_(); self.jtj.zero_()
         if self.fim_mode in ("tensor", "fused"):      # the reset step's record / contribution is dropped, like its reward (:545-548)
             self.trace_acc.zero_(); self.dead_steps.zero_()

@@ -16,7 +16,7 @@ ex = act.ActiveExploration(eng, act.PolicyMLP.random(eng.device, seed=0, gain=0.
 rng = np.random.default_rng(0)
 r = np.asarray(act.COMMAND_RANGES)
 vals = rng.uniform(r[act.COMMAND_SAMPLING_IDXS, 0], r[act.COMMAND_SAMPLING_IDXS, 1], (M, 5, 3)).astype(np.float32)
-cmds = torch.from_numpy(np.stack([act.expand_commands(act.commands_constant(v, 250)) for v in vals]))
+cmds = torch.from_numpy(np.stack([act.expand_commands(act.commands_constant(v, 250)) for v in vals])).pin_memory()
 for graph in (True, False):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     out = ex.evaluate_policy(cmds, total_steps=steps, use_cuda_graph=graph)
@@ -36,6 +36,22 @@ for n_pipe in (2, 3, 4, 6):
         torch.cuda.synchronize(); t0 = time.perf_counter()
         out = pipe.evaluate_policy(cmds, total_steps=steps, use_cuda_graph=True)
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    # is the host the limit?  time of the launch loop alone (advance_rollout calls return before the GPU is done)
+    for i, (sub, sl) in enumerate(zip(pipe.subs, pipe.slices)):
+        with torch.cuda.stream(pipe.streams[i]):
+            nst = sub.begin_rollout(cmds[sl], steps, True, act.ActiveExploration.initial_main_states(M, pipe.model, pipe.cfg)[sl])
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(nst):
+        for i, sub in enumerate(pipe.subs):
+            with torch.cuda.stream(pipe.streams[i]):
+                sub.advance_rollout()
+    t_host = time.perf_counter() - t0
+    torch.cuda.synchronize(); t_all = time.perf_counter() - t0
+    for i, sub in enumerate(pipe.subs):
+        with torch.cuda.stream(pipe.streams[i]):
+            sub.finish_rollout()
+    torch.cuda.synchronize()
+    print(f"   launch loop {t_host:.3f} s of {t_all:.3f} s")
     rew = out["total_reward"][::pipe.param_dim + 1]
     print(f"pipelines={n_pipe} graph=True M={M} envs={pipe.num_envs} steps={out['steps']}: {dt:.3f} s  -> "
           f"{pipe.num_envs * out['steps'] / dt:.3e} env-steps/s; reward mean {rew.mean():.4g} alive {(rew > 0).mean():.2f}")
