@@ -200,6 +200,34 @@ def test_terminated_groups_score_zero(blob, nominal_model):
     assert ex.step_reward[:2].abs().sum() == 0 and ex.step_reward[2] > 0
 
 
+@pytest.mark.parametrize("k,K", [(5, 1), (1, 1), (0, 1), (5, 64), (3, 7)])
+def test_step_schedule_rows_follow_the_per_step_definition(k, K):
+    """The step schedule uploaded once per rollout shape (active._build_schedule, vectorised and cached) holds, row by row, what
+    the host computes step by step in _advance_inputs: command row (clamped to the last one), k-sync flag
+    (active_sysid_openloop.py:247-252), the slot of the Fisher history ring and the head of the observation ring."""
+    from types import SimpleNamespace
+    ns = SimpleNamespace(cfg=SimpleNamespace(ksync_steps=k), hist=(torch.zeros(K, 1) if K > 1 else None),
+                         device=torch.device("cpu"), counter=torch.ones(1, dtype=torch.int32), _graph="captured")
+    n_calls, T = 57, 50
+    act.ActiveExploration._build_schedule(ns, n_calls, T)
+    rows = ns.schedule.numpy()
+    assert rows.shape == (n_calls + 4, 4) and int(ns.counter[0]) == 0 and ns._graph is None
+    for i in range(n_calls + 4):
+        idx = i + 1
+        want = (min(idx, T - 1), int((k == 1) or (k > 1 and idx % k == 1)), 0 if i == 0 else (i - 1) % K,
+                (-i) % act.RING_SLOTS)
+        assert tuple(int(v) for v in rows[i]) == want, (i, rows[i], want)
+    # the same shape again: nothing is rebuilt (a captured step keeps its buffer), only the step counter restarts
+    buf, ns._graph = ns.schedule, "captured"
+    ns.schedule[:, 0] = -7
+    ns.counter.fill_(9)
+    act.ActiveExploration._build_schedule(ns, n_calls, T)
+    assert ns.schedule is buf and ns._graph == "captured" and int(ns.counter[0]) == 0 and int(ns.schedule[0, 0]) == -7
+    # another command length: rebuilt in place (same buffer: it is large enough)
+    act.ActiveExploration._build_schedule(ns, n_calls, T - 10)
+    assert ns.schedule is buf and int(ns.schedule[n_calls - 1, 0]) == T - 11
+
+
 def test_command_samplers():
     c = act.commands_constant(np.array([[1.0, 2.0], [3.0, 4.0]]), 3)
     assert c.shape == (6, 2) and c[:3, 0].tolist() == [1, 1, 1] and c[3:, 1].tolist() == [4, 4, 4]
