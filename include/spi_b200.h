@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SPI_B200_VERSION 104 /* major*100 + minor */
+#define SPI_B200_VERSION 105 /* major*100 + minor */
 
 /* ------------------------------------------------------------------------------------------
  * Model blob layout (fp32[SPI_BLOB_SIZE]).  Built on the host from the URDF
@@ -331,8 +331,10 @@ int spi_b200_fp32_peak(int iters, float* out_tflops, float* out_ms, void* cuda_s
 
 /* Rollout-kernel selection for this handle: 0 = automatic (the warp-specialised Go2-family fast path when the
  * blob has that structure, else the generic leg-per-lane kernel), 1 = force the generic kernel, 2 = require the
- * fast path (error if the blob does not qualify).  Both are CUDA kernels; there is no CPU path.              */
-enum { SPI_KERNEL_AUTO = 0, SPI_KERNEL_LANE = 1, SPI_KERNEL_WS = 2 };
+ * fast path (error if the blob does not qualify), 3 = the fast path with every candidate's segments padded to whole
+ * 32-rollout CTAs (the default packs the (candidate, segment) space densely: S = 1730 -> 54.06 instead of 55 CTAs per
+ * candidate; the costs are bit-identical either way — kept for that comparison).  All are CUDA kernels; there is no CPU path. */
+enum { SPI_KERNEL_AUTO = 0, SPI_KERNEL_LANE = 1, SPI_KERNEL_WS = 2, SPI_KERNEL_WS_PADDED = 3 };
 int spi_b200_model_set_kernel(spi_b200_model* model, int kernel);
 
 /* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */

@@ -25,9 +25,12 @@ struct WsArgs {
   int S, H, decimation, motor_model; unsigned flags;
   int n_cta_per_cand;
   int C_grid;          // number of candidate rows of the grid (C; 1 in paired mode)
+  int flat;            // 1: rollout r = c S + seg of the flattened (candidate, segment) space sits in CTA r / 32, lane r % 32 — no
+                       // padding at the end of every candidate (S = 1730: 55 -> 54.06 CTAs per candidate, -1.7 % of the grid); a CTA
+                       // then holds rollouts of up to two candidates and leaves the sum over a candidate's segments to the reduce kernel
   int rotate_roles;
   int paired;          // 1: rollout r uses candidate row r AND segment r (one env per rollout; C == 1 for the grid)
-  float* partial;      // [C][n_cta_per_cand][3]
+  float* partial;      // [C][n_cta_per_cand][3]; flat: [C][S][3] masked per-segment errors
   float* per_seg;      // [C][S][3] or null
   int* bad;            // [C]
   float* out_states;   // [C][S][H][37] (RECORD)
@@ -371,6 +374,17 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, const 
     o[0] = err[0]; o[1] = err[1]; o[2] = err[2];
   }
   const bool counts = active && (A.seg_mask ? (A.seg_mask[seg] != 0) : true);
+  if (A.flat) {
+    // a candidate's segments straddle CTAs at an offset that depends on its index, so the sum over them is left to
+    // reduce_cost_flat_kernel, which applies the SAME association as the code below (butterfly over segments 32 w .. 32 w + 31, then
+    // w in order): the costs are bit-identical to the padded launch and independent of where a candidate sits in the batch
+    if (active) {
+      float* o = A.partial + ((size_t)c * A.S + seg) * 3;
+#pragma unroll
+      for (int i = 0; i < 3; i++) o[i] = counts ? err[i] : 0.f;
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 3; i++) {
     float v = counts ? err[i] : 0.f;
@@ -390,10 +404,18 @@ __device__ __forceinline__ void rollout_ws_body(const WsArgs& A) {
   __shared__ WsSmem sm;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int role = __shfl_sync(0xffffffffu, A.rotate_roles ? (warp + blockIdx.x) % kWsWarps : warp, 0);  // warp-uniform
-  const int cg = (int)(blockIdx.x / A.n_cta_per_cand);
+  int cg = (int)(blockIdx.x / A.n_cta_per_cand);
   const int cta_in_cand = (int)(blockIdx.x - (unsigned)cg * A.n_cta_per_cand);
-  const int seg_raw = cta_in_cand * kWsRollouts + lane;
-  const bool active = seg_raw < A.S;
+  int seg_raw = cta_in_cand * kWsRollouts + lane;
+  bool active = seg_raw < A.S;
+  if (A.flat) {            // (the host guarantees C S < 2^31)
+    const int total = A.C * A.S;
+    const int r_raw = (int)blockIdx.x * kWsRollouts + lane;
+    active = r_raw < total;
+    const int r = active ? r_raw : total - 1;
+    cg = r / A.S;
+    seg_raw = r - cg * A.S;
+  }
   const int seg = seg_raw < A.S ? seg_raw : A.S - 1;
   const int c = A.paired ? seg : cg;
   const WsBars bars{};

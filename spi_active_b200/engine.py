@@ -483,8 +483,9 @@ class RolloutEngine:
         return float(tf.value), float(ms.value)
 
     def set_kernel(self, kernel: str = "auto") -> None:
-        """'auto' | 'lane' (generic leg-per-lane kernel) | 'ws' (warp-specialised Go2-family fast path)."""
-        kid = {"auto": 0, "lane": 1, "ws": 2}[kernel]
+        """'auto' | 'lane' (generic leg-per-lane kernel) | 'ws' (warp-specialised Go2-family fast path) | 'ws-padded' (the fast
+        path with every candidate padded to whole CTAs instead of the dense packing: same bits, for comparison)."""
+        kid = {"auto": 0, "lane": 1, "ws": 2, "ws-padded": 3}[kernel]
         _lib.check(self.lib.spi_b200_model_set_kernel(self._handle, kid), "spi_b200_model_set_kernel")
         self.kernel = kernel
 

@@ -27,7 +27,7 @@ def _segs(config, H, device, steps=None):
 
 
 def test_library_loaded(engine):
-    assert engine.lib.spi_b200_version() == 104
+    assert engine.lib.spi_b200_version() == 105
 
 
 @pytest.mark.parametrize("config,H", [("stand", 5), ("sine", 5), ("jump", 3), ("all", 5)])
@@ -151,6 +151,39 @@ def test_mask_and_ragged_sizes(engine, oracle_lib, blob):
         cost = engine.evaluate_candidates(torch.from_numpy(params), ["mass"], segs).cpu().numpy()
         ref, _ = oracle_lib.eval_candidates(blob, params, [0], init[:n], act[:n], tgt[:n], gains[:n], m)
         np.testing.assert_allclose(cost, ref, rtol=5e-5, atol=2e-6)
+
+
+def test_dense_packing_is_bit_identical_to_the_padded_launch():
+    """The fast path packs the (candidate, segment) space densely into 32-rollout CTAs (a CTA may hold the end of one candidate
+    and the start of the next) and sums a candidate's segments in a separate kernel with the association of the padded launch:
+    costs, per-segment errors and status flags are bit-identical, for ragged S, masks with holes, many candidates, a NaN row."""
+    from spi_active_b200.dataset import SegmentBatch
+    from spi_active_b200.engine import RolloutEngine
+    from spi_active_b200 import cem
+    dense, padded = RolloutEngine(), RolloutEngine()
+    dense.set_kernel("ws"); padded.set_kernel("ws-padded")
+    S, ds = synth.dataset("all", 5)
+    init, act, tgt, gains, mask, denom = synth.pack_numpy(ds)
+    cfg = cem.default_full_config(dense.model)
+    rng = np.random.default_rng(11)
+    dev = dense.device
+    for n, C in ((1, 5), (7, 64), (33, 37), (100, 3), (245, 129), (S, 40)):
+        m = mask[:n].copy(); m[::5] = 0
+        if m.sum() == 0: m[0] = 1
+        segs = SegmentBatch(torch.from_numpy(init[:n]).to(dev), torch.from_numpy(act[:n]).to(dev),
+                            torch.from_numpy(tgt[:n]).to(dev), torch.from_numpy(gains[:n]).to(dev),
+                            torch.from_numpy(m).to(dev), 0.0)
+        params = (np.asarray(cfg.mean) + 0.3 * np.asarray(cfg.std) * rng.standard_normal((C, len(cfg.names)))).astype(np.float32)
+        if C > 4:
+            params[C // 2, 0] = np.nan
+        out = []
+        for eng in (dense, padded):
+            cost, per, status = eng.evaluate_candidates(torch.from_numpy(params), cfg.names, segs, motor_model=cfg.motor_model,
+                                                        return_per_seg=True, return_status=True)
+            out.append((cost.cpu().numpy(), per.cpu().numpy(), status.cpu().numpy()))
+        for a, b in zip(*out):
+            assert np.array_equal(a, b, equal_nan=True), (n, C)
+        assert out[0][2].sum() == (1 if C > 4 else 0)
 
 
 def test_nonfinite_candidate_flagged(engine):
