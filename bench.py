@@ -140,7 +140,8 @@ def ncu_executed_flops_per_rollout():
     p = ROOT / "profiles" / "ncu_rollout_summary.json"
     try:
         rec = json.loads(p.read_text())
-        return rec["executed_fp32_flop_per_launch"] / (rec["grid_size"] * 32.0 * 1730.0 / (55.0 * 32.0))
+        rollouts = rec.get("rollouts_per_launch") or rec["grid_size"] * 32.0 * 1730.0 / (55.0 * 32.0)   # (older captures: padded grid)
+        return rec["executed_fp32_flop_per_launch"] / rollouts
     except Exception:
         return None
 

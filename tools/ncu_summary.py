@@ -46,6 +46,8 @@ def main():
     ap.add_argument("--row", type=int, default=0, help="which captured launch of the report")
     ap.add_argument("--set-roofline-traffic", action="store_true",
                     help="also write profiles/ncu_rollout_summary.json (bench.py reads `traffic` from it)")
+    ap.add_argument("--rollouts", type=float, default=None,
+                    help="(candidate, segment) rollouts of the captured launch (C x S), written next to the traffic figure")
     a = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", a.report, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
@@ -96,11 +98,11 @@ def main():
     if a.set_roofline_traffic:
         (ROOT / "profiles" / "ncu_rollout_summary.json").write_text(json.dumps(
             {"source": dst.name, "kernel": out["kernel"], "grid_size": out.get("grid_size"),
-             "dram_bytes_per_launch": out["dram_bytes_per_launch"],
+             "dram_bytes_per_launch": out["dram_bytes_per_launch"], "rollouts_per_launch": a.rollouts,
              "executed_fp32_flop_per_launch": out.get("executed_fp32", {}).get("flop_per_launch"),
              "note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the rollout kernel at the grid "
-                     "size above (ncu --set full); the dataset and candidate rows are L2-resident, so DRAM traffic "
-                     "does not grow with the candidate count"}, indent=1) + "\n")
+                     "size above (ncu --set full); the dataset and candidate rows are L2-resident; since the dense packing "
+                     "the kernel also writes 12 bytes of per-segment errors per rollout for the reduce kernel"}, indent=1) + "\n")
     print(json.dumps(out, indent=1))
 
 
