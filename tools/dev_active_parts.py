@@ -43,12 +43,21 @@ def part_fn(sub, part):
                                      act.TERMINATION_GRAVITY, sub.model.q_default, obs_hi=sub.obs_hi, obs_lo=sub.obs_lo,
                                      ring_slots=act.RING_SLOTS, fim_jtj=sub.jtj, fim_trace=sub.trace_acc,
                                      fim_delta=float(c.delta_param))
+    n_small = 30 * 32      # 30 CTAs instead of 117: the same launch latency on a quarter of the SMs
+
+    def physics_small():
+        sub.backend.env_step(sub.state[:n_small], sub.raw_actions[:n_small], params=sub.params[:n_small], param_names=sub.param_names,
+                             motor_model=cfg.motor_model, flags=gm.FLAG_HIP_HALF, zero_action_mask=sub.done[:n_small])
+    if part == "actor+physics30":
+        return lambda: (actor(), physics_small())
+    if part == "physics30":
+        return physics_small
     return {"actor": actor, "physics": physics, "post": post, "all": sub._policy_step,
             "actor+physics": lambda: (actor(), physics()), "physics+post": lambda: (physics(), post())}[part]
 
 
 init = act.ActiveExploration.initial_main_states(M, pipe.model, pipe.cfg)
-for part in ("actor", "physics", "post", "actor+physics", "physics+post", "all"):
+for part in (sys.argv[3].split(",") if len(sys.argv) > 3 else ("actor", "physics", "post", "actor+physics", "physics+post", "all")):
     graphs = []
     for i, (sub, sl) in enumerate(zip(pipe.subs, pipe.slices)):
         with torch.cuda.stream(pipe.streams[i]):
