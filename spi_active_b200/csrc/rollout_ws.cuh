@@ -25,12 +25,13 @@ struct WsArgs {
   int S, H, decimation, motor_model; unsigned flags;
   int n_cta_per_cand;
   int C_grid;          // number of candidate rows of the grid (C; 1 in paired mode)
-  int flat;            // 1: rollout r = c S + seg of the flattened (candidate, segment) space sits in CTA r / 32, lane r % 32 — no
-                       // padding at the end of every candidate (S = 1730: 55 -> 54.06 CTAs per candidate, -1.7 % of the grid); a CTA
-                       // then holds rollouts of up to two candidates and leaves the sum over a candidate's segments to the reduce kernel
+  int tail_lanes;      // 0: every candidate owns ceil(S / 32) CTAs (the last one padded).  L' > 0 (dense packing): a candidate owns its
+                       // S / 32 full CTAs only; the S % 32 left-over segments of 32 / L' candidates share one TAIL CTA, each in its own
+                       // aligned group of L' lanes (L' = the power of two >= S % 32).  S = 1730: 2 left-over segments, 16 candidates
+                       // per tail CTA, 54.06 instead of 55 CTAs per candidate
   int rotate_roles;
   int paired;          // 1: rollout r uses candidate row r AND segment r (one env per rollout; C == 1 for the grid)
-  float* partial;      // [C][n_cta_per_cand][3]; flat: [C][S][3] masked per-segment errors
+  float* partial;      // [C][n_cta_per_cand][3]
   float* per_seg;      // [C][S][3] or null
   int* bad;            // [C]
   float* out_states;   // [C][S][H][37] (RECORD)
@@ -273,7 +274,7 @@ __device__ __forceinline__ void ws_leg_role(const WsArgs& A, WsSmem& sm, const W
 
 template <bool RECORD>
 __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, const WsBars bars, int lane, int c,
-                                             int cta_in_cand, int seg, bool active, bool group_live) {
+                                             int cta_in_cand, int seg, bool active, bool group_live, int tail_lp) {
   const SimK& S = A.M.sim;
   BaseInertia B;
   {
@@ -374,14 +375,19 @@ __device__ __forceinline__ void ws_base_role(const WsArgs& A, WsSmem& sm, const 
     o[0] = err[0]; o[1] = err[1]; o[2] = err[2];
   }
   const bool counts = active && (A.seg_mask ? (A.seg_mask[seg] != 0) : true);
-  if (A.flat) {
-    // a candidate's segments straddle CTAs at an offset that depends on its index, so the sum over them is left to
-    // reduce_cost_flat_kernel, which applies the SAME association as the code below (butterfly over segments 32 w .. 32 w + 31, then
-    // w in order): the costs are bit-identical to the padded launch and independent of where a candidate sits in the batch
-    if (active) {
-      float* o = A.partial + ((size_t)c * A.S + seg) * 3;
+  if (tail_lp > 0) {
+    // tail CTA: group j = lane / L' holds the left-over segments of one candidate.  The butterfly over the L' lanes of a group is the
+    // tail of the 32-lane butterfly the padded launch runs on the same values (its first steps only add the zeros of the idle
+    // lanes), so the partial sum has the same bits
 #pragma unroll
-      for (int i = 0; i < 3; i++) o[i] = counts ? err[i] : 0.f;
+    for (int i = 0; i < 3; i++) {
+      float v = counts ? err[i] : 0.f;
+      for (int o = tail_lp >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      err[i] = v;
+    }
+    if ((lane & (tail_lp - 1)) == 0 && group_live) {
+      float* o = A.partial + ((size_t)c * A.n_cta_per_cand + cta_in_cand) * 3;
+      o[0] = err[0]; o[1] = err[1]; o[2] = err[2];
     }
     return;
   }
@@ -405,22 +411,34 @@ __device__ __forceinline__ void rollout_ws_body(const WsArgs& A) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int role = __shfl_sync(0xffffffffu, A.rotate_roles ? (warp + blockIdx.x) % kWsWarps : warp, 0);  // warp-uniform
   int cg = (int)(blockIdx.x / A.n_cta_per_cand);
-  const int cta_in_cand = (int)(blockIdx.x - (unsigned)cg * A.n_cta_per_cand);
+  int cta_in_cand = (int)(blockIdx.x - (unsigned)cg * A.n_cta_per_cand);
   int seg_raw = cta_in_cand * kWsRollouts + lane;
-  bool active = seg_raw < A.S;
-  if (A.flat) {            // (the host guarantees C S < 2^31)
-    const int total = A.C * A.S;
-    const int r_raw = (int)blockIdx.x * kWsRollouts + lane;
-    active = r_raw < total;
-    const int r = active ? r_raw : total - 1;
-    cg = r / A.S;
-    seg_raw = r - cg * A.S;
+  bool active = seg_raw < A.S, group_live = true;
+  int tail_lp = 0;
+  if (A.tail_lanes) {                          // dense packing (WsArgs::tail_lanes)
+    const int n_full = A.S / kWsRollouts;
+    const unsigned first_tail = (unsigned)A.C * (unsigned)n_full;
+    if (blockIdx.x < first_tail) {             // one of the candidate's full CTAs
+      cg = (int)(blockIdx.x / (unsigned)n_full);
+      cta_in_cand = (int)(blockIdx.x - (unsigned)cg * (unsigned)n_full);
+      seg_raw = cta_in_cand * kWsRollouts + lane;
+      active = true;
+    } else {                                   // a tail CTA: 32 / L' candidates, L' lanes each
+      tail_lp = A.tail_lanes;
+      const int in_group = lane & (tail_lp - 1);
+      const int cand = (int)(blockIdx.x - first_tail) * (kWsRollouts / tail_lp) + lane / tail_lp;
+      group_live = cand < A.C;
+      cg = group_live ? cand : A.C - 1;
+      cta_in_cand = n_full;
+      seg_raw = n_full * kWsRollouts + in_group;
+      active = group_live && seg_raw < A.S;
+    }
   }
   const int seg = seg_raw < A.S ? seg_raw : A.S - 1;
   const int c = A.paired ? seg : cg;
   const WsBars bars{};
   if (role < 4) ws_leg_role<RECORD, MOTOR>(A, sm, bars, lane, role, c, seg, active);
-  else ws_base_role<RECORD>(A, sm, bars, lane, c, cta_in_cand, seg, active, true);
+  else ws_base_role<RECORD>(A, sm, bars, lane, c, cta_in_cand, seg, active, group_live, tail_lp);
 }
 
 template <bool RECORD, int MINB, int MOTOR = -1>

@@ -195,44 +195,6 @@ __global__ void reduce_cost_kernel(const float* partial, const int* bad, const u
   if (out_status && k == 0) out_status[c] = b;
 }
 
-// The same sums for the flat launch of the rollout kernel (rollout_ws.cuh: WsArgs::flat), which leaves the masked per-segment
-// errors err[C][S][3]: one warp per candidate, and exactly the association of the padded launch + reduce_cost_kernel — a butterfly
-// over the 32 segments of chunk w (what the rollout CTA w of the candidate does there), then the chunks in order.
-__global__ void reduce_cost_flat_kernel(const float* err, const int* bad, const unsigned char* seg_mask, int C, int S,
-                                        float cost_denominator, float* out_cost, int* out_status) {
-  const int lane = threadIdx.x & 31;
-  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (c >= C) return;
-  float denom = cost_denominator;
-  if (!(denom > 0.f)) {
-    int n = 0;
-    if (seg_mask) { for (int s = lane; s < S; s += 32) n += seg_mask[s] ? 1 : 0; } else n = (lane == 0) ? S : 0;
-    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-    denom = (float)n;
-  }
-  float sum[3] = {0.f, 0.f, 0.f};
-  const float* row = err + (size_t)c * S * 3;
-#pragma unroll 8
-  for (int s0 = 0; s0 < S; s0 += 32) {
-    const int s = s0 + lane;
-    float v[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) v[k] = (s < S) ? row[(size_t)s * 3 + k] : 0.f;
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-      sum[k] += v[k];
-    }
-  }
-  if (lane == 0) {
-    const int b = bad[c];
-#pragma unroll
-    for (int k = 0; k < 3; k++) out_cost[c * 3 + k] = b ? INFINITY : sum[k] / denom;
-    if (out_status) out_status[c] = b;
-  }
-}
-
 // BaseSimulator.simulate_at_each_physics_step for N envs (4 lanes per env), n_steps physics steps
 struct StepArgs {
   const DeviceModel* model;
@@ -769,12 +731,18 @@ int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C
   A.seg_mask = seg_mask; A.S = S; A.H = H; A.decimation = decimation; A.motor_model = motor_model; A.flags = flags;
   A.n_cta_per_cand = (S + ws::kWsRollouts - 1) / ws::kWsRollouts;
   A.paired = paired; A.zero_mask = zero_mask; A.C_grid = C;
-  // the throughput launch packs the (candidate, segment) space without the padding at the end of every candidate (WsArgs::flat)
-  static const int flat_env = [] { const char* e = getenv("SPI_B200_WS_FLAT"); return e ? atoi(e) : 1; }();
-  // (needs 12 bytes of scratch per rollout for the per-segment errors: capped at 1 GiB, beyond that the padded launch)
-  A.flat = (!record && !paired && flat_env && m->kernel != SPI_KERNEL_WS_PADDED && S % ws::kWsRollouts != 0 && (long long)C * S <= (1LL << 30) / 12) ? 1 : 0;
+  // the throughput launch packs the left-over segments (S % 32) of several candidates into shared tail CTAs (WsArgs::tail_lanes)
+  static const int dense_env = [] { const char* e = getenv("SPI_B200_WS_DENSE"); return e ? atoi(e) : 1; }();
+  const int n_full = S / ws::kWsRollouts, left = S - n_full * ws::kWsRollouts;
+  A.tail_lanes = 0;
+  if (!record && !paired && dense_env && m->kernel != SPI_KERNEL_WS_PADDED && left > 0) {
+    int lp = 1;
+    while (lp < left) lp <<= 1;
+    if (lp < ws::kWsRollouts) A.tail_lanes = lp;        // (left > 16: a tail CTA would hold one candidate — the padded launch)
+  }
   { static const int rot = getenv("SPI_B200_WS_ROT") ? atoi(getenv("SPI_B200_WS_ROT")) : 0; A.rotate_roles = rot; }
-  const long long n_cta = A.flat ? ((long long)C * S + ws::kWsRollouts - 1) / ws::kWsRollouts : (long long)C * A.n_cta_per_cand;
+  const int cand_per_tail = A.tail_lanes ? ws::kWsRollouts / A.tail_lanes : 1;
+  const long long n_cta = A.tail_lanes ? (long long)C * n_full + (C + cand_per_tail - 1) / cand_per_tail : (long long)C * A.n_cta_per_cand;
   if (n_cta > 2147483647LL) return fail(-3, "C * ceil(S/32) exceeds the grid limit");
 #if defined(SPI_WS_PROFILE)
   A.prof = g_ws_prof; A.prof_blk0 = g_ws_prof_blk0; A.prof_nblk = g_ws_prof_nblk;
@@ -791,7 +759,7 @@ int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C
     else CUDA_OK(pdl::launch(pdl_on(), ws::rollout_ws_kernel<true, 2>, dim3((unsigned)n_cta), dim3(ws::kWsThreads), 0, st, A));
     return check_launch("rollout_ws_kernel<record>");
   }
-  if (int rc = ensure(&m->d_partial, &m->partial_cap, A.flat ? (size_t)C * S * 3 : (size_t)C * A.n_cta_per_cand * 3)) return rc;
+  if (int rc = ensure(&m->d_partial, &m->partial_cap, (size_t)C * A.n_cta_per_cand * 3)) return rc;
   if (int rc = ensure(&m->d_bad, &m->bad_cap, (size_t)C)) return rc;
   CUDA_OK(cudaMemsetAsync(m->d_bad, 0, (size_t)C * sizeof(int), st));
   A.partial = m->d_partial; A.bad = m->d_bad; A.per_seg = out_per_seg;
@@ -825,11 +793,8 @@ int launch_rollout_ws(spi_b200_model* m, bool record, const float* params, int C
     m->ev_pending.push_back(e0); m->ev_pending.push_back(e1);
   }
   const int n = C * 3;
-  if (A.flat)
-    reduce_cost_flat_kernel<<<(C + 3) / 4, 128, 0, st>>>(m->d_partial, m->d_bad, seg_mask, C, S, cost_denominator, out_cost, out_status);
-  else
-    reduce_cost_kernel<<<(n + 127) / 128, 128, 0, st>>>(m->d_partial, m->d_bad, seg_mask, C, S, A.n_cta_per_cand,
-                                                        cost_denominator, out_cost, out_status);
+  reduce_cost_kernel<<<(n + 127) / 128, 128, 0, st>>>(m->d_partial, m->d_bad, seg_mask, C, S, A.n_cta_per_cand,
+                                                      cost_denominator, out_cost, out_status);
   return check_launch("reduce_cost_kernel");
 }
 

@@ -154,9 +154,11 @@ def test_mask_and_ragged_sizes(engine, oracle_lib, blob):
 
 
 def test_dense_packing_is_bit_identical_to_the_padded_launch():
-    """The fast path packs the (candidate, segment) space densely into 32-rollout CTAs (a CTA may hold the end of one candidate
-    and the start of the next) and sums a candidate's segments in a separate kernel with the association of the padded launch:
-    costs, per-segment errors and status flags are bit-identical, for ragged S, masks with holes, many candidates, a NaN row."""
+    """The fast path gives a candidate only its S // 32 full CTAs and packs the S % 32 left-over segments of several candidates
+    into shared tail CTAs (aligned groups of L' lanes, L' the power of two >= S % 32), whose partial sums use the tail of the padded
+    launch's butterfly: costs, per-segment errors and status flags are bit-identical to the padded launch, for ragged S (left-overs
+    of 1, 7, 4, 2 -> groups of 1, 8, 4, 2 lanes; S < 32: tail CTAs only; a left-over of 21: no packing), masks with holes, many candidates,
+    a NaN row."""
     from spi_active_b200.dataset import SegmentBatch
     from spi_active_b200.engine import RolloutEngine
     from spi_active_b200 import cem
@@ -167,7 +169,7 @@ def test_dense_packing_is_bit_identical_to_the_padded_launch():
     cfg = cem.default_full_config(dense.model)
     rng = np.random.default_rng(11)
     dev = dense.device
-    for n, C in ((1, 5), (7, 64), (33, 37), (100, 3), (245, 129), (S, 40)):
+    for n, C in ((1, 5), (7, 64), (33, 37), (100, 3), (245, 129), (S, 40), (66, 17)):
         m = mask[:n].copy(); m[::5] = 0
         if m.sum() == 0: m[0] = 1
         segs = SegmentBatch(torch.from_numpy(init[:n]).to(dev), torch.from_numpy(act[:n]).to(dev),
