@@ -332,8 +332,9 @@ int spi_b200_fp32_peak(int iters, float* out_tflops, float* out_ms, void* cuda_s
 /* Rollout-kernel selection for this handle: 0 = automatic (the warp-specialised Go2-family fast path when the
  * blob has that structure, else the generic leg-per-lane kernel), 1 = force the generic kernel, 2 = require the
  * fast path (error if the blob does not qualify), 3 = the fast path with every candidate's segments padded to whole
- * 32-rollout CTAs (the default packs the (candidate, segment) space densely: S = 1730 -> 54.06 instead of 55 CTAs per
- * candidate; the costs are bit-identical either way — kept for that comparison).  All are CUDA kernels; there is no CPU path. */
+ * 32-rollout CTAs (the default gives a candidate its S / 32 full CTAs and packs the left-over segments of several candidates
+ * into shared CTAs: S = 1730 -> 54.06 instead of 55 CTAs per candidate; the costs are bit-identical either way — kept for
+ * that comparison).  All are CUDA kernels; there is no CPU path. */
 enum { SPI_KERNEL_AUTO = 0, SPI_KERNEL_LANE = 1, SPI_KERNEL_WS = 2, SPI_KERNEL_WS_PADDED = 3 };
 int spi_b200_model_set_kernel(spi_b200_model* model, int kernel);
 

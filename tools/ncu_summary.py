@@ -101,8 +101,8 @@ def main():
              "dram_bytes_per_launch": out["dram_bytes_per_launch"], "rollouts_per_launch": a.rollouts,
              "executed_fp32_flop_per_launch": out.get("executed_fp32", {}).get("flop_per_launch"),
              "note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the rollout kernel at the grid "
-                     "size above (ncu --set full); the dataset and candidate rows are L2-resident; since the dense packing "
-                     "the kernel also writes 12 bytes of per-segment errors per rollout for the reduce kernel"}, indent=1) + "\n")
+                     "size above (ncu --set full); the dataset and candidate rows are L2-resident, so DRAM traffic hardly grows "
+                     "with the candidate count"}, indent=1) + "\n")
     print(json.dumps(out, indent=1))
 
 
