@@ -248,8 +248,10 @@ int spi_b200_fim_reward(spi_b200_model* model, const float* states, int M, int P
  *   fim_jtj [M,P,P] / fim_trace [M] (or NULL): FUSED Fisher accumulation — jtj[m] += live * J J^T of this step, trace[m] += its
  *   trace, J = (main - aux_p) / fim_delta in R^{P x 25} (active_sysid_openloop.py:402-426), from the rows the kernel already
  *   holds; the alternative to recording fim_hist / fim_live for spi_b200_fim_contract (pass those as NULL then);
- *   counter [1] / ctrl [4] device ints: ctrl <- schedule[counter++] on the device before the step; schedule has
- *   `schedule_rows` rows of 4 ints — a step past the last row re-reads the last row instead of running off the buffer;
+ *   counter [2] / ctrl [4] device ints: the step uses row schedule[counter[0]]; the last block of the kernel publishes that row
+ *   in ctrl (ctrl[3] = the ring head spi_b200_policy_forward_ring reads next) and advances counter[0]; counter[1] is the block
+ *   ticket of that hand-over and must be 0 at launch (it is 0 again afterwards).  schedule has `schedule_rows` rows of 4 ints —
+ *   a step past the last row re-reads the last row instead of running off the buffer;
  *   q_default [12] HOST.  1 <= P1 <= 17.                                                                          */
 int spi_b200_active_post_step(spi_b200_model* model, float* state, const float* raw_actions, unsigned char* done,
                               const float* main_commands, int T, float* commands, float* actions, float* gait,

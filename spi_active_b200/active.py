@@ -298,7 +298,7 @@ class ActiveExploration:
         self.step_impl = impl
         if impl == "fused":
             self.hist_index_i32 = self.hist_index.to(torch.int32).contiguous()
-            self.counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.counter = torch.zeros(2, dtype=torch.int32, device=self.device)   # step counter, block ticket of the post-step kernel
             self.ctrl = torch.zeros(4, dtype=torch.int32, device=self.device)
             self.zero_actions = z(N, 12)
             self.tc_policy = self.obs_hi = self.obs_lo = None

@@ -60,8 +60,13 @@ struct Args {
   float* fim_jtj;                  // [M,P,P] or null
   float* fim_trace;                // [M] or null
   float fim_inv_delta;
-  const int* ctrl;                 // device: [0] command row t, [1] k-sync flag, [2] FIM ring slot, [3] observation ring head
-                                   // (written by tick_kernel)
+  // The per-step host inputs come from a schedule uploaded once per rollout: this step uses row counter[0] (the last row once
+  // the counter runs past it).  The LAST block to finish (ticket counter[1]) publishes that row in ctrl — [0] command row t,
+  // [1] k-sync flag, [2] FIM ring slot, [3] observation ring head: what the actor's first layer reads next — and advances
+  // counter[0]: no separate one-thread kernel between the physics and this one
+  const int* schedule; int schedule_rows;
+  int* counter;                    // [2]: step counter, block ticket (0 between launches)
+  int* ctrl;                       // [4] out
   int M, P1, T;
   float dt, action_clip, clip_obs, grav_x, grav_y;
   float q_default[12];
@@ -90,20 +95,7 @@ inline size_t smem_bytes(int P1, bool ring = false) {
   return (size_t)P1 * ((ring ? kEnvSmemFloatsRing : kEnvSmemFloats) * sizeof(float) + sizeof(int));
 }
 
-// The per-step host inputs (command row, k-sync flag, FIM ring slot) come from a schedule uploaded once per rollout:
-// ctrl <- schedule[counter], counter += 1.  One thread; runs right before the post-step kernel of the same step, so a
-// captured step needs no host work between replays.
-// A step past the last scheduled row (an extra advance_rollout() / graph replay) re-reads the last row: stale inputs, but
-// never an index outside the command / FIM / observation rings.
-__global__ void tick_kernel(const int* schedule, int n_rows, int* counter, int* ctrl) {
-  pdl::trigger();
-  pdl::wait();
-  const int c0 = counter[0];
-  const int c = c0 < n_rows ? c0 : n_rows - 1;
-  ctrl[0] = schedule[4 * c]; ctrl[1] = schedule[4 * c + 1]; ctrl[2] = schedule[4 * c + 2]; ctrl[3] = schedule[4 * c + 3];
-  counter[0] = c0 < n_rows ? c0 + 1 : c0;
-}
-
+// (the per-step host inputs — command row, k-sync flag, FIM ring slot, ring head — come from a schedule uploaded once per rollout: Args)
 __global__ void __launch_bounds__(32 * kMaxGroup) active_post_step_kernel(const Args A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl::trigger();
@@ -121,7 +113,10 @@ __global__ void __launch_bounds__(32 * kMaxGroup) active_post_step_kernel(const 
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = blockIdx.x;
   const int env = m * A.P1 + w;
-  const int t_cmd = A.ctrl[0], do_sync = A.ctrl[1], slot = A.ctrl[2];
+  // (counter[0] only changes when the last block of this launch is done, i.e. after every block has read it)
+  const int c0 = A.counter[0];
+  const int* sched = A.schedule + 4 * (c0 < A.schedule_rows ? c0 : A.schedule_rows - 1);
+  const int t_cmd = sched[0], do_sync = sched[1], slot = sched[2], ring_head = sched[3];
 
   // ---- state row, termination ------------------------------------------------------------------------------------
   float* srow = A.state + (size_t)env * kState;
@@ -209,7 +204,7 @@ __global__ void __launch_bounds__(32 * kMaxGroup) active_post_step_kernel(const 
   if (ring) {
     // ---- ring mode: the clipped frame, split, into slot ctrl[3] of the actor's input operand -------------------------------
     __syncwarp();
-    const int k0 = A.ctrl[3] * kFrame;
+    const int k0 = ring_head * kFrame;
     for (int i = lane; i < kFrame; i += 32) {
       const float o = fminf(fmaxf(sm.frame(w)[i], -A.clip_obs), A.clip_obs) * A.obs_scale;
       const __half h = __float2half_rn(o);
@@ -254,6 +249,18 @@ __global__ void __launch_bounds__(32 * kMaxGroup) active_post_step_kernel(const 
       if (r < dur) warped = r * (0.5f / dur);
       if (r > dur) warped = 0.5f + (r - dur) * (0.5f / (1.0f - dur));
       A.clock[(size_t)env * 4 + f] = sinf(6.2831855f * warped);
+    }
+  }
+
+  // ---- the last block publishes the step's schedule row and advances the counter ------------------------------------------------
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int ticket = atomicAdd(A.counter + 1, 1);
+    if (ticket == (int)gridDim.x - 1) {
+      A.ctrl[0] = t_cmd; A.ctrl[1] = do_sync; A.ctrl[2] = slot; A.ctrl[3] = ring_head;
+      A.counter[0] = c0 < A.schedule_rows ? c0 + 1 : c0;
+      A.counter[1] = 0;
     }
   }
 }

@@ -1,5 +1,5 @@
 // pdl.cuh — programmatic dependent launch (sm_90+): the kernels of one control step of the closed-loop rollout form a chain on
-// one stream (actor layers -> physics -> tick -> post-step -> next step's actor ...), each a few microseconds long, so the gaps
+// one stream (actor layers -> physics -> post-step -> next step's actor ...), each a few microseconds long, so the gaps
 // between them are a visible share of the step.  Launched with cudaLaunchAttributeProgrammaticStreamSerialization a kernel may
 // be scheduled as soon as every CTA of its predecessor has started (pdl_trigger) and runs its prologue while the predecessor
 // drains; pdl_wait() blocks until the predecessor grid has COMPLETED and its writes are visible, so placing it in front of the

@@ -1110,13 +1110,12 @@ int spi_b200_active_post_step(spi_b200_model* m, float* state, const float* raw_
   A.obs_hi = static_cast<__half*>(obs_hi); A.obs_lo = static_cast<__half*>(obs_lo); A.obs_stride = obs_stride;
   A.obs_scale = mlptc::kActScale; A.ring_slots = ring_slots;
   A.fim_hist = fim_hist; A.fim_live = fim_live; A.dead_steps = dead_steps; A.ctrl = ctrl;
+  A.schedule = schedule; A.schedule_rows = schedule_rows; A.counter = counter;
   A.fim_jtj = fim_jtj; A.fim_trace = fim_trace; A.fim_inv_delta = fim_delta != 0.f ? 1.0f / fim_delta : 0.f;
   A.M = Mn; A.P1 = P1; A.T = T; A.dt = dt; A.action_clip = action_clip; A.clip_obs = clip_obs;
   A.grav_x = grav_x; A.grav_y = grav_y;
   for (int j = 0; j < 12; j++) A.q_default[j] = q_default[j];
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  CUDA_OK(pdl::launch(pdl_on(), activestep::tick_kernel, dim3(1), dim3(1), 0, st, schedule, schedule_rows, counter, ctrl));
-  if (int rc = check_launch("tick_kernel")) return rc;
   CUDA_OK(pdl::launch(pdl_on(), activestep::active_post_step_kernel, dim3(Mn), dim3(32 * P1),
                       activestep::smem_bytes(P1, ring_slots > 0), st, A));
   return check_launch("active_post_step_kernel");
